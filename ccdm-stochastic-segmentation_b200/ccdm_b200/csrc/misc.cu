@@ -1,0 +1,181 @@
+// Small kernels around the reverse step: the timestep-embedding table, layout
+// converters at the chain boundary, label <-> one-hot conversion.
+#include "common.cuh"
+
+namespace ccdm {
+namespace {
+
+// One CTA per table row (= one timestep).  Replaces nn.py:103-121
+// (timestep_embedding), unet.py:506-510,758 (time_embed MLP) and, for every
+// ResBlock, emb_layers = SiLU -> Linear (unet.py:205-211,251).  The embedding
+// depends only on (t, weights), so the whole [rows, sum(Cout)] table is built
+// once per chain instead of 3 + n_resblocks tiny GEMMs per step.
+__global__ void __launch_bounds__(256) time_table_kernel(const float *__restrict__ t, int mc, const float *__restrict__ w0,
+                                                         const float *__restrict__ b0, const float *__restrict__ w2,
+                                                         const float *__restrict__ b2, const float *__restrict__ w_all,
+                                                         const float *__restrict__ b_all, int cols, float *__restrict__ out) {
+    extern __shared__ float sm[];
+    const int ed = 4 * mc;
+    float *e0 = sm;            // [mc]   sinusoid
+    float *h1 = e0 + mc;       // [ed]   silu(time_embed.0)
+    float *e2 = h1 + ed;       // [ed]   silu(time_embed.2) == silu(emb)
+    const int r = blockIdx.x;
+    const float tv = t[r];
+    const int half = mc / 2;
+    for (int i = threadIdx.x; i < mc; i += blockDim.x) {
+        float v = 0.f;
+        if (i < 2 * half) {
+            int k = i < half ? i : i - half;
+            // freqs = exp(-ln(10000) * k / half) in fp32 (nn.py:113-116)
+            float f = expf(-9.210340371976184f * float(k) / float(half));
+            float a = tv * f;
+            v = i < half ? cosf(a) : sinf(a);
+        }
+        e0[i] = v;
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < ed; o += blockDim.x) {
+        float s = b0[o];
+        for (int i = 0; i < mc; ++i) s += w0[o * mc + i] * e0[i];
+        h1[o] = silu_exact(s);
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < ed; o += blockDim.x) {
+        float s = b2[o];
+        for (int i = 0; i < ed; ++i) s += w2[o * ed + i] * h1[i];
+        e2[o] = silu_exact(s);
+    }
+    __syncthreads();
+    // one warp per output column: coalesced reads of the weight row
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    for (int o = warp; o < cols; o += nwarp) {
+        float s = 0.f;
+        for (int i = lane; i < ed; i += 32) s += w_all[size_t(o) * ed + i] * e2[i];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        if (lane == 0) out[size_t(r) * cols + o] = s + b_all[o];
+    }
+}
+
+__global__ void onehot_to_labels_kernel(const float *__restrict__ x, int64_t sb, int64_t sk, int64_t sh, int64_t sw, int B, int K,
+                                        int H, int W, uint8_t *__restrict__ labels) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t n = size_t(B) * H * W;
+    if (i >= n) return;
+    const int w = int(i % W), h = int((i / W) % H), b = int(i / (size_t(W) * H));
+    const float *p = x + b * sb + h * sh + w * sw;
+    int best = 0;
+    float bv = p[0];
+    for (int k = 1; k < K; ++k) {
+        float v = p[k * sk];
+        if (v > bv) {
+            bv = v;
+            best = k;
+        }
+    }
+    labels[i] = uint8_t(best);
+}
+
+__global__ void labels_to_onehot_i64_kernel(const uint8_t *__restrict__ labels, size_t n_pix, int K, long long *__restrict__ out) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n_pix * K) return;
+    const size_t p = i / K;
+    const int k = int(i - p * K);
+    out[i] = labels[p] == k ? 1ll : 0ll;
+}
+
+// NCHW fp32 -> NHWC T, one CTA per (32-pixel strip, sample); per-channel sums are
+// accumulated in double with one atomicAdd per (CTA, channel): this runs once per
+// chain on the feature condition, so its cost and (tiny) order non-determinism in
+// the 17th digit of a double do not matter; the sums are rounded through the same
+// double -> float path every step.
+template <typename T>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_stats_kernel(const float *__restrict__ src, int C, int HW, T *__restrict__ dst,
+                                                                 double *__restrict__ stat) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int j = ty; j < 32; j += 8) {
+        int c = c0 + j, p = p0 + tx;
+        tile[j][tx] = (c < C && p < HW) ? src[(size_t(b) * C + c) * HW + p] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        int p = p0 + j, c = c0 + tx;
+        if (p < HW && c < C) {
+            float v = tile[tx][j];
+            if (sizeof(T) == 2) {
+                __nv_bfloat16 h = __float2bfloat16_rn(v);
+                reinterpret_cast<__nv_bfloat16 *>(dst)[(size_t(b) * HW + p) * C + c] = h;
+                tile[tx][j] = __bfloat162float(h);
+            } else {
+                reinterpret_cast<float *>(dst)[(size_t(b) * HW + p) * C + c] = v;
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int c = c0 + threadIdx.x;
+        if (c < C) {
+            double s = 0.0, q = 0.0;
+            for (int j = 0; j < 32; ++j)
+                if (p0 + j < HW) {
+                    double v = tile[threadIdx.x][j];
+                    s += v;
+                    q += v * v;
+                }
+            atomicAdd(stat + (size_t(b) * C + c) * 2, s);
+            atomicAdd(stat + (size_t(b) * C + c) * 2 + 1, q);
+        }
+    }
+}
+
+}  // namespace
+}  // namespace ccdm
+
+using namespace ccdm;
+
+extern "C" int ccdm_time_table(const float *t, int rows, int model_channels, const float *te0_w, const float *te0_b,
+                               const float *te2_w, const float *te2_b, const float *w_all, const float *b_all, int cols,
+                               float *out, void *stream) {
+    if (rows <= 0 || cols <= 0) return 0;
+    if (model_channels <= 0 || model_channels > 1024) CCDM_FAIL(-2, "time_table: model_channels=%d", model_channels);
+    size_t smem = sizeof(float) * size_t(model_channels) * 9;
+    time_table_kernel<<<rows, 256, smem, (cudaStream_t)stream>>>(t, model_channels, te0_w, te0_b, te2_w, te2_b, w_all, b_all, cols, out);
+    CCDM_LAUNCH_CHECK("time_table_kernel");
+    return 0;
+}
+
+extern "C" int ccdm_onehot_to_labels(const float *x, int64_t sb, int64_t sk, int64_t sh, int64_t sw, int B, int K, int H, int W,
+                                     uint8_t *labels, void *stream) {
+    const size_t n = size_t(B) * H * W;
+    if (n == 0) return 0;
+    if (K < 1 || K > 255) CCDM_FAIL(-2, "onehot_to_labels: K=%d", K);
+    onehot_to_labels_kernel<<<unsigned((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, sb, sk, sh, sw, B, K, H, W, labels);
+    CCDM_LAUNCH_CHECK("onehot_to_labels_kernel");
+    return 0;
+}
+
+extern "C" int ccdm_labels_to_onehot_i64(const uint8_t *labels, size_t n_pix, int K, int64_t *out, void *stream) {
+    const size_t n = n_pix * size_t(K);
+    if (n == 0) return 0;
+    labels_to_onehot_i64_kernel<<<unsigned((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(labels, n_pix, K, (long long *)out);
+    CCDM_LAUNCH_CHECK("labels_to_onehot_i64_kernel");
+    return 0;
+}
+
+extern "C" int ccdm_nchw_to_nhwc_stats(const float *src, int B, int C, int H, int W, int dtype, void *dst, double *stat,
+                                       void *stream) {
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    CCDM_CUDA(cudaMemsetAsync(stat, 0, sizeof(double) * 2 * size_t(B) * C, s));
+    const int HW = H * W;
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, B);
+    if (dtype == CCDM_DT_BF16)
+        nchw_to_nhwc_stats_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(src, C, HW, (__nv_bfloat16 *)dst, stat);
+    else
+        nchw_to_nhwc_stats_kernel<float><<<grid, 256, 0, s>>>(src, C, HW, (float *)dst, stat);
+    CCDM_LAUNCH_CHECK("nchw_to_nhwc_stats_kernel");
+    return 0;
+}

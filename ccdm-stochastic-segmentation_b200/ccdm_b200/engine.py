@@ -1,0 +1,634 @@
+"""Host side of the CUDA engine: compiles a ``UNetArch`` into a launch program and runs chains.
+
+What lives here (all host logic; every FLOP is in ``libccdm_b200.so``):
+
+* ``pack_weights``  -- repack the reference-layout parameters (OIHW fp32, checkpoint key
+  names) into kernel layouts (``[tap][Cin][Cout]``, fused biases, the concatenated
+  timestep-embedding projection) inside ONE device buffer whose addresses never change,
+  re-done lazily whenever a parameter is modified (``load_state_dict`` / ``.to()`` /
+  in-place EMA writes, SURVEY.md 8b "staleness hazard").
+* ``Program``       -- the op list of one reverse step for a fixed (B, H, W): every
+  activation gets an offset in a liveness-planned workspace; the op structs carry
+  absolute device addresses so the C side can capture them into a CUDA graph once.
+* ``UNetEngine``    -- caches programs, runs ``single_step`` (reference
+  ``UNetModel.forward``, unet.py:744-808) and ``run_chain`` (reference
+  ``DenoisingModel.forward_denoising``, diffusion_denoising.py:164-215).
+
+torch is used for device memory, streams and the global generator (noise parity
+with the reference) only.
+"""
+import ctypes
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import Op, StepEntry
+
+ALIGN = 256
+
+
+def _ceil(a, b):
+    return (a + b - 1) // b * b
+
+
+# --------------------------------------------------------------------------------------
+# workspace planning
+# --------------------------------------------------------------------------------------
+@dataclass
+class Ten:
+    name: str
+    C: int
+    H: int
+    W: int
+    esize: int            # bytes per element
+    want_stat: bool
+    nbytes: int = 0
+    off: int = -1         # byte offset in the activation arena
+    stat_off: int = -1    # byte offset in the stat arena
+    born: int = -1
+    last: int = -1
+    external: bool = False  # lives outside the arena (feature condition)
+    addr: int = 0
+    stat_addr: int = 0
+
+
+class Arena:
+    """First-fit allocator over op-index lifetimes (tensors die after their last reader)."""
+
+    def __init__(self):
+        self.live = []  # (off, nbytes, ten)
+        self.size = 0
+
+    def alloc(self, t: Ten):
+        self.live.sort(key=lambda x: x[0])
+        pos = 0
+        for off, nb, _ in self.live:
+            if off - pos >= t.nbytes:
+                break
+            pos = max(pos, off + nb)
+        t.off = pos
+        self.live.append((pos, t.nbytes, t))
+        self.size = max(self.size, pos + t.nbytes)
+
+    def release_dead(self, op_index: int):
+        self.live = [x for x in self.live if x[2].last > op_index]
+
+
+# --------------------------------------------------------------------------------------
+# weights
+# --------------------------------------------------------------------------------------
+class PackedWeights:
+    """All kernel-layout parameters in one flat fp32 device buffer with stable addresses."""
+
+    def __init__(self, unet, device):
+        self.unet = unet
+        self.device = device
+        self.slots: Dict[str, tuple] = {}  # name -> (offset_floats, numel)
+        self.total = 0
+        self.buf: Optional[torch.Tensor] = None
+        self._stamp = None
+        self._layout()
+
+    def _reserve(self, name, numel):
+        self.slots[name] = (self.total, numel)
+        self.total += _ceil(numel, ALIGN // 4)
+
+    def _layout(self):
+        arch = self.unet.arch
+        mc = self.unet.model_channels
+        ed = 4 * mc
+        for k, n in (("te0_w", ed * mc), ("te0_b", ed), ("te2_w", ed * ed), ("te2_b", ed)):
+            self._reserve(k, n)
+        self._reserve("emb_w", arch.emb_cols * ed)
+        self._reserve("emb_b", arch.emb_cols)
+        for blk in arch.blocks:
+            for L in blk.layers:
+                p = L.path
+                if L.kind == "conv_in":
+                    self._reserve(p + ":w", 9 * _ceil(L.cin, 8) * _ceil(L.cout, 32))
+                    self._reserve(p + ":b", _ceil(L.cout, 32))
+                elif L.kind in ("down", "up"):
+                    self._reserve(p + ":w", 9 * L.cin * _ceil(L.cout, 32))
+                    self._reserve(p + ":b", _ceil(L.cout, 32))
+                elif L.kind == "res":
+                    self._reserve(p + ":g1", L.cin); self._reserve(p + ":be1", L.cin)
+                    self._reserve(p + ":w1", 9 * L.cin * L.cout); self._reserve(p + ":b1", L.cout)
+                    self._reserve(p + ":g2", L.cout); self._reserve(p + ":be2", L.cout)
+                    self._reserve(p + ":w2", 9 * L.cout * L.cout); self._reserve(p + ":b2", L.cout)
+                    if L.skip_conv:
+                        self._reserve(p + ":ws", L.cin * L.cout)
+                elif L.kind == "attn":
+                    self._reserve(p + ":g", L.cin); self._reserve(p + ":be", L.cin)
+                    self._reserve(p + ":wqkv", L.cin * 3 * L.cin); self._reserve(p + ":bqkv", 3 * L.cin)
+                    self._reserve(p + ":wproj", L.cin * L.cin); self._reserve(p + ":bproj", L.cin)
+        K = self.unet.out_channels
+        c_head = int(self.unet.channel_mult[0] * mc)
+        self._reserve("out:g", c_head); self._reserve("out:be", c_head)
+        self._reserve("out:w", 9 * c_head * _ceil(K, 32)); self._reserve("out:b", _ceil(K, 32))
+
+    def addr(self, name) -> int:
+        return self.buf.data_ptr() + 4 * self.slots[name][0]
+
+    def view(self, name) -> torch.Tensor:
+        off, n = self.slots[name]
+        return self.buf[off:off + n]
+
+    def _current_stamp(self):
+        return tuple((p.data_ptr(), p._version) for p in self.unet.parameters())
+
+    def refresh(self) -> bool:
+        """(Re)pack if any parameter changed since the last call.  Returns True if repacked."""
+        stamp = self._current_stamp()
+        if self.buf is not None and stamp == self._stamp:
+            return False
+        if self.buf is None:
+            self.buf = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+        sd = {k: v.detach().to(device=self.device, dtype=torch.float32) for k, v in self.unet.state_dict().items()}
+
+        def put(name, t):
+            v = self.view(name)
+            v.zero_()
+            v[:t.numel()].copy_(t.reshape(-1))
+
+        def conv_w(w, cin_pad=None):  # OIHW -> [tap][CinP][CoutP]
+            co, ci, kh, kw = w.shape
+            cip = cin_pad or ci
+            cop = _ceil(co, 32)
+            out = torch.zeros(kh * kw, cip, cop, dtype=torch.float32, device=self.device)
+            out[:, :ci, :co] = w.permute(2, 3, 1, 0).reshape(kh * kw, ci, co)
+            return out
+
+        def padded(b):
+            out = torch.zeros(_ceil(b.numel(), 32), dtype=torch.float32, device=self.device)
+            out[:b.numel()] = b
+            return out
+
+        put("te0_w", sd["time_embed.0.weight"]); put("te0_b", sd["time_embed.0.bias"])
+        put("te2_w", sd["time_embed.2.weight"]); put("te2_b", sd["time_embed.2.bias"])
+        emb_w, emb_b = [], []
+        for blk in self.unet.arch.blocks:
+            for L in blk.layers:
+                p = L.path
+                if L.kind == "conv_in":
+                    put(p + ":w", conv_w(sd[p + ".weight"], _ceil(L.cin, 8))); put(p + ":b", padded(sd[p + ".bias"]))
+                elif L.kind in ("down", "up"):
+                    put(p + ":w", conv_w(sd[p + ".weight"])); put(p + ":b", padded(sd[p + ".bias"]))
+                elif L.kind == "res":
+                    put(p + ":g1", sd[p + ".in_layers.0.weight"]); put(p + ":be1", sd[p + ".in_layers.0.bias"])
+                    put(p + ":w1", conv_w(sd[p + ".in_layers.2.weight"])); put(p + ":b1", sd[p + ".in_layers.2.bias"])
+                    put(p + ":g2", sd[p + ".out_layers.0.weight"]); put(p + ":be2", sd[p + ".out_layers.0.bias"])
+                    put(p + ":w2", conv_w(sd[p + ".out_layers.3.weight"]))
+                    b2 = sd[p + ".out_layers.3.bias"]
+                    if L.skip_conv:
+                        ws = sd[p + ".skip_connection.weight"]  # [Cout, Cin, 1, 1] -> [Cin][Cout]
+                        put(p + ":ws", ws[:, :, 0, 0].t().contiguous())
+                        b2 = b2 + sd[p + ".skip_connection.bias"]
+                    put(p + ":b2", b2)
+                    emb_w.append(sd[p + ".emb_layers.1.weight"]); emb_b.append(sd[p + ".emb_layers.1.bias"])
+                elif L.kind == "attn":
+                    put(p + ":g", sd[p + ".norm.weight"]); put(p + ":be", sd[p + ".norm.bias"])
+                    put(p + ":wqkv", sd[p + ".qkv.weight"][:, :, 0].t().contiguous()); put(p + ":bqkv", sd[p + ".qkv.bias"])
+                    put(p + ":wproj", sd[p + ".proj_out.weight"][:, :, 0].t().contiguous()); put(p + ":bproj", sd[p + ".proj_out.bias"])
+        put("emb_w", torch.cat(emb_w, 0)); put("emb_b", torch.cat(emb_b, 0))
+        put("out:g", sd["out.0.weight"]); put("out:be", sd["out.0.bias"])
+        put("out:w", conv_w(sd["out.2.weight"])); put("out:b", padded(sd["out.2.bias"]))
+        self._stamp = stamp
+        return True
+
+
+# --------------------------------------------------------------------------------------
+# program
+# --------------------------------------------------------------------------------------
+class Program:
+    """One reverse step for fixed (B, H, W): op list + workspace, bound to device addresses."""
+
+    def __init__(self, engine: "UNetEngine", B: int, H: int, W: int, rows_per_sample: int):
+        unet, arch = engine.unet, engine.unet.arch
+        self.engine = engine
+        self.B, self.H, self.W = B, H, W
+        self.K = unet.out_channels
+        self.C_img = unet.in_channels - self.K
+        self.esize = 4 if engine.precision == "fp32" else 2
+        self.dt = _lib.DT_F32 if engine.precision == "fp32" else _lib.DT_BF16
+        self.exact = 1 if engine.precision == "fp32" else 0
+        dev = engine.device
+        L = _lib.lib()
+
+        ops: List[dict] = []      # op field dicts with Ten references, resolved after allocation
+        tens: List[Ten] = []
+
+        def new(name, C, h, w, stat=True, esize=None):
+            t = Ten(name, C, h, w, esize or self.esize, stat)
+            t.nbytes = _ceil(B * h * w * C * t.esize, ALIGN)
+            tens.append(t)
+            return t
+
+        def emit(kind, ins, out, **f):
+            i = len(ops)
+            for t in ins:
+                if t is not None:
+                    t.last = max(t.last, i)
+            if out is not None:
+                out.born = i
+                out.last = max(out.last, i)
+            f.update(kind=kind, _ins=ins, _out=out)
+            ops.append(f)
+            return out
+
+        self.feat: Optional[Ten] = None
+        fc = unet.feat_channels
+        if fc:
+            self.feat = Ten("feature_condition", fc, H // 8, W // 8, self.esize, True, external=True)
+
+        hs: List[Ten] = []
+        h: Optional[Ten] = None
+        ch, cw = H, W
+        for blk in arch.blocks:
+            srcs: List[Ten] = [h] if h is not None else []
+            if blk.feat_concat:
+                if self.feat is None or (self.feat.H, self.feat.W) != (ch, cw):
+                    raise ValueError("feature condition resolution does not match its target layer")
+                srcs = [h, self.feat]
+            if blk.stage == "out":
+                srcs = [h, hs.pop()]
+            for Ly in blk.layers:
+                p = Ly.path
+                if Ly.kind == "conv_in":
+                    h = emit(_lib.OP_INPUT_CONV, [], new(p, Ly.cout, ch, cw), src_kind=1, ksize=3, stride=1, Hin=ch, Win=cw,
+                             Hout=ch, Wout=cw, Cout=Ly.cout, K=self.K, C_img=self.C_img, _w=p + ":w", _b=p + ":b")
+                elif Ly.kind == "res":
+                    if len(srcs) == 2 and not Ly.skip_conv:
+                        raise NotImplementedError("identity skip over a concatenated input")
+                    if sum(s.C for s in srcs) != Ly.cin:
+                        raise ValueError(f"{p}: expected {Ly.cin} input channels, got {[s.C for s in srcs]}")
+                    h1 = emit(_lib.OP_CONV, srcs, new(p + ":h1", Ly.cout, ch, cw), ksize=3, stride=1, gn=1, silu=1, Hin=ch,
+                              Win=cw, Hout=ch, Wout=cw, Cout=Ly.cout, _src=srcs, _g=p + ":g1", _be=p + ":be1", _w=p + ":w1",
+                              _b=p + ":b1", emb_off=Ly.emb_off, _emb=True)
+                    f = dict(ksize=3, stride=1, gn=1, silu=1, Hin=ch, Win=cw, Hout=ch, Wout=cw, Cout=Ly.cout, _src=[h1],
+                             _g=p + ":g2", _be=p + ":be2", _w=p + ":w2", _b=p + ":b2")
+                    if Ly.skip_conv:
+                        f.update(_skip=srcs, _ws=p + ":ws")
+                    else:
+                        f.update(_res=srcs[0])
+                    h = emit(_lib.OP_CONV, [h1] + srcs, new(p, Ly.cout, ch, cw), **f)
+                    srcs = [h]
+                elif Ly.kind == "attn":
+                    x = srcs[0]
+                    C = Ly.cin
+                    qkv = emit(_lib.OP_CONV, [x], new(p + ":qkv", 3 * C, ch, cw, stat=False), ksize=1, stride=1, gn=1, silu=0,
+                               Hin=ch, Win=cw, Hout=ch, Wout=cw, Cout=3 * C, _src=[x], _g=p + ":g", _be=p + ":be",
+                               _w=p + ":wqkv", _b=p + ":bqkv")
+                    a = emit(_lib.OP_ATTENTION, [qkv], new(p + ":a", C, ch, cw, stat=False), Hin=ch, Win=cw, Hout=ch, Wout=cw,
+                             Cout=C, heads=Ly.heads, head_dim=C // Ly.heads, _src=[qkv])
+                    h = emit(_lib.OP_CONV, [a, x], new(p, C, ch, cw), ksize=1, stride=1, gn=0, silu=0, Hin=ch, Win=cw, Hout=ch,
+                             Wout=cw, Cout=C, _src=[a], _w=p + ":wproj", _b=p + ":bproj", _res=x)
+                    srcs = [h]
+                elif Ly.kind == "down":
+                    nh, nw = (ch + 1) // 2, (cw + 1) // 2
+                    h = emit(_lib.OP_CONV, srcs, new(p, Ly.cout, nh, nw), ksize=3, stride=2, Hin=ch, Win=cw, Hout=nh, Wout=nw,
+                             Cout=Ly.cout, _src=srcs, _w=p + ":w", _b=p + ":b")
+                    ch, cw = nh, nw
+                    srcs = [h]
+                elif Ly.kind == "up":
+                    h = emit(_lib.OP_CONV, srcs, new(p, Ly.cout, ch * 2, cw * 2), ksize=3, stride=1, upsample=1, Hin=ch, Win=cw,
+                             Hout=ch * 2, Wout=cw * 2, Cout=Ly.cout, _src=srcs, _w=p + ":w", _b=p + ":b")
+                    ch, cw = ch * 2, cw * 2
+                    srcs = [h]
+            if blk.stage == "in":
+                hs.append(h)
+                h.last = 10 ** 9  # provisional: popped later, fixed when consumed
+        assert (ch, cw) == (H, W) and not hs
+        logits = emit(_lib.OP_CONV, [h], new("logits", self.K, H, W, stat=False, esize=4), ksize=3, stride=1, gn=1, silu=1,
+                      Hin=H, Win=W, Hout=H, Wout=W, Cout=self.K, _src=[h], _g="out:g", _be="out:be", _w="out:w", _b="out:b",
+                      out_dtype=_lib.DT_F32)
+        emit(_lib.OP_HEAD, [logits], None, Hin=H, Win=W, K=self.K, _src=[logits])
+
+        # skip tensors: recompute true last use (emit() already recorded every reader)
+        for t in tens:
+            if t.last >= 10 ** 9:
+                t.last = max(i for i, o in enumerate(ops) if t in o["_ins"])
+
+        # ---- allocate ---------------------------------------------------------------
+        arena = Arena()
+        stat_bytes = 0
+        for i, o in enumerate(ops):
+            out = o["_out"]
+            if out is not None:
+                arena.alloc(out)
+                if out.want_stat:
+                    out.stat_off = stat_bytes
+                    stat_bytes += _ceil(B * out.C * 16, ALIGN)
+            arena.release_dead(i)
+        part_floats = max([L.ccdm_conv_part_floats(B, o["Hout"], o["Wout"], o["Cout"]) for o in ops
+                           if o["_out"] is not None and o["_out"].want_stat] + [1])
+        n_pix = B * H * W
+        feat_bytes = _ceil(B * fc * (H // 8) * (W // 8) * self.esize, ALIGN) if fc else 0
+        layout = dict(arena=arena.size, stat=stat_bytes, part=_ceil(part_floats * 4, ALIGN), ticket=_ceil(4 * (B + 1), ALIGN),
+                      labels=_ceil(n_pix, ALIGN), image=_ceil(n_pix * self.C_img * 4, ALIGN), feat=feat_bytes,
+                      feat_stat=_ceil(B * fc * 16, ALIGN) if fc else 0, probs=_ceil(n_pix * self.K * 4, ALIGN),
+                      noise=_ceil(n_pix * self.K * 4, ALIGN), step=ALIGN)
+        offs, total = {}, 0
+        for k, v in layout.items():
+            offs[k] = total
+            total += v
+        self.workspace = torch.zeros(total, dtype=torch.uint8, device=dev)
+        base = self.workspace.data_ptr()
+        self.addr = {k: base + v for k, v in offs.items()}
+        self.nbytes = total
+        self.arena_bytes = arena.size
+        if self.feat is not None:
+            self.feat.addr = self.addr["feat"]
+            self.feat.stat_addr = self.addr["feat_stat"]
+        for t in tens:
+            t.addr = self.addr["arena"] + t.off
+            t.stat_addr = self.addr["stat"] + t.stat_off if t.want_stat else 0
+
+        # typed views for the host side
+        def view(key, dtype, shape):
+            n = int(torch.tensor([], dtype=dtype).element_size()) * math.prod(shape)
+            return self.workspace[offs[key]:offs[key] + n].view(dtype).view(*shape)
+
+        self.labels = view("labels", torch.uint8, (B, H, W))
+        self.image = view("image", torch.float32, (B, self.C_img, H, W))
+        self.probs = view("probs", torch.float32, (B, H, W, self.K))
+        self.noise = view("noise", torch.float32, (n_pix, self.K))
+        self.step_counter = view("step", torch.int32, (1,))
+        self.logits = None
+        self.tens = {t.name: t for t in tens}
+
+        # step table + embedding table are (re)bound per run
+        self.max_rows = 0
+        self.steps_buf: Optional[torch.Tensor] = None
+        self.emb_buf: Optional[torch.Tensor] = None
+        self.rows_per_sample = rows_per_sample
+        self._op_dicts = ops
+        self.plan = None
+        self.n_ops = len(ops)
+        self._bound_rows = -1
+
+    # -- binding ---------------------------------------------------------------------
+    def bind(self, n_rows: int):
+        """(Re)build the C plan against step/emb tables of at least ``n_rows`` rows."""
+        L = _lib.lib()
+        if self.plan is not None and n_rows <= self.max_rows:
+            return
+        if self.plan is not None:
+            L.ccdm_plan_destroy(self.plan)
+            self.plan = None
+        eng = self.engine
+        dev = eng.device
+        self.max_rows = max(n_rows, 8)
+        emb_cols = eng.unet.arch.emb_cols
+        self.steps_buf = torch.zeros(self.max_rows * ctypes.sizeof(StepEntry), dtype=torch.uint8, device=dev)
+        self.emb_buf = torch.zeros(self.max_rows * max(emb_cols, 1), dtype=torch.float32, device=dev)
+        self.t_buf = torch.zeros(self.max_rows, dtype=torch.float32, device=dev)
+        W = eng.weights
+        arr = (Op * self.n_ops)()
+        for i, o in enumerate(self._op_dicts):
+            f = {k: v for k, v in o.items() if not k.startswith("_")}
+            fields = dict(dtype=self.dt, B=self.B, exact=self.exact, out_dtype=self.dt)
+            fields.update(f)
+            op = Op(**fields)
+            src = o.get("_src", [])
+            if o["kind"] == _lib.OP_INPUT_CONV:
+                op.labels_in = self.addr["labels"]
+                op.image = self.addr["image"]
+            if o["kind"] in (_lib.OP_CONV, _lib.OP_ATTENTION):
+                op.src0, op.C0 = src[0].addr, src[0].C
+                op.stat0 = src[0].stat_addr
+                if len(src) > 1:
+                    op.src1, op.C1, op.stat1 = src[1].addr, src[1].C, src[1].stat_addr
+            if "_g" in o:
+                op.gamma, op.beta = W.addr(o["_g"]), W.addr(o["_be"])
+            if "_w" in o:
+                op.weight, op.bias = W.addr(o["_w"]), W.addr(o["_b"])
+            if o.get("_emb"):
+                op.emb = self.emb_buf.data_ptr()
+                op.emb_cols = emb_cols
+                op.emb_bstride = self.rows_per_sample
+            if "_skip" in o:
+                sk = o["_skip"]
+                op.skip0, op.S0 = sk[0].addr, sk[0].C
+                if len(sk) > 1:
+                    op.skip1, op.S1 = sk[1].addr, sk[1].C
+                op.skip_w = W.addr(o["_ws"])
+            if "_res" in o:
+                op.res = o["_res"].addr
+            out = o["_out"]
+            if out is not None:
+                op.out = out.addr
+                if out.want_stat:
+                    op.ostat = out.stat_addr
+                    op.part = self.addr["part"]
+                    op.ticket = self.addr["ticket"]
+            if o["kind"] == _lib.OP_HEAD:
+                op.src0 = src[0].addr
+                op.labels_in = self.addr["labels"]
+                op.labels_out = self.addr["labels"]
+                op.probs_out = self.addr["probs"]
+                op.noise = self.addr["noise"]
+                op.ticket = self.addr["ticket"] + 4 * self.B
+            op.steps = self.steps_buf.data_ptr()
+            op.step_ptr = self.addr["step"]
+            arr[i] = op
+        self._op_array = arr
+        self.plan = L.ccdm_plan_create(arr, self.n_ops)
+        if not self.plan:
+            raise _lib.CcdmError("ccdm_plan_create failed: " + L.ccdm_last_error().decode())
+
+    def __del__(self):
+        try:
+            if self.plan is not None:
+                _lib.lib().ccdm_plan_destroy(self.plan)
+        except Exception:
+            pass
+
+
+# --------------------------------------------------------------------------------------
+# engine
+# --------------------------------------------------------------------------------------
+class UNetEngine:
+    def __init__(self, unet, precision: str = "fp32", dry_run: bool = False):
+        """``dry_run``: plan programs with host buffers and never launch (host-logic tests
+        on machines without a GPU); any attempt to run raises."""
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        p0 = next(unet.parameters())
+        self.dry_run = dry_run
+        if not dry_run:
+            _lib.require_device()
+            if p0.device.type != "cuda":
+                raise _lib.CcdmError("the model must live on a CUDA device (B200); there is no CPU path")
+        self.unet = unet
+        self.precision = precision
+        self.device = p0.device
+        self.weights = PackedWeights(unet, self.device)
+        self.programs: Dict[tuple, Program] = {}
+        self.stream = None if dry_run else torch.cuda.Stream(device=self.device)
+        self.use_graph = True
+
+    # -- helpers ----------------------------------------------------------------------
+    def program(self, B, H, W, rows_per_sample=0) -> Program:
+        key = (B, H, W, rows_per_sample)
+        prog = self.programs.get(key)
+        if prog is None:
+            prog = self.programs[key] = Program(self, B, H, W, rows_per_sample)
+        return prog
+
+    def _sp(self):
+        return _lib.stream_ptr(self.stream)
+
+    def _load_inputs(self, prog: Program, x, condition, feature_condition):
+        L = _lib.lib()
+        dev = self.device
+        B, H, W, K = prog.B, prog.H, prog.W, prog.K
+        if x.dtype == torch.uint8 and x.dim() == 3:
+            prog.labels.copy_(x.to(dev, non_blocking=True))
+        else:
+            if tuple(x.shape) != (B, K, H, W):
+                raise ValueError(f"x must be one-hot [B,{K},H,W] (or uint8 labels [B,H,W]); got {tuple(x.shape)}")
+            xf = x.to(device=dev, dtype=torch.float32, non_blocking=True)
+            sb, sk, sh, sw = xf.stride()
+            _lib.check(L.ccdm_onehot_to_labels(xf.data_ptr(), sb, sk, sh, sw, B, K, H, W, prog.labels.data_ptr(), self._sp()),
+                       "onehot_to_labels")
+            xf.record_stream(self.stream)
+        if tuple(condition.shape) != (B, prog.C_img, H, W):
+            raise ValueError(f"condition must be [B,{prog.C_img},{H},{W}]; got {tuple(condition.shape)}")
+        prog.image.copy_(condition.to(device=dev, dtype=torch.float32, non_blocking=True))
+        if prog.feat is not None:
+            if feature_condition is None:
+                raise ValueError("this UNet was built with a feature_cond_encoder: feature_condition is required")
+            f = prog.feat
+            if tuple(feature_condition.shape) != (B, f.C, f.H, f.W):
+                raise ValueError(f"feature_condition must be [B,{f.C},{f.H},{f.W}]; got {tuple(feature_condition.shape)}")
+            fcond = feature_condition.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+            _lib.check(L.ccdm_nchw_to_nhwc_stats(fcond.data_ptr(), B, f.C, f.H, f.W, prog.dt, f.addr, f.stat_addr, self._sp()),
+                       "nchw_to_nhwc_stats")
+            fcond.record_stream(self.stream)
+        # (unet.py:770: a feature_condition passed to a UNet without an encoder slot is ignored)
+
+    def _write_tables(self, prog: Program, entries: Sequence[tuple], t_rows: Sequence[float]):
+        """entries: (t, alpha, cumalpha_tm1, mode, draw, emb_row) per step; t_rows: timesteps of the embedding rows."""
+        L = _lib.lib()
+        n_rows = max(len(entries), len(t_rows))
+        prog.bind(n_rows)
+        arr = (StepEntry * len(entries))()
+        for i, (t, a, c, mode, draw, row) in enumerate(entries):
+            arr[i] = StepEntry(float(t), float(a), float(c), int(mode), int(draw), int(row), 0, 0)
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        prog.steps_buf[:host.numel()].copy_(host, non_blocking=False)
+        prog.t_buf[:len(t_rows)].copy_(torch.tensor(list(t_rows), dtype=torch.float32))
+        prog.step_counter.zero_()
+        Wt = self.weights
+        mc = self.unet.model_channels
+        cols = self.unet.arch.emb_cols
+        _lib.check(L.ccdm_time_table(prog.t_buf.data_ptr(), len(t_rows), mc, Wt.addr("te0_w"), Wt.addr("te0_b"), Wt.addr("te2_w"),
+                                     Wt.addr("te2_b"), Wt.addr("emb_w"), Wt.addr("emb_b"), cols, prog.emb_buf.data_ptr(), self._sp()),
+                   "time_table")
+
+    # -- reference UNetModel.forward (one evaluation) ------------------------------------
+    @torch.no_grad()
+    def single_step(self, x, condition, feature_condition, timesteps, softmax=True):
+        if not softmax:
+            raise NotImplementedError("softmax_output=False is not implemented by the B200 sampler")
+        L = _lib.lib()
+        if self.dry_run:
+            raise _lib.CcdmError("dry-run engine cannot execute")
+        B, _, H, W = x.shape if x.dim() == 4 else (x.shape[0], None, x.shape[1], x.shape[2])
+        ts = timesteps.detach().float().reshape(-1).cpu().tolist()
+        if len(ts) != B:
+            raise ValueError("timesteps must have one entry per sample")
+        if x.dim() == 4 and x.is_floating_point():
+            xs = x.detach()
+            if not bool(((xs.max(dim=1).values == 1) & (xs.sum(dim=1) == 1)).all()):
+                raise ValueError("UNetModel.forward: x must be a one-hot label map (the hot path keeps x_t as labels)")
+        cur = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            self.weights.refresh()
+            prog = self.program(B, H, W, rows_per_sample=1)
+            self._load_inputs(prog, x, condition, feature_condition)
+            self._write_tables(prog, [(ts[0], 0.0, 1.0, _lib.DRAW_X0, 0, 0)], ts)
+            _lib.check(L.ccdm_plan_set_noise(prog.plan, _lib.NOISE_PHILOX, 0, 0, None, None))
+            _lib.check(L.ccdm_plan_step(prog.plan, 0, self._sp()), "plan_step")
+            out = prog.probs.clone()
+        cur.wait_stream(self.stream)
+        return out.permute(0, 3, 1, 2)
+
+    # -- reference DenoisingModel.forward_denoising -----------------------------------------
+    @torch.no_grad()
+    def run_chain(self, x, condition, feature_condition, t_values: Sequence[int], alphas, cumalphas, last_mode: int,
+                  noise: str = "torch", seed: int = 0, sample0: int = 0, record=None):
+        """Runs the reverse chain; returns (labels uint8 [B,H,W], probs fp32 [B,H,W,K] or None).
+
+        ``alphas``/``cumalphas``: host float lists (the DiffusionModel buffers).  ``noise``:
+        'torch' draws ``E = empty(B*H*W, K).exponential_(1)`` from the device's global
+        generator once per step with t > 1, exactly the stream the reference's
+        ``torch.multinomial`` consumes; 'philox' draws in-kernel (sharding-invariant).
+        A sequence of tensors instead of a string injects explicit noise (golden replays).
+        ``record``: optional list; receives per-step dicts of device tensors (tests).
+        """
+        L = _lib.lib()
+        if self.dry_run:
+            raise _lib.CcdmError("dry-run engine cannot execute")
+        if x.dim() == 4:
+            B, _, H, W = x.shape
+        else:
+            B, H, W = x.shape
+        noise_list = None
+        if not isinstance(noise, str):
+            noise_list = list(noise)
+            if len(noise_list) != sum(1 for t in t_values if t > 1):
+                raise ValueError("explicit noise needs one [B*H*W, K] tensor per step with t > 1")
+            noise = "torch"
+        elif noise not in ("torch", "philox"):
+            raise ValueError(f"noise={noise!r}")
+        cur = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            self.weights.refresh()
+            prog = self.program(B, H, W, rows_per_sample=0)
+            self._load_inputs(prog, x, condition, feature_condition)
+            entries = []
+            n = len(t_values)
+            for i, t in enumerate(t_values):
+                t0 = t - 1  # diffusion_denoising.py:107-113
+                a, c = (0.0, 1.0) if t0 == 0 else (alphas[t0], cumalphas[t0 - 1])
+                mode = _lib.DRAW_SAMPLE if t > 1 else last_mode  # :206-212
+                entries.append((float(t), a, c, mode, i, i))
+            self._write_tables(prog, entries, [float(t) for t in t_values])
+            use_tensor = noise == "torch"
+            want_noise_out = record is not None and not use_tensor
+            _lib.check(L.ccdm_plan_set_noise(prog.plan, _lib.NOISE_TENSOR if use_tensor else _lib.NOISE_PHILOX, int(seed),
+                                             int(sample0), prog.noise.data_ptr() if use_tensor else None,
+                                             prog.noise.data_ptr() if want_noise_out else None), "set_noise")
+            if not use_tensor and record is None:
+                _lib.check(L.ccdm_plan_run(prog.plan, n, 1 if self.use_graph else 0, self._sp()), "plan_run")
+            else:
+                for i, t in enumerate(t_values):
+                    if use_tensor and t > 1:
+                        if noise_list is not None:
+                            prog.noise.copy_(noise_list.pop(0).reshape(prog.noise.shape))
+                        else:
+                            prog.noise.exponential_(1)  # the reference's torch.multinomial draw
+                    if record is not None:
+                        rec = dict(t=t, labels_in=prog.labels.clone())
+                    _lib.check(L.ccdm_plan_step(prog.plan, 1 if self.use_graph else 0, self._sp()), "plan_step")
+                    if record is not None:
+                        lg = prog.tens["logits"]
+                        rec.update(labels_out=prog.labels.clone(), noise=prog.noise.clone() if t > 1 else None,
+                                   logits=self.tensor_view(prog, lg).clone())
+                        record.append(rec)
+            labels = prog.labels.clone()
+            probs = prog.probs.clone() if last_mode == _lib.DRAW_CONFIDENCE and t_values[-1] == 1 else None
+        cur.wait_stream(self.stream)
+        return labels, probs
+
+    def tensor_view(self, prog: Program, t: Ten) -> torch.Tensor:
+        dtype = torch.float32 if t.esize == 4 else torch.bfloat16
+        off = t.addr - prog.workspace.data_ptr()
+        n = prog.B * t.H * t.W * t.C * t.esize
+        return prog.workspace[off:off + n].view(dtype).view(prog.B, t.H, t.W, t.C)

@@ -1,0 +1,196 @@
+/*
+ * ccdm_b200.h -- C ABI of libccdm_b200.so, the sm_100a implementation of the CCDM
+ * reverse-process hot path.
+ *
+ * The reference (LarsDoorenbos/ccdm-stochastic-segmentation) is pure
+ * Python/PyTorch and has no FFI of its own; its boundary is the Python object
+ * protocol `DenoisingModel.forward` (ddpm/models/diffusion_denoising.py:144).
+ * Each entry point below names the reference lines it replaces; INTEGRATION.md
+ * shows the ctypes binding (ccdm_b200/_lib.py) that sits between them.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer except `ops`, `err` strings
+ *    and handles is a DEVICE pointer owned by the caller.
+ *  - no allocation of caller-visible memory, no host synchronisation, every
+ *    launch goes to the `stream` argument (a cudaStream_t passed as void*).
+ *  - return 0 on success, negative on error; ccdm_last_error() describes it.
+ *  - activations are NHWC ("pixel-major, channel-minor"), fp32 or bf16
+ *    (`CCDM_DT_*`); label maps are uint8 [B,H,W]; GroupNorm statistics travel
+ *    beside every activation as per-(sample,channel) double2 {sum, sum of
+ *    squares} written by the producing kernel.
+ *  - one process per GPU; a plan is not re-entrant.
+ */
+#ifndef CCDM_B200_H
+#define CCDM_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCDM_ABI_VERSION 1
+
+/* storage types of activations / packed conv weights */
+#define CCDM_DT_F32 0
+#define CCDM_DT_BF16 1
+
+/* last-step / draw modes of the categorical head (diffusion_denoising.py:206-212) */
+#define CCDM_DRAW_SAMPLE 0     /* t > 1: x_{t-1} ~ Cat(p)  == argmax p/E            */
+#define CCDM_DRAW_MAJORITY 1   /* t == 1, step_T_sample None|"majority": argmax p   */
+#define CCDM_DRAW_CONFIDENCE 2 /* t == 1, "confidence": normalised probabilities    */
+#define CCDM_DRAW_X0 3         /* no posterior: emit softmax(logits) (forward_step) */
+#define CCDM_DRAW_POSTERIOR 4  /* standalone API only: emit the raw (unclamped) theta_post_prob (:128) */
+
+/* noise sources of the draw */
+#define CCDM_NOISE_TENSOR 0 /* explicit E ~ Exp(1), fp32 [B*H*W, K] (torch generator parity) */
+#define CCDM_NOISE_PHILOX 1 /* in-kernel Philox4x32-10 keyed by (seed, global sample, draw, pixel) */
+
+/* One row per chain step, resident on the device; kernels index it with the
+ * device-side step counter so one captured CUDA graph replays for every t. */
+typedef struct ccdm_step_entry {
+    float t;            /* timestep fed to the UNet (diffusion_denoising.py:191-194) */
+    float alpha_t;      /* alphas[t-1], 0 at t==1   (:110-113)                        */
+    float cumalpha_tm1; /* cumalphas[t-2], 1 at t==1 (:111-113)                        */
+    int32_t mode;       /* CCDM_DRAW_*                                                */
+    uint32_t draw;      /* Philox draw index (chain step ordinal)                     */
+    int32_t emb_row;    /* row of the timestep-embedding table this step uses         */
+    int32_t pad0, pad1;
+} ccdm_step_entry;
+
+/* ---- program ops: one fused kernel launch each ---------------------------- */
+#define CCDM_OP_INPUT_CONV 1 /* unet.py:760 + input_blocks[0] (:516-518)                 */
+#define CCDM_OP_CONV 2       /* GN+SiLU+conv3x3/1x1 (+emb +bias +residual/1x1 skip)     */
+#define CCDM_OP_ATTENTION 3  /* QKVAttentionLegacy (:343-360)                           */
+#define CCDM_OP_HEAD 4       /* softmax + theta_post_prob + clamp + draw                */
+
+typedef struct ccdm_op {
+    int32_t kind; /* CCDM_OP_* */
+    int32_t dtype; /* CCDM_DT_* of activations in/out */
+    int32_t B, Hin, Win, Hout, Wout;
+    int32_t C0, C1;     /* channels of the two concatenated sources (C1 may be 0) */
+    int32_t Cout;
+    int32_t ksize;      /* 1 or 3 */
+    int32_t stride;     /* 1 or 2 (Downsample, unet.py:136-139) */
+    int32_t upsample;   /* 1: nearest x2 in front of the conv (Upsample, :106-116) */
+    int32_t gn;         /* 1: GroupNorm(32 groups, eps 1e-5) on the input (nn.py:93-100) */
+    int32_t silu;       /* 1: SiLU after the norm */
+    int32_t S0, S1;     /* channels of the 1x1-skip sources (ResBlock.skip_connection, :221-228) */
+    int32_t heads, head_dim; /* attention */
+    int32_t K;          /* classes (input conv, head) */
+    int32_t C_img;      /* image channels (input conv) */
+    int32_t emb_off;    /* column of this block in the embedding table, -1: none */
+    int32_t emb_cols;   /* row length of the embedding table */
+    int32_t emb_bstride;/* rows between consecutive samples (0: same t for the batch) */
+    int32_t noise_mode; /* CCDM_NOISE_* (head) */
+    int32_t sample0;    /* global index of local sample 0 (Philox counter; sharding) */
+    int32_t out_dtype;  /* CCDM_DT_* of `out` (logits stay fp32 in bf16 mode) */
+    int32_t src_kind;   /* 0: src0/src1 NHWC activations; 1: one-hot(labels_in) ++ image (unet.py:760) */
+    int32_t exact;      /* 1: fp32 FFMA kernels (parity mode); 0: tensor-core kernels where available */
+    int32_t reserved[2];
+    uint64_t seed;      /* Philox key */
+    /* device pointers (0 = absent) */
+    uint64_t src0, src1;       /* inputs NHWC                                             */
+    uint64_t stat0, stat1;     /* double2 [B,C] stats of src0/src1 (gn=1)                 */
+    uint64_t gamma, beta;      /* fp32 [C0+C1]                                            */
+    uint64_t weight;           /* packed [tap][CinP][CoutP], CinP=ceil8(Cin), CoutP=ceil32(Cout), zero padded */
+    uint64_t bias;             /* fp32 [CoutP] (conv bias, + skip bias folded in)         */
+    uint64_t emb;              /* fp32 table [rows, emb_cols]                             */
+    uint64_t skip0, skip1;     /* raw NHWC inputs of the fused 1x1 skip conv              */
+    uint64_t skip_w;           /* packed [S0+S1][CoutP]                                   */
+    uint64_t res;              /* identity residual NHWC [B,Hout,Wout,Cout]               */
+    uint64_t out;              /* NHWC output                                             */
+    uint64_t ostat;            /* double2 [B,Cout] stats of `out` (0: not needed)         */
+    uint64_t part;             /* fp32 scratch for per-tile partial stats                 */
+    uint64_t ticket;           /* uint32 [B] arrival counters (self-resetting)            */
+    uint64_t labels_in;        /* uint8 [B,H,W]   (input conv, head)                      */
+    uint64_t labels_out;       /* uint8 [B,H,W]   (head)                                  */
+    uint64_t image;            /* fp32 NCHW [B,C_img,H,W] (input conv)                    */
+    uint64_t noise;            /* fp32 [B*H*W,K]  (head, CCDM_NOISE_TENSOR)               */
+    uint64_t probs_out;        /* fp32 [B,H,W,K]  (head: confidence / x0 output, or 0)    */
+    uint64_t noise_out;        /* fp32 [B*H*W,K]  (head: export of the E used, or 0)      */
+    uint64_t steps;            /* const ccdm_step_entry* table                            */
+    uint64_t step_ptr;         /* int32* device step counter                              */
+} ccdm_op;
+
+/* ---- library ---------------------------------------------------------------- */
+int ccdm_abi_version(void);
+const char *ccdm_last_error(void);
+/* struct sizes, so a foreign-language binding can verify its mirror of the structs */
+size_t ccdm_sizeof_op(void);
+size_t ccdm_sizeof_step_entry(void);
+/* floats of `part` scratch a conv op with statistics needs */
+size_t ccdm_conv_part_floats(int B, int Hout, int Wout, int Cout);
+/* 0 if the current device is compute capability 10.x, negative otherwise. */
+int ccdm_check_device(void);
+
+/* ---- single kernels (unit-parity surface) ---------------------------------- */
+
+/* Launch one op.  Replaces, depending on op->kind: unet.py:760+516-518 (input
+ * conv), :242-262 / :106-116 / :144-146 / :305-311 (fused conv variants),
+ * :343-360 (attention), :701-707 + diffusion_denoising.py:197-212 (head). */
+int ccdm_launch_op(const ccdm_op *op, void *stream);
+
+/* Timestep-embedding table.  Replaces nn.py:103-121 + unet.py:506-510,758 and
+ * every ResBlock's emb_layers (:205-211,251): out[r, :] = W_all * silu(time_embed(
+ * sinusoid(t[r]))) + b_all, with W_all [cols, 4*mc] the row-concatenation of all
+ * emb_layers.1.weight.  t: fp32 [rows]. */
+int ccdm_time_table(const float *t, int rows, int model_channels, const float *te0_w, const float *te0_b,
+                    const float *te2_w, const float *te2_b, const float *w_all, const float *b_all, int cols,
+                    float *out, void *stream);
+
+/* One-hot (or any score map) -> labels: argmax over K of a strided fp32
+ * [B,K,H,W] tensor (strides in elements).  Replaces the `.argmax(dim=1)` the
+ * callers apply to x_T (the chain keeps x_t as uint8 labels). */
+int ccdm_onehot_to_labels(const float *x, int64_t sb, int64_t sk, int64_t sh, int64_t sw, int B, int K, int H,
+                          int W, uint8_t *labels, void *stream);
+
+/* labels -> one-hot int64 [B,H,W,K] (max_prob_sample, one_hot_categorical.py:46-50). */
+int ccdm_labels_to_onehot_i64(const uint8_t *labels, size_t n_pix, int K, int64_t *out, void *stream);
+
+/* NCHW fp32 -> NHWC (fp32|bf16) + per-(sample,channel) stats; used once per chain
+ * for the feature condition (unet.py:784-786). */
+int ccdm_nchw_to_nhwc_stats(const float *src, int B, int C, int H, int W, int dtype, void *dst, double *stat,
+                            void *stream);
+
+/* Standalone posterior + draw on probabilities theta fp32 [n_pix_total, K]
+ * (diffusion_denoising.py:99-128,204-212; one_hot_categorical.py:30-54).
+ * labels_in/labels_out uint8; noise fp32 [n, K] or NULL with philox; probs_out
+ * (normalised clamped posterior) and noise_out optional. */
+int ccdm_posterior_draw(const float *theta, const uint8_t *labels_in, size_t n_pix_per_sample, int B, int K,
+                        float alpha_t, float cumalpha_tm1, int mode, int noise_mode, const float *noise,
+                        uint64_t seed, uint32_t draw, uint32_t sample0, uint8_t *labels_out, float *probs_out,
+                        float *noise_out, void *stream);
+
+/* Raw Philox words, layout [n_samples, n_pix, K] (tests the counter layout). */
+int ccdm_philox_bits(uint64_t seed, uint32_t draw, uint32_t sample0, uint32_t n_samples, uint32_t n_pix, int K,
+                     uint32_t *bits, void *stream);
+
+/* x_T: uniform labels from Philox (draw index `draw`), the device-side
+ * equivalent of OneHotCategoricalBCHW(logits=zeros).sample(). */
+int ccdm_uniform_labels(uint64_t seed, uint32_t draw, uint32_t sample0, uint32_t n_samples, uint32_t n_pix,
+                        int K, uint8_t *labels, void *stream);
+
+/* ---- programs: the whole reverse step as one launch sequence / CUDA graph --- */
+typedef struct ccdm_plan ccdm_plan;
+
+/* Copies `ops` (host array).  The op sequence is one reverse step:
+ * UNet forward (unet.py:744-808) + posterior + draw. */
+ccdm_plan *ccdm_plan_create(const ccdm_op *ops, int n_ops);
+void ccdm_plan_destroy(ccdm_plan *plan);
+int ccdm_plan_num_launches(const ccdm_plan *plan);
+/* Rewrites per-run fields (head noise mode / seed / sample0 / export pointers);
+ * invalidates a captured graph if they changed. */
+int ccdm_plan_set_noise(ccdm_plan *plan, int noise_mode, uint64_t seed, int32_t sample0, const float *noise,
+                        float *noise_out);
+/* One reverse step: replays the captured graph (captured on first use when
+ * use_graph != 0), then advances the device step counter. */
+int ccdm_plan_step(ccdm_plan *plan, int use_graph, void *stream);
+/* n_steps reverse steps back to back (the T-loop of forward_denoising, :189-212). */
+int ccdm_plan_run(ccdm_plan *plan, int n_steps, int use_graph, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCDM_B200_H */

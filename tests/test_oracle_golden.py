@@ -1,0 +1,132 @@
+"""Pins the CPU oracle (oracle/) to the fixtures generated from the unmodified reference
+(tests/golden/make_golden.py).  CPU only."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES, build_ours, golden
+from oracle import cdm, chain_ref, unet_ref
+from ccdm_b200.synthetic import synthetic_inputs
+
+
+def test_cosine_and_linear_schedules():
+    g = golden("schedules.npz")
+    for T in (100, 250, 1000):
+        b, a, c = cdm.cosine_schedule(T)
+        # betas/alphas: float64 python math in the reference -> identical after rounding to fp32
+        np.testing.assert_array_equal(b, g[f"cosine{T}_betas"])
+        np.testing.assert_array_equal(a, g[f"cosine{T}_alphas"])
+        # cumalphas: torch's vectorised fp32 cos vs libm: allow 2 ulp of the value
+        np.testing.assert_allclose(c, g[f"cosine{T}_cumalphas"], rtol=2.5e-7, atol=0)
+    b, a, c = cdm.linear_schedule(250)
+    np.testing.assert_allclose(b, g["linear250_betas"], rtol=2e-7)
+    np.testing.assert_allclose(c, g["linear250_cumalphas"], rtol=5e-6)
+    # quirks called out in SURVEY.md section 7 item 8
+    assert abs(g["cosine250_cumalphas"][0] - 0.99984455) < 1e-7
+    assert not np.allclose(np.cumprod(g["cosine250_alphas"]), g["cosine250_cumalphas"], rtol=1e-3)
+
+
+def test_t_values_match_reference_loop():
+    g = golden("t_values.npz")
+    for key in g.files:
+        T, req = key[1:].split("_req")
+        req = None if req == "None" else int(req)
+        assert cdm.t_values(int(T), req) == g[key].tolist(), key
+    with pytest.raises(AssertionError):
+        cdm.t_values(250, 10000 + 251)
+    with pytest.raises(AssertionError):
+        cdm.t_values(250, 20000)
+
+
+@pytest.mark.parametrize("K", [2, 20])
+@pytest.mark.parametrize("T", [250, 1000])
+def test_posterior_matches_reference(K, T):
+    g = golden("posterior.npz")
+    sch = golden("schedules.npz")
+    tag = f"K{K}_T{T}"
+    theta, labels, ts, post = (g[tag + s] for s in ("_theta", "_labels", "_t", "_post"))
+    for i, t in enumerate(ts):
+        a, c = cdm.step_scalars(sch[f"cosine{T}_alphas"], sch[f"cosine{T}_cumalphas"], int(t))
+        lit = cdm.posterior_literal(labels[i], theta[i], a, c)
+        clo = cdm.posterior_closed(labels[i], theta[i], a, c)
+        np.testing.assert_allclose(lit, post[i], rtol=0, atol=2e-6)
+        np.testing.assert_allclose(clo, post[i], rtol=0, atol=2e-6)  # <= 7.8e-7 observed
+        if t == 1:  # alpha:=0, cumalpha':=1  ->  posterior == theta
+            np.testing.assert_allclose(clo, theta[i], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("K", [2, 20])
+def test_draw_matches_reference_bit_exact(K):
+    g = golden("draw.npz")
+    p = g[f"K{K}_probs_in"]
+    lab, pn = cdm.draw(p, g[f"K{K}_noise"].reshape(p.shape), 0)
+    np.testing.assert_array_equal(lab, g[f"K{K}_sample_labels"])
+    lab, pn = cdm.draw(p, None, 1)
+    np.testing.assert_array_equal(lab, g[f"K{K}_majority_labels"])
+    lab, pn = cdm.draw(p, None, 2)
+    np.testing.assert_allclose(pn, g[f"K{K}_confidence"], rtol=3e-7, atol=0)
+    xt = cdm.uniform_labels(g[f"K{K}_xT_noise"].reshape(p.shape))
+    np.testing.assert_array_equal(xt, g[f"K{K}_xT_labels"])
+
+
+def test_philox_known_answers():
+    # Random123 known-answer vectors for philox4x32-10
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, out in kat:
+        assert tuple(int(v) for v in cdm.philox4x32_10(ctr, key)) == out
+    bits = cdm.philox_bits(0x1234567890ABCDEF, 3, 5, 2, 7, 20)
+    assert bits.shape == (2, 7, 20)
+    ref = cdm.philox4x32_10((6, 5 + 1, 3, 4), (0x90ABCDEF, 0x12345678))
+    assert bits[1, 6, 16] == ref[0] and bits[1, 6, 19] == ref[3]
+    e = cdm.bits_to_exponential(bits)
+    assert np.all(e > 0) and np.all(np.isfinite(e))
+
+
+def _load_case(tag):
+    T, B, C_img, H, W, K, fce, mult, t_probe, steps = GOLDEN_CASES[tag]
+    m = build_ours(T, C_img, H, W, K, "majority", fce, mult)
+    image, feat, labels = synthetic_inputs(B, C_img, H, W, K, 384 if fce else 0)
+    return m, image, feat, labels
+
+
+@pytest.mark.parametrize("tag", ["lidc64", "lidc128", "cs64x128"])
+def test_unet_restatement_matches_reference(tag):
+    T, B, C_img, H, W, K, fce, mult, t_probe, steps = GOLDEN_CASES[tag]
+    g = golden(tag + ".npz")
+    m, image, feat, labels = _load_case(tag)
+    sd = m.unet.state_dict()
+    x = chain_ref.labels_to_onehot(labels.numpy(), K)
+    for t in t_probe:
+        out = unet_ref.unet_forward(sd, x, image, feat, torch.full((B,), float(t)),
+                                    feature_condition_idx=10 if fce else None)
+        np.testing.assert_allclose(out.permute(0, 2, 3, 1).numpy(), g[f"x0pred_t{t}"], rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("tag", ["lidc64", "cs64x128"])
+def test_chain_restatement_matches_reference(tag):
+    T, B, C_img, H, W, K, fce, mult, t_probe, steps = GOLDEN_CASES[tag]
+    g = golden(tag + ".npz")
+    m, image, feat, labels = _load_case(tag)
+    sd = m.unet.state_dict()
+    al, ca = m.diffusion.alphas.numpy(), m.diffusion.cumalphas.numpy()
+    digest = hashlib.sha256()
+
+    def noise_fn(shape):
+        e = chain_ref.torch_noise(shape)
+        digest.update(e.tobytes())
+        return e
+
+    torch.manual_seed(42)
+    lab, _ = chain_ref.reverse_chain(sd, labels.numpy(), image, feat, al, ca, T, 10000 + steps, "majority", noise_fn,
+                                     feature_condition_idx=10 if fce else None, K=K)
+    assert np.array_equal(np.frombuffer(digest.digest(), np.uint8), g["chain_noise_sha256"]), "torch CPU generator stream changed"
+    np.testing.assert_array_equal(lab, g["chain_majority_labels"])
+    torch.manual_seed(42)
+    _, probs = chain_ref.reverse_chain(sd, labels.numpy(), image, feat, al, ca, T, 10000 + steps, "confidence",
+                                       feature_condition_idx=10 if fce else None, K=K)
+    np.testing.assert_allclose(probs, g["chain_confidence_probs"], rtol=0, atol=2e-6)
