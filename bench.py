@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""Benchmark of the CCDM reverse-process sampler (BASELINE.json: seg samples/sec, full T-step chain).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload lidc|cityscapes] [--precision fp32|bf16]
+    python bench.py --impl reference ...      # the reference's own CPU path on the host cores
+
+One "step" = one full T-step reverse chain over one batch of synthetic inputs (random-init weights
+of the named architecture, random conditioning image, uniform random x_T).  Prints ONE JSON line.
+Launch with torchrun for N > 1 (one rank per GPU, weak scaling: every rank runs its own batch and the
+label maps are gathered over NCCL at the end of the chain, inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "ccdm-stochastic-segmentation_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+UNET_PARAMS = dict(base_channels=32, channel_mult=None, attention_resolutions=[32, 16, 8], num_heads=1, num_head_channels=32,
+                   softmax_output=True)
+DINO = dict(type="dino", model="dino_vits8", channels=384, conditioning="concat_pixels_concat_features", output_stride=8,
+            scale="single", train=False, source_layer=11, target_layer=10)
+WORKLOADS = {
+    # BASELINE.json configs[1] / configs[2]
+    "lidc": dict(name="LIDC 128x128, 2-class, T=250, batch=64", C_img=1, H=128, W=128, K=2, T=250, B=64, fce=None,
+                 dataset="datasets.lidc", elements=28686336, flops=8.44e9),
+    "cityscapes": dict(name="Cityscapes 256x512, 20-class, T=250, batch=8 (DINO-conditioned)", C_img=3, H=256, W=512, K=20,
+                       T=250, B=8, fce=DINO, dataset="datasets.cityscapes", elements=227983360, flops=72.71e9),
+}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops_sustained"], source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def build_model(wl, device=None, reference=False):
+    from ccdm_b200.synthetic import fill_synthetic_
+    if reference:
+        from oracle.build_ref import load_reference_models
+        models = load_reference_models()
+        kind = "reference"
+        if models is None:
+            kind = "port"
+    else:
+        from ccdm_b200 import models
+        kind = "ours"
+    if reference and kind == "port":
+        from ccdm_b200 import models as ours_models  # parameter container only; evaluated by oracle/unet_ref on the CPU
+        models = ours_models
+    shapes = [(wl["C_img"], wl["H"], wl["W"]), (wl["K"], wl["H"], wl["W"])]
+    m = models.build_model(wl["T"], "cosine", {"s": 0.008}, shapes, shapes[0], "unet_openai", dict(UNET_PARAMS), wl["dataset"],
+                           "majority", wl["fce"]).eval()
+    fill_synthetic_(m.unet, 0)
+    if device is not None:
+        m = m.to(device)
+    return m, kind
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation (bytecode under oracle/_ref) or the oracle port
+# ----------------------------------------------------------------------------------------------
+def cpu_chain_rate(wl, budget_s=20.0, max_steps=None):
+    """Times a bounded sample of the workload (batch 1, the first n steps of the T-step chain) on the
+    host cores and extrapolates to samples/s for the full chain."""
+    from ccdm_b200.synthetic import synthetic_inputs
+    m, kind = build_model(wl, reference=True)
+    image, feat, labels = synthetic_inputs(1, wl["C_img"], wl["H"], wl["W"], wl["K"], 384 if wl["fce"] else 0)
+    x = torch.nn.functional.one_hot(labels.long(), wl["K"]).permute(0, 3, 1, 2).float()
+    T = wl["T"]
+    torch.manual_seed(0)
+    with torch.no_grad():
+        if kind == "reference":
+            def run(n):  # the reference's strided chain with n steps == n reverse steps of identical cost
+                return m(x, image, feat, t=torch.as_tensor(10000 + n))
+        else:
+            from oracle import chain_ref
+            sd = m.unet.state_dict()
+            al, ca = m.diffusion.alphas.numpy(), m.diffusion.cumalphas.numpy()
+
+            def run(n):
+                return chain_ref.reverse_chain(sd, labels.numpy(), image, feat, al, ca, T, 10000 + n, "majority",
+                                               feature_condition_idx=10 if wl["fce"] else None, K=wl["K"])
+        t0 = time.perf_counter()
+        run(2)  # warm-up (allocator, mkldnn primitives)
+        per_step = (time.perf_counter() - t0) / 2
+        n = max(2, min(T, int(budget_s / max(per_step, 1e-6))))
+        if max_steps:
+            n = min(n, max_steps)
+        t0 = time.perf_counter()
+        run(n)
+        dt = time.perf_counter() - t0
+    per_step = dt / n
+    return dict(value=1.0 / (per_step * T), unit="samples/s", cores=torch.get_num_threads(), kind=kind,
+                sample=f"batch 1, {n} of {T} reverse steps of the same workload timed ({dt:.1f} s), extrapolated to the full chain",
+                ms_per_reverse_step=per_step * 1e3, host_cpus=os.cpu_count())
+
+
+def run_reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    rates = []
+    for i in range(args.warmup + steps):
+        r = cpu_chain_rate(wl, budget_s=max(2.0, 60.0 / (args.warmup + steps)))
+        if i >= args.warmup:
+            rates.append(r)
+    value = sum(r["value"] for r in rates) / len(rates)
+    base = rates[-1]
+    base["value"] = value
+    line = {"impl": "reference", "metric": "seg samples/sec (full T-step chain)", "value": value, "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "arm": "reference CPU path on host cores"}, "cpu_baseline": base,
+            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def op_bytes(o, esize):
+    """Algorithmic HBM bytes of one fused op: every input and output once."""
+    from ccdm_b200 import _lib
+    B = o.B
+    if o.kind == _lib.OP_INPUT_CONV:
+        return B * (o.Hin * o.Win * (1 + 4 * o.C_img) + o.Hout * o.Wout * o.Cout * esize)
+    if o.kind == _lib.OP_CONV:
+        n = o.Hin * o.Win * (o.C0 + o.C1) * esize + o.Hout * o.Wout * o.Cout * (4 if o.out_dtype == _lib.DT_F32 else 2)
+        n += o.Hout * o.Wout * (o.S0 + o.S1) * esize
+        if o.res:
+            n += o.Hout * o.Wout * o.Cout * esize
+        return B * n
+    if o.kind == _lib.OP_ATTENTION:
+        return B * o.Hin * o.Win * (o.C0 + o.Cout) * esize
+    if o.kind == _lib.OP_HEAD:
+        return B * o.Hin * o.Win * (4 * o.K + 2)
+    return 0
+
+
+def op_flops(o):
+    from ccdm_b200 import _lib
+    if o.kind in (_lib.OP_CONV, _lib.OP_INPUT_CONV):
+        cin = (o.K + o.C_img) if o.kind == _lib.OP_INPUT_CONV else (o.C0 + o.C1)
+        return 2.0 * o.B * o.Hout * o.Wout * o.Cout * (o.ksize * o.ksize * cin + o.S0 + o.S1)
+    if o.kind == _lib.OP_ATTENTION:
+        T = o.Hin * o.Win
+        return 4.0 * o.B * o.heads * T * T * o.head_dim
+    return 0.0
+
+
+def op_class(o):
+    from ccdm_b200 import _lib
+    if o.kind == _lib.OP_ATTENTION:
+        return f"attention T={o.Hin * o.Win} heads={o.heads}"
+    if o.kind == _lib.OP_HEAD:
+        return f"head K={o.K}"
+    if o.kind == _lib.OP_INPUT_CONV:
+        return f"input_conv {o.K}+{o.C_img}->{o.Cout} @{o.Hout}x{o.Wout}"
+    tag = "conv%dx%d" % (o.ksize, o.ksize) + ("/s2" if o.stride == 2 else "") + ("/up" if o.upsample else "")
+    return f"{tag} {o.C0 + o.C1}->{o.Cout}{'+skip' if o.S0 else ''} @{o.Hout}x{o.Wout}"
+
+
+def per_op_profile(engine, prog, n_iter=3):
+    """CUDA-event duration of every launch of one reverse step (eager launches on the engine stream),
+    averaged over n_iter steps; returns rows aggregated per op class."""
+    import ctypes
+    from ccdm_b200 import _lib
+    L = _lib.lib()
+    sp = _lib.stream_ptr(engine.stream)
+    n = prog.n_ops
+    acc = [0.0] * n
+    with torch.cuda.stream(engine.stream):
+        for it in range(n_iter + 1):
+            prog.step_counter.zero_()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+            ev[0].record(engine.stream)
+            for i in range(n):
+                _lib.check(L.ccdm_launch_op(ctypes.byref(prog._op_array[i]), sp), f"op {i}")
+                ev[i + 1].record(engine.stream)
+            engine.stream.synchronize()
+            if it:  # first pass is warm-up
+                for i in range(n):
+                    acc[i] += ev[i].elapsed_time(ev[i + 1]) / n_iter
+    esize = prog.esize
+    rows = {}
+    for i in range(n):
+        o = prog._op_array[i]
+        r = rows.setdefault(op_class(o), dict(ms=0.0, launches=0, bytes=0, flops=0.0))
+        r["ms"] += acc[i]
+        r["launches"] += 1
+        r["bytes"] += op_bytes(o, esize)
+        r["flops"] += op_flops(o)
+    return rows, sum(acc)
+
+
+def run_gpu_arm(args, wl):
+    from ccdm_b200 import _lib
+    from ccdm_b200.models.diffusion_denoising import reverse_t_values
+    from ccdm_b200.synthetic import synthetic_inputs
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.require_device()
+
+    B, T, K, H, W = args.batch or wl["B"], args.T or wl["T"], wl["K"], wl["H"], wl["W"]
+    wl = dict(wl, T=T)
+    m, _ = build_model(wl, dev)
+    m.precision, m.noise, m.seed, m.sample_offset = args.precision, "philox", 2024, rank * B
+    engine = m.unet.engine(args.precision)
+    image, feat, labels = synthetic_inputs(B, wl["C_img"], H, W, K, 384 if wl["fce"] else 0, seed=1234 + rank)
+    x_host = torch.nn.functional.one_hot(labels.long(), K).permute(0, 3, 1, 2).float().contiguous().pin_memory()
+    image_host = image.pin_memory()
+    feat_host = feat.pin_memory() if feat is not None else None
+    x_dev, image_dev = labels.to(dev), image.to(dev)
+    feat_dev = feat.to(dev) if feat is not None else None
+    ts = reverse_t_values(T, None)
+    al, ca = m._schedule_host()
+    gathered = torch.empty((world * B, H, W), dtype=torch.uint8, device=dev) if world > 1 else None
+
+    def chain_resident():
+        lab, _ = engine.run_chain(x_dev, image_dev, feat_dev, ts, al, ca, _lib.DRAW_MAJORITY, noise="philox", seed=2024,
+                                  sample0=rank * B)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, lab)  # the single collective of the path
+        return lab
+
+    def chain_e2e():
+        out = m(x_host.to(dev, non_blocking=True), image_host.to(dev, non_blocking=True),
+                feat_host.to(dev, non_blocking=True) if feat_host is not None else None)["diffusion_out"]
+        lab = out.argmax(dim=1).to(torch.uint8)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, lab)
+            return gathered.cpu()
+        return lab.cpu()
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        chain_resident()
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms_total = timed(chain_resident, args.steps)
+    clk = clocks.stop()
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step / 1e3)
+
+    chain_e2e()  # warm-up of the host path
+    ms_e2e = timed(chain_e2e, max(1, min(args.steps, 2))) / max(1, min(args.steps, 2))
+    e2e_value = world * B / (ms_e2e / 1e3)
+    h2d = x_host.numel() * 4 + image_host.numel() * 4 + (feat_host.numel() * 4 if feat_host is not None else 0)
+    d2h = world * B * H * W
+
+    prog = engine.program(B, H, W)
+    line = None
+    if rank == 0:
+        peaks = measured_peaks()
+        rows, step_ms_eager = per_op_profile(engine, prog)
+        top = max(rows.items(), key=lambda kv: kv[1]["ms"])
+        per_launch_ms = top[1]["ms"] / top[1]["launches"]
+        per_launch_bytes = top[1]["bytes"] / top[1]["launches"]
+        achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
+        esize = prog.esize
+        chain_bytes = (wl["elements"] * esize + 3 * K * H * W * 4) * B * T
+        roof_chain = chain_bytes / (ms_step * 1e-3) / 1e9
+        cpu = cpu_chain_rate(wl, budget_s=args.cpu_budget) if not args.no_cpu_baseline else None
+        line = {
+            "metric": "seg samples/sec (full T-step chain)", "value": value, "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": wl["name"], "batch_per_gpu": B, "T": T, "precision": args.precision,
+                       "noise": "philox (in-kernel)", "parallelism": f"sample-sharded x{world}, 1 NCCL all-gather of labels",
+                       "l2_policy": "per-step activation traffic exceeds L2 (126 MB): inputs larger than L2, no flush",
+                       "cuda_graph": True},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": prog.n_ops * T * args.steps,
+            "clocks": clk,
+            "roofline": {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                         "launches_per_step": top[1]["launches"], "avg_launch_ms": per_launch_ms,
+                         "share_of_step": top[1]["ms"] / step_ms_eager,
+                         "tflops": top[1]["flops"] / top[1]["launches"] / (per_launch_ms * 1e-3) / 1e12},
+            "roofline_chain": {"bound": "hbm", "achieved": roof_chain, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                               "frac": roof_chain / peaks["hbm_gbs"],
+                               "bytes_per_sample_step": chain_bytes / (B * T), "tflops": wl["flops"] * B * T / (ms_step * 1e-3) / 1e12},
+            "cpu_baseline": cpu,
+            "kernel_breakdown": sorted(([k, round(v["ms"], 4), v["launches"]] for k, v in rows.items()), key=lambda r: -r[1])[:12],
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="lidc", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default=os.environ.get("CCDM_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (parity/debug runs)")
+    ap.add_argument("--T", type=int, default=0, help="override the chain length (debug runs; invalid as a bench number)")
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference_arm(args, wl)
+    if args.warmup < 3:
+        sys.stderr.write("note: fewer than 3 warm-up chains; not a valid bench number\n")
+    run_gpu_arm(args, wl)
+
+
+if __name__ == "__main__":
+    main()

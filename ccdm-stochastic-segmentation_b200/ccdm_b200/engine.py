@@ -80,6 +80,24 @@ class Arena:
 # --------------------------------------------------------------------------------------
 # weights
 # --------------------------------------------------------------------------------------
+def pack_conv_weight(w: torch.Tensor, cin_pad: Optional[int] = None) -> torch.Tensor:
+    """OIHW (or OI1 for Conv1d) -> the kernels' [tap][CinP][CoutP] fp32 layout, zero padded
+    (CinP defaults to Cin, CoutP = ceil32(Cout))."""
+    if w.dim() == 3:
+        w = w[:, :, :, None]
+    co, ci, kh, kw = w.shape
+    cip = cin_pad or ci
+    out = torch.zeros(kh * kw, cip, _ceil(co, 32), dtype=torch.float32, device=w.device)
+    out[:, :ci, :co] = w.float().permute(2, 3, 1, 0).reshape(kh * kw, ci, co)
+    return out
+
+
+def pack_bias(b: torch.Tensor) -> torch.Tensor:
+    out = torch.zeros(_ceil(b.numel(), 32), dtype=torch.float32, device=b.device)
+    out[:b.numel()] = b.float()
+    return out
+
+
 class PackedWeights:
     """All kernel-layout parameters in one flat fp32 device buffer with stable addresses."""
 
@@ -153,18 +171,7 @@ class PackedWeights:
             v.zero_()
             v[:t.numel()].copy_(t.reshape(-1))
 
-        def conv_w(w, cin_pad=None):  # OIHW -> [tap][CinP][CoutP]
-            co, ci, kh, kw = w.shape
-            cip = cin_pad or ci
-            cop = _ceil(co, 32)
-            out = torch.zeros(kh * kw, cip, cop, dtype=torch.float32, device=self.device)
-            out[:, :ci, :co] = w.permute(2, 3, 1, 0).reshape(kh * kw, ci, co)
-            return out
-
-        def padded(b):
-            out = torch.zeros(_ceil(b.numel(), 32), dtype=torch.float32, device=self.device)
-            out[:b.numel()] = b
-            return out
+        conv_w, padded = pack_conv_weight, pack_bias
 
         put("te0_w", sd["time_embed.0.weight"]); put("te0_b", sd["time_embed.0.bias"])
         put("te2_w", sd["time_embed.2.weight"]); put("te2_b", sd["time_embed.2.bias"])
@@ -439,6 +446,19 @@ class Program:
         if not self.plan:
             raise _lib.CcdmError("ccdm_plan_create failed: " + L.ccdm_last_error().decode())
 
+    def set_noise(self, noise_mode: int, seed: int = 0, sample0: int = 0, use_noise_buf: bool = False,
+                  export_noise: bool = False):
+        """Per-run fields of the head op, on the C plan and on the host mirror used for single launches."""
+        L = _lib.lib()
+        nz = self.noise.data_ptr() if use_noise_buf else 0
+        nz_out = self.noise.data_ptr() if export_noise else 0
+        _lib.check(L.ccdm_plan_set_noise(self.plan, noise_mode, int(seed), int(sample0), ctypes.c_void_p(nz or None),
+                                         ctypes.c_void_p(nz_out or None)), "plan_set_noise")
+        for i in range(self.n_ops):
+            if self._op_array[i].kind == _lib.OP_HEAD:
+                o = self._op_array[i]
+                o.noise_mode, o.seed, o.sample0, o.noise, o.noise_out = noise_mode, int(seed), int(sample0), nz, nz_out
+
     def __del__(self):
         try:
             if self.plan is not None:
@@ -552,7 +572,7 @@ class UNetEngine:
             prog = self.program(B, H, W, rows_per_sample=1)
             self._load_inputs(prog, x, condition, feature_condition)
             self._write_tables(prog, [(ts[0], 0.0, 1.0, _lib.DRAW_X0, 0, 0)], ts)
-            _lib.check(L.ccdm_plan_set_noise(prog.plan, _lib.NOISE_PHILOX, 0, 0, None, None))
+            prog.set_noise(_lib.NOISE_PHILOX)
             _lib.check(L.ccdm_plan_step(prog.plan, 0, self._sp()), "plan_step")
             out = prog.probs.clone()
         cur.wait_stream(self.stream)
@@ -602,9 +622,8 @@ class UNetEngine:
             self._write_tables(prog, entries, [float(t) for t in t_values])
             use_tensor = noise == "torch"
             want_noise_out = record is not None and not use_tensor
-            _lib.check(L.ccdm_plan_set_noise(prog.plan, _lib.NOISE_TENSOR if use_tensor else _lib.NOISE_PHILOX, int(seed),
-                                             int(sample0), prog.noise.data_ptr() if use_tensor else None,
-                                             prog.noise.data_ptr() if want_noise_out else None), "set_noise")
+            prog.set_noise(_lib.NOISE_TENSOR if use_tensor else _lib.NOISE_PHILOX, seed, sample0, use_noise_buf=use_tensor,
+                           export_noise=want_noise_out)
             if not use_tensor and record is None:
                 _lib.check(L.ccdm_plan_run(prog.plan, n, 1 if self.use_graph else 0, self._sp()), "plan_run")
             else:
@@ -626,6 +645,39 @@ class UNetEngine:
             probs = prog.probs.clone() if last_mode == _lib.DRAW_CONFIDENCE and t_values[-1] == 1 else None
         cur.wait_stream(self.stream)
         return labels, probs
+
+    @torch.no_grad()
+    def trace_step(self, x, condition, feature_condition, t: float, alpha=0.0, cumalpha=1.0, mode=_lib.DRAW_X0):
+        """Debug/test aid: run ONE step op by op and return {tensor name: NHWC fp32 copy} of every
+        op output (the liveness-planned workspace recycles buffers, so a finished step only holds
+        the tail).  Same kernels, same order as the captured graph."""
+        L = _lib.lib()
+        if x.dim() == 4:
+            B, _, H, W = x.shape
+        else:
+            B, H, W = x.shape
+        out = {}
+        cur = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            self.weights.refresh()
+            prog = self.program(B, H, W, rows_per_sample=0)
+            self._load_inputs(prog, x, condition, feature_condition)
+            self._write_tables(prog, [(float(t), alpha, cumalpha, mode, 0, 0)], [float(t)])
+            prog.set_noise(_lib.NOISE_PHILOX)
+            for i, o in enumerate(prog._op_dicts):
+                _lib.check(L.ccdm_launch_op(ctypes.byref(prog._op_array[i]), self._sp()), f"op {i}")
+                ten = o["_out"]
+                if ten is not None:
+                    out[ten.name] = self.tensor_view(prog, ten).float().clone()
+                    if ten.want_stat:
+                        soff = ten.stat_addr - prog.workspace.data_ptr()
+                        out[ten.name + "#stat"] = prog.workspace[soff:soff + B * ten.C * 16].view(torch.float64).view(B, ten.C, 2).clone()
+            out["probs"] = prog.probs.clone()
+            out["labels"] = prog.labels.clone()
+        cur.wait_stream(self.stream)
+        torch.cuda.synchronize(self.device)
+        return out
 
     def tensor_view(self, prog: Program, t: Ten) -> torch.Tensor:
         dtype = torch.float32 if t.esize == 4 else torch.bfloat16

@@ -1,0 +1,141 @@
+"""Helpers for the GPU parity tests: build single ops through the C ABI on torch-owned buffers."""
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from ccdm_b200 import _lib
+from ccdm_b200.engine import pack_bias, pack_conv_weight
+
+
+def sp():
+    return _lib.stream_ptr(torch.cuda.current_stream())
+
+
+def nhwc(x, dtype=torch.float32):
+    """NCHW cpu/gpu -> contiguous NHWC on the GPU."""
+    return x.permute(0, 2, 3, 1).contiguous().to("cuda", dtype)
+
+
+def stats_of(x_nhwc):
+    """double [B,C,2] = (sum, sum of squares) over pixels, as the producing kernel would emit."""
+    xd = x_nhwc.double()
+    return torch.stack([xd.sum(dim=(1, 2)), (xd * xd).sum(dim=(1, 2))], dim=-1).contiguous()
+
+
+class StepCtx:
+    """A one-row step table + counter on the device."""
+
+    def __init__(self, t=0.0, alpha=0.0, cum=1.0, mode=_lib.DRAW_X0, draw=0, emb_row=0):
+        e = _lib.StepEntry(float(t), float(alpha), float(cum), int(mode), int(draw), int(emb_row), 0, 0)
+        self.table = torch.frombuffer(bytearray(bytes(e)), dtype=torch.uint8).cuda()
+        self.counter = torch.zeros(1, dtype=torch.int32, device="cuda")
+
+
+def run_conv(srcs, weight, bias, *, gn=None, silu=False, ksize=3, stride=1, upsample=False, skip=None, skip_w=None,
+             res=None, emb=None, dtype=torch.float32, out_f32=False, want_stat=True, labels=None, image=None, K=0):
+    """Launch one CCDM_OP_CONV.  srcs: list of NHWC GPU tensors (1 or 2) or [] with labels/image.
+    weight: OIHW fp32 (cpu or gpu); gn: (gamma, beta) or None; skip: list of NHWC tensors for the fused
+    1x1 skip conv with skip_w [Cout, Cin_skip, 1, 1]; res: NHWC residual; emb: fp32 [B or 1, Cout] rows.
+    Returns (out NHWC, ostat or None)."""
+    L = _lib.lib()
+    dev = "cuda"
+    one_hot_in = labels is not None
+    if one_hot_in:
+        B, Hin, Win = labels.shape
+        C_img = image.shape[1]
+        cin = K + C_img
+    else:
+        B, Hin, Win, _ = srcs[0].shape
+        cin = sum(s.shape[3] for s in srcs)
+    Cout = weight.shape[0]
+    Hout = Hin * 2 if upsample else ((Hin + 1) // 2 if stride == 2 else Hin)
+    Wout = Win * 2 if upsample else ((Win + 1) // 2 if stride == 2 else Win)
+    keep = []
+    wp = pack_conv_weight(weight.to(dev), (cin + 7) // 8 * 8 if one_hot_in else None).contiguous()
+    b = bias.to(dev).float()
+    if skip is not None:
+        assert skip_w is not None
+    bp = pack_bias(b)
+    out_dtype = torch.float32 if (out_f32 or dtype == torch.float32) else torch.bfloat16
+    out = torch.full((B, Hout, Wout, Cout), float("nan"), dtype=out_dtype, device=dev)
+    op = _lib.Op(kind=_lib.OP_CONV, dtype=_lib.DT_F32 if dtype == torch.float32 else _lib.DT_BF16,
+                 out_dtype=_lib.DT_F32 if out_dtype == torch.float32 else _lib.DT_BF16, B=B, Hin=Hin, Win=Win, Hout=Hout,
+                 Wout=Wout, Cout=Cout, ksize=ksize, stride=stride, upsample=int(upsample), gn=int(gn is not None),
+                 silu=int(silu), exact=1)
+    op.weight, op.bias, op.out = wp.data_ptr(), bp.data_ptr(), out.data_ptr()
+    if one_hot_in:
+        op.kind = _lib.OP_INPUT_CONV
+        op.src_kind, op.K, op.C_img = 1, K, C_img
+        lab = labels.to(dev, torch.uint8).contiguous()
+        img = image.to(dev, torch.float32).contiguous()
+        keep += [lab, img]
+        op.labels_in, op.image = lab.data_ptr(), img.data_ptr()
+    else:
+        op.src0, op.C0 = srcs[0].data_ptr(), srcs[0].shape[3]
+        if len(srcs) > 1:
+            op.src1, op.C1 = srcs[1].data_ptr(), srcs[1].shape[3]
+        if gn is not None:
+            st = [stats_of(s) for s in srcs]
+            keep += st
+            op.stat0 = st[0].data_ptr()
+            if len(srcs) > 1:
+                op.stat1 = st[1].data_ptr()
+            g, be = gn[0].to(dev).float().contiguous(), gn[1].to(dev).float().contiguous()
+            keep += [g, be]
+            op.gamma, op.beta = g.data_ptr(), be.data_ptr()
+    if skip is not None:
+        sw = skip_w.to(dev).float()[:, :, 0, 0].t().contiguous()
+        keep.append(sw)
+        op.skip0, op.S0 = skip[0].data_ptr(), skip[0].shape[3]
+        if len(skip) > 1:
+            op.skip1, op.S1 = skip[1].data_ptr(), skip[1].shape[3]
+        op.skip_w = sw.data_ptr()
+    if res is not None:
+        op.res = res.data_ptr()
+    ctx = StepCtx()
+    keep.append(ctx)
+    op.steps, op.step_ptr = ctx.table.data_ptr(), ctx.counter.data_ptr()
+    if emb is not None:
+        e = emb.to(dev).float().contiguous()
+        keep.append(e)
+        op.emb, op.emb_off, op.emb_cols = e.data_ptr(), 0, e.shape[1]
+        op.emb_bstride = 1 if e.shape[0] == B and B > 1 else 0
+    ostat = None
+    if want_stat:
+        ostat = torch.full((B, Cout, 2), float("nan"), dtype=torch.float64, device=dev)
+        part = torch.zeros(L.ccdm_conv_part_floats(B, Hout, Wout, Cout), dtype=torch.float32, device=dev)
+        ticket = torch.zeros(B, dtype=torch.int32, device=dev)
+        keep += [part, ticket]
+        op.ostat, op.part, op.ticket = ostat.data_ptr(), part.data_ptr(), ticket.data_ptr()
+    _lib.check(L.ccdm_launch_op(ctypes.byref(op), sp()), "conv")
+    torch.cuda.synchronize()
+    if want_stat:
+        assert int(ticket.abs().sum()) == 0, "ticket counters must self-reset"
+    return out, ostat
+
+
+def ref_conv(srcs_nchw, weight, bias, *, gn=None, silu=False, stride=1, upsample=False, skip=None, skip_w=None,
+             skip_b=None, res=None, emb=None):
+    """fp32 CPU torch reference of the same fused op (NCHW)."""
+    x = torch.cat([s.float().cpu() for s in srcs_nchw], dim=1)
+    h = x
+    if gn is not None:
+        h = F.group_norm(h, 32, gn[0].float().cpu(), gn[1].float().cpu(), eps=1e-5)
+    if silu:
+        h = F.silu(h)
+    if upsample:
+        h = F.interpolate(h, scale_factor=2, mode="nearest")
+    h = F.conv2d(h, weight.float().cpu(), bias.float().cpu(), stride=stride, padding=weight.shape[-1] // 2)
+    if emb is not None:
+        h = h + emb.float().cpu()[:, :, None, None]
+    if skip is not None:
+        h = h + F.conv2d(torch.cat([s.float().cpu() for s in skip], dim=1), skip_w.float().cpu(), skip_b)
+    if res is not None:
+        h = h + res.float().cpu()
+    return h
+
+
+def max_err(a, b):
+    return float((a.double().cpu() - b.double().cpu()).abs().max())

@@ -1,0 +1,223 @@
+"""Host-side logic, CPU only: the reference-shaped surface, program planning, the C ABI."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import DINO, GOLDEN, REFERENCE, ROOT, UNET_PARAMS, build_ours, golden
+
+
+def _build(C, H, W, K, fce, mult, base=32, **kw):
+    from ccdm_b200 import models
+    p = dict(UNET_PARAMS, channel_mult=mult, base_channels=base)
+    p.update(kw)
+    return models.build_model(250, "cosine", {"s": 0.008}, [(C, H, W), (K, H, W)], (C, H, W), "unet_openai", p, "d",
+                              "majority", DINO if fce else None)
+
+
+def test_state_dict_layout_matches_reference_manifest():
+    """Key names, order and shapes of state_dict() for five configurations, recorded from the reference."""
+    man = json.load(open(os.path.join(GOLDEN, "state_dict_manifest.json")))
+    for tag, rec in man.items():
+        C, H, W, K, fce, mult, base = rec["args"]
+        m = _build(C, H, W, K, fce, tuple(mult) if mult else None, base)
+        got = [[k, list(v.shape)] for k, v in m.state_dict().items()]
+        assert got == rec["keys"], tag
+
+
+def test_schedule_buffers_bit_identical_to_reference():
+    from ccdm_b200.models import DiffusionModel
+    g = golden("schedules.npz")
+    for T in (100, 250, 1000):
+        d = DiffusionModel("cosine", T, 2, {"s": 0.008})
+        for n in ("betas", "alphas", "cumalphas"):
+            np.testing.assert_array_equal(getattr(d, n).numpy(), g[f"cosine{T}_{n}"])
+    d = DiffusionModel("linear", 250, 2, None)
+    for n in ("betas", "alphas", "cumalphas"):
+        np.testing.assert_array_equal(getattr(d, n).numpy(), g[f"linear250_{n}"])
+    assert d.time_steps == 250
+    assert d.step_scalars(1) == (0.0, 1.0)
+    assert d.step_scalars(2) == (float(d.alphas[1]), float(d.cumalphas[0]))
+
+
+def test_reverse_t_values_match_reference_and_oracle():
+    from ccdm_b200.models.diffusion_denoising import reverse_t_values
+    from oracle import cdm
+    g = golden("t_values.npz")
+    for key in g.files:
+        T, req = key[1:].split("_req")
+        req = None if req == "None" else int(req)
+        assert reverse_t_values(int(T), req) == g[key].tolist() == cdm.t_values(int(T), req)
+    with pytest.raises(AssertionError):
+        reverse_t_values(250, 10000 + 300)
+
+
+def test_constructor_surface_and_errors():
+    from ccdm_b200 import models
+    from ccdm_b200.models.unet_openai import create_unet_openai
+    with pytest.raises(NotImplementedError, match="backbone resnet50"):
+        models.build_model(250, "cosine", None, [(1, 64, 64), (2, 64, 64)], None, "resnet50", {}, "d")
+    with pytest.raises(ValueError, match="unsupported image size"):
+        create_unet_openai(100, 32, 3, 2, 2, None)
+    for flag in ("use_fp16", "use_scale_shift_norm", "resblock_updown", "use_new_attention_order", "ce_head"):
+        with pytest.raises(NotImplementedError):
+            create_unet_openai(64, 32, 3, 2, 2, None, **{flag: True})
+    with pytest.raises(KeyError):
+        models.DiffusionModel("quadratic", 10, 2)
+    m = _build(1, 64, 64, 2, False, None)
+    assert m.unet.in_channels == 3 and m.unet.out_channels == 2 and m.unet.model_channels == 32
+    assert m.unet.channel_mult == (1, 2, 3, 4) and m.time_steps == 250 and m.diffusion.num_classes == 2
+    assert m.step_T_sample == "majority" and m.dataset_file == "d" and m.unet.feature_condition_idx == []
+    assert _build(3, 256, 512, 20, True, None).unet.feature_condition_idx == [10]
+    # fresh constructor = the reference's degenerate zero-initialised heads (unet.py:216-218,300,705)
+    sd = m.unet.state_dict()
+    assert float(sd["out.2.weight"].abs().sum()) == 0 and float(sd["input_blocks.1.0.out_layers.3.weight"].abs().sum()) == 0
+    assert float(sd["middle_block.1.proj_out.weight"].abs().sum()) == 0
+    assert float(sd["out.0.weight"].min()) == 1.0
+
+
+def test_forward_dispatch_errors_without_gpu():
+    m = build_ours(250, 1, 64, 64, 2)
+    x = torch.zeros(1, 2, 64, 64)
+    m.train()
+    with pytest.raises(ValueError, match="'t' needs to be a Tensor"):
+        m(x, torch.zeros(1, 1, 64, 64), None, None)
+    m.eval()
+    with pytest.raises(NotImplementedError):
+        m(x, torch.zeros(1, 1, 64, 64), None, label_ref_logits=torch.zeros(1))
+    if not torch.cuda.is_available():
+        from ccdm_b200 import _lib
+        with pytest.raises(_lib.CcdmError):  # no CPU fallback
+            m(x, torch.zeros(1, 1, 64, 64), None)
+
+
+def test_onehot_categorical_matches_torch_distributions():
+    from ccdm_b200.models import OneHotCategoricalBCHW
+    g = golden("draw.npz")
+    for K in (2, 20):
+        p = torch.as_tensor(g[f"K{K}_probs_in"]).permute(0, 3, 1, 2).contiguous()  # NCHW memory, as in the fixture
+        torch.manual_seed(1000 + K)
+        s = OneHotCategoricalBCHW(probs=p).sample()
+        assert s.dtype == torch.float32 and not s.is_contiguous()
+        np.testing.assert_array_equal(s.argmax(1).numpy(), g[f"K{K}_sample_labels"])
+        d = OneHotCategoricalBCHW(probs=p)
+        assert d.max_prob_sample().dtype == torch.int64
+        np.testing.assert_array_equal(d.max_prob_sample().argmax(1).numpy(), g[f"K{K}_majority_labels"])
+        np.testing.assert_array_equal(d.prob_sample().permute(0, 2, 3, 1).numpy(), g[f"K{K}_confidence"])
+        torch.manual_seed(2000 + K)
+        xT = OneHotCategoricalBCHW(logits=torch.zeros(p.shape)).sample()
+        np.testing.assert_array_equal(xT.argmax(1).numpy(), g[f"K{K}_xT_labels"])
+    with pytest.raises(ValueError):
+        OneHotCategoricalBCHW(probs=torch.ones(3))
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from ccdm_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "ccdm_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    names = set(re.findall(r"\b(ccdm_[a-z0-9_]+)\s*\(", header))
+    assert len(names) >= 18
+    L = _lib.lib()  # also checks ABI version and struct sizes against the ctypes mirrors
+    for n in sorted(names):
+        assert hasattr(L, n), f"{n} declared in include/ccdm_b200.h but not exported"
+    assert L.ccdm_abi_version() == _lib.ABI_VERSION
+    assert ctypes.sizeof(_lib.StepEntry) == 32
+
+
+@pytest.mark.parametrize("cfg", [(1, 128, 128, 2, False, 3), (3, 256, 512, 20, True, 1), (1, 64, 64, 2, False, 2)])
+def test_program_planning_dry_run(cfg):
+    """Op list, liveness-planned workspace and struct marshalling, without a GPU."""
+    from ccdm_b200 import _lib
+    C, H, W, K, fce, B = cfg
+    m = _build(C, H, W, K, fce, None)
+    eng = m.unet.engine("fp32", dry_run=True)
+    eng.weights.refresh()
+    prog = eng.program(B, H, W)
+    prog.bind(250)
+    ops = prog._op_array
+    kinds = [o.kind for o in ops]
+    assert kinds[0] == _lib.OP_INPUT_CONV and kinds[-1] == _lib.OP_HEAD and kinds[-2] == _lib.OP_CONV
+    n_res = sum(1 for b in m.unet.arch.blocks for l in b.layers if l.kind == "res")
+    n_att = sum(1 for b in m.unet.arch.blocks for l in b.layers if l.kind == "attn")
+    n_updown = sum(1 for b in m.unet.arch.blocks for l in b.layers if l.kind in ("up", "down"))
+    assert len(ops) == 1 + 2 * n_res + 3 * n_att + n_updown + 2
+    assert kinds.count(_lib.OP_ATTENTION) == n_att
+    # no live tensor overlaps another one it coexists with
+    tens = sorted(prog.tens.values(), key=lambda t: t.off)
+    for i, a in enumerate(tens):
+        for b in tens[i + 1:]:
+            if b.off >= a.off + a.nbytes:
+                break
+            assert a.last < b.born or b.last < a.born, (a.name, b.name)
+    # every op reads tensors that are alive and writes inside the arena
+    lo, hi = prog.addr["arena"], prog.addr["arena"] + prog.arena_bytes
+    for o in ops:
+        if o.kind in (_lib.OP_CONV, _lib.OP_INPUT_CONV, _lib.OP_ATTENTION):
+            assert lo <= o.out < hi
+            assert o.B == B and o.Cout > 0
+        if o.kind == _lib.OP_CONV and o.gn:
+            assert o.stat0 and o.gamma and o.beta and (o.C0 + o.C1) % 32 == 0
+    # concat never materialised: output blocks read two sources
+    assert sum(1 for o in ops if o.kind == _lib.OP_CONV and o.C1 > 0) == sum(1 for b in m.unet.arch.blocks if b.stage == "out" or b.feat_concat)
+    assert sum(1 for o in ops if o.S0 > 0) == sum(1 for b in m.unet.arch.blocks for l in b.layers if l.kind == "res" and l.skip_conv)
+    # reuse actually happens
+    assert prog.arena_bytes < 0.6 * sum(t.nbytes for t in prog.tens.values())
+    with pytest.raises(_lib.CcdmError):
+        eng.run_chain(torch.zeros(B, K, H, W), torch.zeros(B, C, H, W), None, [1], [0.0], [1.0], 1)
+
+
+def test_weight_packing_layout():
+    from ccdm_b200.engine import pack_bias, pack_conv_weight
+    w = torch.arange(2 * 3 * 3 * 3, dtype=torch.float32).reshape(2, 3, 3, 3)
+    p = pack_conv_weight(w, 8)
+    assert p.shape == (9, 8, 32)
+    assert p[4, 1, 1] == w[1, 1, 1, 1] and p[2, 2, 0] == w[0, 2, 0, 2] and float(p[:, 3:, :].abs().sum()) == 0
+    assert float(p[:, :, 2:].abs().sum()) == 0
+    q = pack_conv_weight(torch.ones(96, 32, 1))
+    assert q.shape == (1, 32, 96)
+    assert pack_bias(torch.ones(20)).shape == (32,)
+    m = build_ours(250, 1, 64, 64, 2)
+    eng = m.unet.engine("fp32", dry_run=True)
+    assert eng.weights.refresh() is True and eng.weights.refresh() is False
+    with torch.no_grad():
+        m.unet.time_embed._modules["0"].bias.add_(1.0)
+    assert eng.weights.refresh() is True  # in-place writes are seen (polyak.py:18-26 hazard)
+    sd = m.unet.state_dict()
+    np.testing.assert_array_equal(eng.weights.view("te0_b").numpy(), sd["time_embed.0.bias"].numpy())
+    cols = m.unet.arch.emb_cols
+    first = next(l for b in m.unet.arch.blocks for l in b.layers if l.kind == "res")
+    np.testing.assert_array_equal(eng.weights.view("emb_w")[:first.cout * 128].reshape(first.cout, 128).numpy(),
+                                  sd[first.path + ".emb_layers.1.weight"].numpy())
+    assert cols == sum(l.cout for b in m.unet.arch.blocks for l in b.layers if l.kind == "res")
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present (GPU box)")
+def test_live_reference_agrees_with_oracle_on_fresh_seed():
+    """Beyond the committed fixtures: a different seed / shape, reference imported live."""
+    import sys
+    sys.path.insert(0, REFERENCE)
+    import models as ref_models
+    from ccdm_b200.synthetic import fill_synthetic_, synthetic_inputs
+    from oracle import chain_ref, unet_ref
+    sys.path.remove(REFERENCE)
+    p = dict(UNET_PARAMS)
+    torch.manual_seed(3)
+    ref = ref_models.build_model(100, "cosine", {"s": 0.008}, [(1, 64, 64), (2, 64, 64)], (1, 64, 64), "unet_openai", p,
+                                 "datasets.lidc", "confidence", None).eval()
+    fill_synthetic_(ref.unet, 5)
+    ours = build_ours(100, 1, 64, 64, 2, "confidence", seed=5)
+    for (k, a), (k2, b) in zip(ref.state_dict().items(), ours.state_dict().items()):
+        assert k == k2 and torch.equal(a, b)
+    image, _, labels = synthetic_inputs(1, 1, 64, 64, 2, seed=99)
+    x = chain_ref.labels_to_onehot(labels.numpy(), 2)
+    torch.manual_seed(8)
+    with torch.no_grad():
+        out = ref(x, image, None, t=torch.as_tensor(10005))["diffusion_out"]
+    torch.manual_seed(8)
+    _, probs = chain_ref.reverse_chain(ours.unet.state_dict(), labels.numpy(), image, None, ours.diffusion.alphas.numpy(),
+                                       ours.diffusion.cumalphas.numpy(), 100, 10005, "confidence", K=2)
+    np.testing.assert_allclose(probs, out.permute(0, 2, 3, 1).numpy(), rtol=0, atol=2e-6)
