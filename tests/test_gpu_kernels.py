@@ -36,7 +36,7 @@ def _posterior_draw(L, theta, labels, a, c, mode, noise=None, philox=None):
     from ccdm_b200 import _lib
     B = theta.shape[0]
     K = theta.shape[-1]
-    n_pix = theta[0].numel() // K
+    n_pix = int(np.asarray(theta[0]).size) // K
     th = torch.as_tensor(theta).cuda().contiguous()
     lab = torch.as_tensor(labels).cuda().contiguous()
     out_l = torch.full(lab.shape, 255, dtype=torch.uint8, device="cuda")
