@@ -82,6 +82,9 @@ def lib():
                                    ctypes.c_void_p, ctypes.c_void_p]
     L.ccdm_uniform_labels.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int,
                                       ctypes.c_void_p, ctypes.c_void_p]
+    L.ccdm_op_part_floats.restype = ctypes.c_size_t
+    L.ccdm_op_part_floats.argtypes = [ctypes.POINTER(Op)]
+    L.ccdm_conv_uses_tc.argtypes = [ctypes.POINTER(Op)]
     L.ccdm_conv_part_floats.restype = ctypes.c_size_t
     L.ccdm_conv_part_floats.argtypes = [ctypes.c_int] * 4
     if L.ccdm_abi_version() != ABI_VERSION:

@@ -347,7 +347,20 @@ size_t conv_part_floats(int B, int Hout, int Wout, int Cout) {
     return size_t(B) * tiles * CoutP * 2;
 }
 
+bool conv_tc_supported(const ccdm_op &op);
+size_t conv_tc_part_floats(const ccdm_op &op);
+int launch_conv_tc(const ccdm_op &op, cudaStream_t s);
+
+bool conv_uses_tc(const ccdm_op &op) { return !op.exact && op.kind == CCDM_OP_CONV && conv_tc_supported(op); }
+
+size_t op_part_floats(const ccdm_op &op) {
+    if (op.kind != CCDM_OP_CONV && op.kind != CCDM_OP_INPUT_CONV) return 0;
+    if (conv_uses_tc(op)) return conv_tc_part_floats(op);
+    return conv_part_floats(op.B, op.Hout, op.Wout, op.Cout);
+}
+
 int launch_conv(const ccdm_op &op, cudaStream_t s) {
+    if (conv_uses_tc(op)) return launch_conv_tc(op, s);
     ConvP p{};
     p.src0 = (const void *)op.src0; p.src1 = (const void *)op.src1;
     p.stat0 = (const double *)op.stat0; p.stat1 = (const double *)op.stat1;

@@ -92,6 +92,19 @@ def pack_conv_weight(w: torch.Tensor, cin_pad: Optional[int] = None) -> torch.Te
     return out
 
 
+def pack_conv_weight_tc(w: torch.Tensor) -> torch.Tensor:
+    """OIHW (or OI1) -> the tcgen05 kernel's bf16 [tap][Cin/8][ceil16(Cout)][8] layout: every
+    (tap, 8-channel plane) is Cout rows of 16 bytes = the UMMA K-major no-swizzle canonical form."""
+    if w.dim() == 3:
+        w = w[:, :, :, None]
+    co, ci, kh, kw = w.shape
+    assert ci % 8 == 0
+    cop = _ceil(co, 16)
+    out = torch.zeros(kh * kw, ci // 8, cop, 8, dtype=torch.bfloat16, device=w.device)
+    out[:, :, :co, :] = w.float().permute(2, 3, 1, 0).reshape(kh * kw, ci // 8, 8, co).permute(0, 1, 3, 2).to(torch.bfloat16)
+    return out
+
+
 def pack_bias(b: torch.Tensor) -> torch.Tensor:
     out = torch.zeros(_ceil(b.numel(), 32), dtype=torch.float32, device=b.device)
     out[:b.numel()] = b.float()
@@ -101,18 +114,27 @@ def pack_bias(b: torch.Tensor) -> torch.Tensor:
 class PackedWeights:
     """All kernel-layout parameters in one flat fp32 device buffer with stable addresses."""
 
-    def __init__(self, unet, device):
+    def __init__(self, unet, device, with_tc: bool = False):
         self.unet = unet
         self.device = device
         self.slots: Dict[str, tuple] = {}  # name -> (offset_floats, numel)
         self.total = 0
         self.buf: Optional[torch.Tensor] = None
+        self.with_tc = with_tc            # also keep bf16 tensor-core layouts of every stride-1 conv
+        self.slots16: Dict[str, tuple] = {}
+        self.total16 = 0
+        self.buf16: Optional[torch.Tensor] = None
         self._stamp = None
         self._layout()
 
-    def _reserve(self, name, numel):
+    def _reserve(self, name, numel, tc_shape=None):
         self.slots[name] = (self.total, numel)
         self.total += _ceil(numel, ALIGN // 4)
+        if tc_shape is not None and self.with_tc:
+            taps, ci, co = tc_shape
+            n16 = taps * ci * _ceil(co, 16)
+            self.slots16[name] = (self.total16, n16)
+            self.total16 += _ceil(n16, ALIGN // 2)
 
     def _layout(self):
         arch = self.unet.arch
@@ -129,26 +151,29 @@ class PackedWeights:
                     self._reserve(p + ":w", 9 * _ceil(L.cin, 8) * _ceil(L.cout, 32))
                     self._reserve(p + ":b", _ceil(L.cout, 32))
                 elif L.kind in ("down", "up"):
-                    self._reserve(p + ":w", 9 * L.cin * _ceil(L.cout, 32))
+                    self._reserve(p + ":w", 9 * L.cin * _ceil(L.cout, 32), (9, L.cin, L.cout) if L.kind == "up" else None)
                     self._reserve(p + ":b", _ceil(L.cout, 32))
                 elif L.kind == "res":
                     self._reserve(p + ":g1", L.cin); self._reserve(p + ":be1", L.cin)
-                    self._reserve(p + ":w1", 9 * L.cin * L.cout); self._reserve(p + ":b1", L.cout)
+                    self._reserve(p + ":w1", 9 * L.cin * L.cout, (9, L.cin, L.cout)); self._reserve(p + ":b1", L.cout)
                     self._reserve(p + ":g2", L.cout); self._reserve(p + ":be2", L.cout)
-                    self._reserve(p + ":w2", 9 * L.cout * L.cout); self._reserve(p + ":b2", L.cout)
+                    self._reserve(p + ":w2", 9 * L.cout * L.cout, (9, L.cout, L.cout)); self._reserve(p + ":b2", L.cout)
                     if L.skip_conv:
-                        self._reserve(p + ":ws", L.cin * L.cout)
+                        self._reserve(p + ":ws", L.cin * L.cout, (1, L.cin, L.cout))
                 elif L.kind == "attn":
                     self._reserve(p + ":g", L.cin); self._reserve(p + ":be", L.cin)
-                    self._reserve(p + ":wqkv", L.cin * 3 * L.cin); self._reserve(p + ":bqkv", 3 * L.cin)
-                    self._reserve(p + ":wproj", L.cin * L.cin); self._reserve(p + ":bproj", L.cin)
+                    self._reserve(p + ":wqkv", L.cin * 3 * L.cin, (1, L.cin, 3 * L.cin)); self._reserve(p + ":bqkv", 3 * L.cin)
+                    self._reserve(p + ":wproj", L.cin * L.cin, (1, L.cin, L.cin)); self._reserve(p + ":bproj", L.cin)
         K = self.unet.out_channels
         c_head = int(self.unet.channel_mult[0] * mc)
         self._reserve("out:g", c_head); self._reserve("out:be", c_head)
-        self._reserve("out:w", 9 * c_head * _ceil(K, 32)); self._reserve("out:b", _ceil(K, 32))
+        self._reserve("out:w", 9 * c_head * _ceil(K, 32), (9, c_head, K)); self._reserve("out:b", _ceil(K, 32))
 
     def addr(self, name) -> int:
         return self.buf.data_ptr() + 4 * self.slots[name][0]
+
+    def addr16(self, name) -> int:
+        return self.buf16.data_ptr() + 2 * self.slots16[name][0]
 
     def view(self, name) -> torch.Tensor:
         off, n = self.slots[name]
@@ -164,12 +189,18 @@ class PackedWeights:
             return False
         if self.buf is None:
             self.buf = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+            self.buf16 = torch.zeros(max(self.total16, 8), dtype=torch.bfloat16, device=self.device)
         sd = {k: v.detach().to(device=self.device, dtype=torch.float32) for k, v in self.unet.state_dict().items()}
 
-        def put(name, t):
+        def put(name, t, raw=None):
             v = self.view(name)
             v.zero_()
             v[:t.numel()].copy_(t.reshape(-1))
+            if raw is not None and name in self.slots16:
+                off, n = self.slots16[name]
+                tc = pack_conv_weight_tc(raw).reshape(-1)
+                assert tc.numel() == n, (name, tc.numel(), n)
+                self.buf16[off:off + n].copy_(tc)
 
         conv_w, padded = pack_conv_weight, pack_bias
 
@@ -182,26 +213,26 @@ class PackedWeights:
                 if L.kind == "conv_in":
                     put(p + ":w", conv_w(sd[p + ".weight"], _ceil(L.cin, 8))); put(p + ":b", padded(sd[p + ".bias"]))
                 elif L.kind in ("down", "up"):
-                    put(p + ":w", conv_w(sd[p + ".weight"])); put(p + ":b", padded(sd[p + ".bias"]))
+                    put(p + ":w", conv_w(sd[p + ".weight"]), sd[p + ".weight"]); put(p + ":b", padded(sd[p + ".bias"]))
                 elif L.kind == "res":
                     put(p + ":g1", sd[p + ".in_layers.0.weight"]); put(p + ":be1", sd[p + ".in_layers.0.bias"])
-                    put(p + ":w1", conv_w(sd[p + ".in_layers.2.weight"])); put(p + ":b1", sd[p + ".in_layers.2.bias"])
+                    put(p + ":w1", conv_w(sd[p + ".in_layers.2.weight"]), sd[p + ".in_layers.2.weight"]); put(p + ":b1", sd[p + ".in_layers.2.bias"])
                     put(p + ":g2", sd[p + ".out_layers.0.weight"]); put(p + ":be2", sd[p + ".out_layers.0.bias"])
-                    put(p + ":w2", conv_w(sd[p + ".out_layers.3.weight"]))
+                    put(p + ":w2", conv_w(sd[p + ".out_layers.3.weight"]), sd[p + ".out_layers.3.weight"])
                     b2 = sd[p + ".out_layers.3.bias"]
                     if L.skip_conv:
                         ws = sd[p + ".skip_connection.weight"]  # [Cout, Cin, 1, 1] -> [Cin][Cout]
-                        put(p + ":ws", ws[:, :, 0, 0].t().contiguous())
+                        put(p + ":ws", ws[:, :, 0, 0].t().contiguous(), ws)
                         b2 = b2 + sd[p + ".skip_connection.bias"]
                     put(p + ":b2", b2)
                     emb_w.append(sd[p + ".emb_layers.1.weight"]); emb_b.append(sd[p + ".emb_layers.1.bias"])
                 elif L.kind == "attn":
                     put(p + ":g", sd[p + ".norm.weight"]); put(p + ":be", sd[p + ".norm.bias"])
-                    put(p + ":wqkv", sd[p + ".qkv.weight"][:, :, 0].t().contiguous()); put(p + ":bqkv", sd[p + ".qkv.bias"])
-                    put(p + ":wproj", sd[p + ".proj_out.weight"][:, :, 0].t().contiguous()); put(p + ":bproj", sd[p + ".proj_out.bias"])
+                    put(p + ":wqkv", sd[p + ".qkv.weight"][:, :, 0].t().contiguous(), sd[p + ".qkv.weight"]); put(p + ":bqkv", sd[p + ".qkv.bias"])
+                    put(p + ":wproj", sd[p + ".proj_out.weight"][:, :, 0].t().contiguous(), sd[p + ".proj_out.weight"]); put(p + ":bproj", sd[p + ".proj_out.bias"])
         put("emb_w", torch.cat(emb_w, 0)); put("emb_b", torch.cat(emb_b, 0))
         put("out:g", sd["out.0.weight"]); put("out:be", sd["out.0.bias"])
-        put("out:w", conv_w(sd["out.2.weight"])); put("out:b", padded(sd["out.2.bias"]))
+        put("out:w", conv_w(sd["out.2.weight"]), sd["out.2.weight"]); put("out:b", padded(sd["out.2.bias"]))
         self._stamp = stamp
         return True
 
@@ -329,8 +360,7 @@ class Program:
                     out.stat_off = stat_bytes
                     stat_bytes += _ceil(B * out.C * 16, ALIGN)
             arena.release_dead(i)
-        part_floats = max([L.ccdm_conv_part_floats(B, o["Hout"], o["Wout"], o["Cout"]) for o in ops
-                           if o["_out"] is not None and o["_out"].want_stat] + [1])
+        part_floats = 1  # sized in bind(), once each op's kernel (FFMA / tcgen05) is known
         n_pix = B * H * W
         feat_bytes = _ceil(B * fc * (H // 8) * (W // 8) * self.esize, ALIGN) if fc else 0
         layout = dict(arena=arena.size, stat=stat_bytes, part=_ceil(part_floats * 4, ALIGN), ticket=_ceil(4 * (B + 1), ALIGN),
@@ -410,8 +440,16 @@ class Program:
                     op.src1, op.C1, op.stat1 = src[1].addr, src[1].C, src[1].stat_addr
             if "_g" in o:
                 op.gamma, op.beta = W.addr(o["_g"]), W.addr(o["_be"])
+            if "_skip" in o:
+                sk = o["_skip"]
+                op.S0 = sk[0].C
+                if len(sk) > 1:
+                    op.S1 = sk[1].C
+            use_tc = bool(self.exact == 0 and o["kind"] == _lib.OP_CONV and L.ccdm_conv_uses_tc(ctypes.byref(op)))
+            if not use_tc:
+                op.exact = 1
             if "_w" in o:
-                op.weight, op.bias = W.addr(o["_w"]), W.addr(o["_b"])
+                op.weight, op.bias = (W.addr16(o["_w"]) if use_tc else W.addr(o["_w"])), W.addr(o["_b"])
             if o.get("_emb"):
                 op.emb = self.emb_buf.data_ptr()
                 op.emb_cols = emb_cols
@@ -421,7 +459,7 @@ class Program:
                 op.skip0, op.S0 = sk[0].addr, sk[0].C
                 if len(sk) > 1:
                     op.skip1, op.S1 = sk[1].addr, sk[1].C
-                op.skip_w = W.addr(o["_ws"])
+                op.skip_w = W.addr16(o["_ws"]) if use_tc else W.addr(o["_ws"])
             if "_res" in o:
                 op.res = o["_res"].addr
             out = o["_out"]
@@ -429,7 +467,7 @@ class Program:
                 op.out = out.addr
                 if out.want_stat:
                     op.ostat = out.stat_addr
-                    op.part = self.addr["part"]
+                    op.part = 1  # patched below once the scratch size is known
                     op.ticket = self.addr["ticket"]
             if o["kind"] == _lib.OP_HEAD:
                 op.src0 = src[0].addr
@@ -441,6 +479,12 @@ class Program:
             op.steps = self.steps_buf.data_ptr()
             op.step_ptr = self.addr["step"]
             arr[i] = op
+        part_floats = max([int(L.ccdm_op_part_floats(ctypes.byref(arr[i]))) for i in range(self.n_ops)] + [1])
+        self.part_buf = torch.zeros(part_floats, dtype=torch.float32, device=dev)
+        for i in range(self.n_ops):
+            if arr[i].part:
+                arr[i].part = self.part_buf.data_ptr()
+        self.n_tc = sum(1 for i in range(self.n_ops) if arr[i].kind == _lib.OP_CONV and not arr[i].exact)
         self._op_array = arr
         self.plan = L.ccdm_plan_create(arr, self.n_ops)
         if not self.plan:
@@ -485,7 +529,7 @@ class UNetEngine:
         self.unet = unet
         self.precision = precision
         self.device = p0.device
-        self.weights = PackedWeights(unet, self.device)
+        self.weights = PackedWeights(unet, self.device, with_tc=(precision == "bf16"))
         self.programs: Dict[tuple, Program] = {}
         self.stream = None if dry_run else torch.cuda.Stream(device=self.device)
         self.use_graph = True

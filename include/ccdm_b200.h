@@ -122,6 +122,11 @@ size_t ccdm_sizeof_op(void);
 size_t ccdm_sizeof_step_entry(void);
 /* floats of `part` scratch a conv op with statistics needs */
 size_t ccdm_conv_part_floats(int B, int Hout, int Wout, int Cout);
+/* the same, for the kernel `op` will actually be dispatched to */
+size_t ccdm_op_part_floats(const ccdm_op *op);
+/* 1 if `op` (exact == 0, bf16, stride 1) runs on the tcgen05 kernel; its `weight` / `skip_w`
+ * must then be bf16 packed [tap][Cin/8][ceil16(Cout)][8] instead of fp32 [tap][CinP][CoutP]. */
+int ccdm_conv_uses_tc(const ccdm_op *op);
 /* 0 if the current device is compute capability 10.x, negative otherwise. */
 int ccdm_check_device(void);
 

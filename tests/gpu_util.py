@@ -6,7 +6,7 @@ import torch
 import torch.nn.functional as F
 
 from ccdm_b200 import _lib
-from ccdm_b200.engine import pack_bias, pack_conv_weight
+from ccdm_b200.engine import pack_bias, pack_conv_weight, pack_conv_weight_tc
 
 
 def sp():
@@ -34,7 +34,7 @@ class StepCtx:
 
 
 def run_conv(srcs, weight, bias, *, gn=None, silu=False, ksize=3, stride=1, upsample=False, skip=None, skip_w=None,
-             res=None, emb=None, dtype=torch.float32, out_f32=False, want_stat=True, labels=None, image=None, K=0):
+             res=None, emb=None, dtype=torch.float32, out_f32=False, want_stat=True, labels=None, image=None, K=0, tc=False):
     """Launch one CCDM_OP_CONV.  srcs: list of NHWC GPU tensors (1 or 2) or [] with labels/image.
     weight: OIHW fp32 (cpu or gpu); gn: (gamma, beta) or None; skip: list of NHWC tensors for the fused
     1x1 skip conv with skip_w [Cout, Cin_skip, 1, 1]; res: NHWC residual; emb: fp32 [B or 1, Cout] rows.
@@ -53,7 +53,10 @@ def run_conv(srcs, weight, bias, *, gn=None, silu=False, ksize=3, stride=1, upsa
     Hout = Hin * 2 if upsample else ((Hin + 1) // 2 if stride == 2 else Hin)
     Wout = Win * 2 if upsample else ((Win + 1) // 2 if stride == 2 else Win)
     keep = []
-    wp = pack_conv_weight(weight.to(dev), (cin + 7) // 8 * 8 if one_hot_in else None).contiguous()
+    if tc:
+        wp = pack_conv_weight_tc(weight.to(dev)).contiguous()
+    else:
+        wp = pack_conv_weight(weight.to(dev), (cin + 7) // 8 * 8 if one_hot_in else None).contiguous()
     b = bias.to(dev).float()
     if skip is not None:
         assert skip_w is not None
@@ -63,7 +66,7 @@ def run_conv(srcs, weight, bias, *, gn=None, silu=False, ksize=3, stride=1, upsa
     op = _lib.Op(kind=_lib.OP_CONV, dtype=_lib.DT_F32 if dtype == torch.float32 else _lib.DT_BF16,
                  out_dtype=_lib.DT_F32 if out_dtype == torch.float32 else _lib.DT_BF16, B=B, Hin=Hin, Win=Win, Hout=Hout,
                  Wout=Wout, Cout=Cout, ksize=ksize, stride=stride, upsample=int(upsample), gn=int(gn is not None),
-                 silu=int(silu), exact=1)
+                 silu=int(silu), exact=0 if tc else 1)
     op.weight, op.bias, op.out = wp.data_ptr(), bp.data_ptr(), out.data_ptr()
     if one_hot_in:
         op.kind = _lib.OP_INPUT_CONV
@@ -86,7 +89,7 @@ def run_conv(srcs, weight, bias, *, gn=None, silu=False, ksize=3, stride=1, upsa
             keep += [g, be]
             op.gamma, op.beta = g.data_ptr(), be.data_ptr()
     if skip is not None:
-        sw = skip_w.to(dev).float()[:, :, 0, 0].t().contiguous()
+        sw = pack_conv_weight_tc(skip_w.to(dev)).contiguous() if tc else skip_w.to(dev).float()[:, :, 0, 0].t().contiguous()
         keep.append(sw)
         op.skip0, op.S0 = skip[0].data_ptr(), skip[0].shape[3]
         if len(skip) > 1:
@@ -103,9 +106,12 @@ def run_conv(srcs, weight, bias, *, gn=None, silu=False, ksize=3, stride=1, upsa
         op.emb, op.emb_off, op.emb_cols = e.data_ptr(), 0, e.shape[1]
         op.emb_bstride = 1 if e.shape[0] == B and B > 1 else 0
     ostat = None
+    if tc:
+        assert L.ccdm_conv_uses_tc(ctypes.byref(op)) == 1, "op was expected to dispatch to the tcgen05 kernel"
     if want_stat:
         ostat = torch.full((B, Cout, 2), float("nan"), dtype=torch.float64, device=dev)
-        part = torch.zeros(L.ccdm_conv_part_floats(B, Hout, Wout, Cout), dtype=torch.float32, device=dev)
+        op.ostat = 1
+        part = torch.zeros(L.ccdm_op_part_floats(ctypes.byref(op)), dtype=torch.float32, device=dev)
         ticket = torch.zeros(B, dtype=torch.int32, device=dev)
         keep += [part, ticket]
         op.ostat, op.part, op.ticket = ostat.data_ptr(), part.data_ptr(), ticket.data_ptr()

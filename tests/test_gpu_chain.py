@@ -265,3 +265,69 @@ def test_no_fallbacks(cuda_device):
         m(_onehot(labels, K), image, None)
     with pytest.raises(NotImplementedError):
         m.cuda()(_onehot(labels, K).cuda(), image.cuda(), None, label_ref_logits=torch.zeros(1))
+
+
+# ---------------------------------------------------------------------------------------------
+# bf16 ("fast") precision: bf16 activation storage, tcgen05 tensor-core convs.
+# Stated tolerance (precision ladder: bf16 autocast on the reference gives
+# max |d x0| 2.1e-2 and flips 3e-4 (mean) .. 6.3e-3 (worst step) of the sampled labels per step):
+#   max |d x0| <= 6e-2, mean |d x0| <= 4e-3, teacher-forced label mismatch <= 1e-2 per chain.
+# ---------------------------------------------------------------------------------------------
+BF16_X0_MAX, BF16_X0_MEAN, BF16_LABEL_FRAC = 6e-2, 4e-3, 1e-2
+
+
+@pytest.mark.parametrize("tag", ["lidc64", "lidc128", "cs64x128"])
+def test_bf16_unet_vs_reference_fixture(cuda_device, tag):
+    T, B, C_img, H, W, K, fce, mult, t_probe, steps = GOLDEN_CASES[tag]
+    g = golden(tag + ".npz")
+    m, image, feat, labels = _case(tag)
+    m.unet.precision = "bf16"
+    x = _onehot(labels, K).cuda()
+    for t in t_probe:
+        p = m.unet(x, image.cuda(), feat.cuda() if feat is not None else None, torch.full((B,), float(t)).cuda())["diffusion_out"]
+        err = np.abs(p.permute(0, 2, 3, 1).cpu().numpy() - g[f"x0pred_t{t}"])
+        flips = float((p.argmax(1).cpu().numpy() != g[f"x0pred_t{t}"].argmax(-1)).mean())
+        _report(f"bf16_unet_{tag}_t{t}", max_abs_err=err.max(), mean_abs_err=err.mean(), argmax_flips=flips)
+        assert err.max() <= BF16_X0_MAX and err.mean() <= BF16_X0_MEAN, (err.max(), err.mean())
+    eng = m.unet.engine("bf16")
+    assert eng.program(B, H, W, 1).n_tc > 40  # the tensor-core kernels are what ran
+
+
+def test_bf16_layerwise_vs_oracle(cuda_device):
+    from oracle import unet_ref
+    tag = "lidc64"
+    T, B, C_img, H, W, K, fce, mult, t_probe, steps = GOLDEN_CASES[tag]
+    m, image, feat, labels = _case(tag)
+    taps = {}
+    unet_ref.unet_forward({k: v.cpu() for k, v in m.unet.state_dict().items()}, _onehot(labels, K), image, feat,
+                          torch.full((B,), 37.0), taps=taps)
+    tr = m.unet.engine("bf16").trace_step(labels.cuda(), image.cuda(), None, 37.0)
+    worst = {}
+    for name, ref in taps.items():
+        key = name if name in tr else (name + ".op" if name + ".op" in tr else name + ".conv")
+        if key not in tr:
+            continue
+        got = tr[key].permute(0, 3, 1, 2).cpu()
+        worst[name] = float((got - ref).abs().max()) / (float(ref.abs().max()) + 1e-6)
+    _report("bf16_layerwise_lidc64", worst_rel=max(worst.values()), worst_layer=max(worst, key=worst.get),
+            first_layers=[round(worst[k], 5) for k in list(worst)[:6]])
+    bad = {k: v for k, v in worst.items() if v > 5e-2}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("tag", ["lidc64", "cs64x128"])
+def test_bf16_chain_teacher_forced_label_agreement(cuda_device, tag):
+    T, B, C_img, H, W, K, fce, mult, t_probe, steps = GOLDEN_CASES[tag]
+    m, image, feat, labels = _case(tag)
+    from ccdm_b200 import _lib
+    from ccdm_b200.models.diffusion_denoising import reverse_t_values
+    ts = reverse_t_values(T, 10000 + steps)
+    record = []
+    al, ca = m._schedule_host()
+    m.unet.engine("bf16").run_chain(_onehot(labels, K).cuda(), image.cuda(), feat.cuda() if feat is not None else None, ts,
+                                    al, ca, _lib.DRAW_MAJORITY, noise="philox", seed=99, record=record)
+    stats = _teacher_forced_check(m, image, feat, fce, K, T, record)
+    frac = stats["mismatch_total"] / stats["pixels"]
+    _report(f"bf16_teacher_forced_{tag}", label_mismatch_frac=frac, **stats)
+    assert stats["max_dx0"] <= BF16_X0_MAX
+    assert frac <= BF16_LABEL_FRAC

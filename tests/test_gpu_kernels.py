@@ -254,6 +254,84 @@ def test_head_conv_ragged_cout_fp32_logits(L, K):
 
 
 # ---------------------------------------------------------------------------------------
+# tcgen05 conv kernel (bf16 storage, fp32 accumulation in TMEM) vs torch fp32 on the same
+# bf16-rounded inputs and weights.  Tolerance: the normalised+activated input is re-rounded
+# to bf16 before the MMA (rel 2^-9) and SiLU uses tanh.approx: |err| <= 2.5e-2 on O(1)
+# outputs, mean |err| <= 3e-3.
+# ---------------------------------------------------------------------------------------
+TC_MAX, TC_MEAN = 2.5e-2, 3e-3
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def _tc_check(out, ref, ostat=None):
+    got = out.float().permute(0, 3, 1, 2).cpu()
+    err = (got - ref).abs()
+    assert float(err.max()) < TC_MAX and float(err.mean()) < TC_MEAN, (float(err.max()), float(err.mean()))
+    if ostat is not None:  # statistics describe the bf16 values as stored
+        gd = out.double()
+        rs = torch.stack([gd.sum(dim=(1, 2)), (gd * gd).sum(dim=(1, 2))], dim=-1).cpu().numpy()
+        np.testing.assert_allclose(ostat.cpu().numpy(), rs, rtol=1e-5, atol=1e-2)
+
+
+@pytest.mark.parametrize("B,C0,C1,Cout,H,W", [(2, 32, 0, 32, 128, 128), (1, 32, 32, 32, 64, 64), (2, 64, 32, 64, 32, 32),
+                                               (2, 128, 96, 96, 16, 16), (3, 128, 128, 128, 8, 8), (1, 64, 384, 64, 32, 64),
+                                               (1, 32, 0, 32, 20, 72)])
+def test_tc_conv3x3_gn_silu_concat(L, B, C0, C1, Cout, H, W):
+    from gpu_util import nhwc, ref_conv, run_conv
+    xs = [_bf(_rand(B, C0, H, W, seed=1) * 1.5 + 0.3)] + ([_bf(_rand(B, C1, H, W, seed=2) * 0.7 - 0.2)] if C1 else [])
+    cin = C0 + C1
+    w, b = _bf(_rand(Cout, cin, 3, 3, seed=3) / math.sqrt(9 * cin)), _rand(Cout, seed=4) * 0.1
+    gn = (1 + 0.1 * _rand(cin, seed=5), 0.1 * _rand(cin, seed=6))
+    emb = _rand(B, Cout, seed=7)
+    out, ostat = run_conv([nhwc(x, torch.bfloat16) for x in xs], w, b, gn=gn, silu=True, emb=emb, dtype=torch.bfloat16, tc=True)
+    _tc_check(out, ref_conv(xs, w, b, gn=gn, silu=True, emb=emb), ostat)
+
+
+def test_tc_conv_second_half_with_skip_residual_and_upsample(L):
+    from gpu_util import nhwc, ref_conv, run_conv
+    B, C0, C1, Cout, H, W = 2, 64, 32, 64, 32, 32
+    h1 = _bf(_rand(B, Cout, H, W, seed=21))
+    xa, xb = _bf(_rand(B, C0, H, W, seed=22)), _bf(_rand(B, C1, H, W, seed=23))
+    w, b = _bf(_rand(Cout, Cout, 3, 3, seed=24) / math.sqrt(9 * Cout)), _rand(Cout, seed=25) * 0.1
+    ws, bs = _bf(_rand(Cout, C0 + C1, 1, 1, seed=26) / math.sqrt(C0 + C1)), _rand(Cout, seed=27) * 0.1
+    gn = (1 + 0.1 * _rand(Cout, seed=28), 0.1 * _rand(Cout, seed=29))
+    bf = torch.bfloat16
+    out, ostat = run_conv([nhwc(h1, bf)], w, b + bs, gn=gn, silu=True, skip=[nhwc(xa, bf), nhwc(xb, bf)], skip_w=ws, dtype=bf, tc=True)
+    _tc_check(out, ref_conv([h1], w, b, gn=gn, silu=True, skip=[xa, xb], skip_w=ws, skip_b=bs), ostat)
+    x = _bf(_rand(B, Cout, H, W, seed=30))
+    out, ostat = run_conv([nhwc(h1, bf)], w, b, gn=gn, silu=True, res=nhwc(x, bf), dtype=bf, tc=True)
+    _tc_check(out, ref_conv([h1], w, b, gn=gn, silu=True, res=x), ostat)
+    out, ostat = run_conv([nhwc(h1, bf)], w, b, upsample=True, dtype=bf, tc=True)
+    _tc_check(out, ref_conv([h1], w, b, upsample=True), ostat)
+
+
+def test_tc_conv1x1_qkv_proj_and_head(L):
+    from gpu_util import nhwc, ref_conv, run_conv
+    bf = torch.bfloat16
+    for (C, H, W) in [(96, 16, 16), (128, 8, 8), (64, 32, 64)]:
+        B = 2
+        x = _bf(_rand(B, C, H, W, seed=31))
+        w, b = _bf(_rand(3 * C, C, 1, 1, seed=32) / math.sqrt(C)), _rand(3 * C, seed=33) * 0.1
+        gn = (1 + 0.1 * _rand(C, seed=34), 0.1 * _rand(C, seed=35))
+        out, _ = run_conv([nhwc(x, bf)], w, b, gn=gn, silu=False, ksize=1, want_stat=False, dtype=bf, tc=True)
+        _tc_check(out, ref_conv([x], w, b, gn=gn))
+        a = _bf(_rand(B, C, H, W, seed=36))
+        wp, bp = _bf(_rand(C, C, 1, 1, seed=37) / math.sqrt(C)), _rand(C, seed=38) * 0.1
+        out, ostat = run_conv([nhwc(a, bf)], wp, bp, ksize=1, res=nhwc(x, bf), dtype=bf, tc=True)
+        _tc_check(out, ref_conv([a], wp, bp, res=x), ostat)
+    for K in (2, 20):  # output head: ragged Cout, fp32 logits
+        x = _bf(_rand(2, 32, 64, 64, seed=51))
+        w, b = _bf(_rand(K, 32, 3, 3, seed=52) / math.sqrt(9 * 32)), _rand(K, seed=53) * 0.1
+        gn = (1 + 0.1 * _rand(32, seed=54), 0.1 * _rand(32, seed=55))
+        out, _ = run_conv([nhwc(x, bf)], w, b, gn=gn, silu=True, want_stat=False, out_f32=True, dtype=bf, tc=True)
+        assert out.dtype == torch.float32
+        _tc_check(out, ref_conv([x], w, b, gn=gn, silu=True))
+
+
+# ---------------------------------------------------------------------------------------
 # attention (QKVAttentionLegacy) vs torch
 # ---------------------------------------------------------------------------------------
 @pytest.mark.parametrize("B,heads,T", [(2, 3, 256), (1, 4, 64), (1, 2, 2048), (2, 4, 100)])
