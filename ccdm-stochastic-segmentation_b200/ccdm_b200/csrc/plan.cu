@@ -52,8 +52,11 @@ extern "C" size_t ccdm_sizeof_step_entry(void) { return sizeof(ccdm_step_entry);
 namespace ccdm { size_t conv_part_floats(int B, int Hout, int Wout, int Cout); }
 extern "C" size_t ccdm_conv_part_floats(int B, int Hout, int Wout, int Cout) { return ccdm::conv_part_floats(B, Hout, Wout, Cout); }
 
-namespace ccdm { bool conv_uses_tc(const ccdm_op &op); size_t op_part_floats(const ccdm_op &op); }
+namespace ccdm { bool conv_uses_tc(const ccdm_op &op); size_t op_part_floats(const ccdm_op &op); int conv_tc_nt(int Cout); }
 extern "C" int ccdm_conv_uses_tc(const ccdm_op *op) { return op && ccdm::conv_uses_tc(*op) ? 1 : 0; }
+extern "C" int ccdm_conv_tc_nt(int Cout) { return ccdm::conv_tc_nt(Cout); }
+namespace ccdm { int conv_tc_config(const ccdm_op &op, int32_t *out); }
+extern "C" int ccdm_conv_tc_config(const ccdm_op *op, int32_t *out16) { return op && out16 ? ccdm::conv_tc_config(*op, out16) : -1; }
 extern "C" size_t ccdm_op_part_floats(const ccdm_op *op) { return op ? ccdm::op_part_floats(*op) : 0; }
 
 extern "C" int ccdm_check_device(void) {

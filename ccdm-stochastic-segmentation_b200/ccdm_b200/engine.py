@@ -92,17 +92,23 @@ def pack_conv_weight(w: torch.Tensor, cin_pad: Optional[int] = None) -> torch.Te
     return out
 
 
-def pack_conv_weight_tc(w: torch.Tensor) -> torch.Tensor:
-    """OIHW (or OI1) -> the tcgen05 kernel's bf16 [tap][Cin/8][ceil16(Cout)][8] layout: every
-    (tap, 8-channel plane) is Cout rows of 16 bytes = the UMMA K-major no-swizzle canonical form."""
+def pack_conv_weight_tc(w: torch.Tensor, nt: Optional[int] = None) -> torch.Tensor:
+    """OIHW (or OI1) -> the tcgen05 kernel's bf16 [cc][Cin/8][tap][NT][8] layout (cc = chunk of NT output
+    channels of ceil16(Cout)): every (chunk, 8-channel plane, tap) is NT rows of 16 bytes = the UMMA K-major
+    no-swizzle canonical form, and any run of planes of one chunk is contiguous (one bulk copy per K chunk)."""
     if w.dim() == 3:
         w = w[:, :, :, None]
     co, ci, kh, kw = w.shape
     assert ci % 8 == 0
+    if nt is None:
+        nt = int(_lib.lib().ccdm_conv_tc_nt(co))
     cop = _ceil(co, 16)
-    out = torch.zeros(kh * kw, ci // 8, cop, 8, dtype=torch.bfloat16, device=w.device)
-    out[:, :, :co, :] = w.float().permute(2, 3, 1, 0).reshape(kh * kw, ci // 8, 8, co).permute(0, 1, 3, 2).to(torch.bfloat16)
-    return out
+    assert cop % nt == 0
+    taps = kh * kw
+    full = torch.zeros(cop, ci, taps, dtype=torch.float32, device=w.device)
+    full[:co] = w.float().reshape(co, ci, taps)
+    out = full.reshape(cop // nt, nt, ci // 8, 8, taps).permute(0, 2, 4, 1, 3).contiguous()
+    return out.to(torch.bfloat16)
 
 
 def pack_bias(b: torch.Tensor) -> torch.Tensor:

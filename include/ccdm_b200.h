@@ -125,8 +125,16 @@ size_t ccdm_conv_part_floats(int B, int Hout, int Wout, int Cout);
 /* the same, for the kernel `op` will actually be dispatched to */
 size_t ccdm_op_part_floats(const ccdm_op *op);
 /* 1 if `op` (exact == 0, bf16, stride 1) runs on the tcgen05 kernel; its `weight` / `skip_w`
- * must then be bf16 packed [tap][Cin/8][ceil16(Cout)][8] instead of fp32 [tap][CinP][CoutP]. */
+ * must then be bf16 packed [cc][Cin/8][tap][NT][8] (cc = chunk of NT = ccdm_conv_tc_nt(Cout) output
+ * channels of ceil16(Cout)) instead of fp32 [tap][CinP][CoutP]: every (chunk, 8-channel plane, tap)
+ * is NT rows of 16 bytes, the UMMA K-major no-swizzle canonical form, and a K chunk of planes is one
+ * contiguous block (one cp.async.bulk). */
 int ccdm_conv_uses_tc(const ccdm_op *op);
+int ccdm_conv_tc_nt(int Cout);
+/* Tile / pipeline configuration the tcgen05 kernel would use for `op` (introspection for DESIGN.md, the
+ * bench and tests): out16 = {PL, R, Wt, MB, WN, NT, n_cc, NS, resident, acc2, tmem_cols, tiles, n_items,
+ * grid, smem bytes, K chunks per item}.  Returns -1 if `op` does not run on that kernel. */
+int ccdm_conv_tc_config(const ccdm_op *op, int32_t *out16);
 /* 0 if the current device is compute capability 10.x, negative otherwise. */
 int ccdm_check_device(void);
 
