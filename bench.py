@@ -322,6 +322,16 @@ def run_gpu_arm(args, wl):
     if rank == 0:
         peaks = measured_peaks()
         rows, step_ms_eager = per_op_profile(engine, prog, n_iter=0 if args.no_op_profile else 3)
+        if args.op_table:
+            os.makedirs(os.path.dirname(os.path.abspath(args.op_table)), exist_ok=True)
+            with open(args.op_table, "w") as fh:
+                fh.write("op class | launches | us/launch | ideal us (HBM) | GB/s | TF/s | share\n")
+                for k, v in sorted(rows.items(), key=lambda kv: -kv[1]["ms"]):
+                    us = v["ms"] * 1e3 / v["launches"]
+                    by = v["bytes"] / v["launches"]
+                    fh.write(f"{k} | {v['launches']} | {us:.1f} | {by / peaks['hbm_gbs'] / 1e3:.1f} | {by / us / 1e3:.0f} | "
+                             f"{v['flops'] / v['launches'] / us / 1e6:.1f} | {v['ms'] / step_ms_eager:.3f}\n")
+                fh.write(f"eager step total {step_ms_eager:.3f} ms; graph step {ms_step / T:.3f} ms; ops {prog.n_ops}\n")
         top = max(rows.items(), key=lambda kv: kv[1]["ms"])
         per_launch_ms = top[1]["ms"] / top[1]["launches"]
         per_launch_bytes = top[1]["bytes"] / top[1]["launches"]
@@ -372,6 +382,7 @@ def main():
     ap.add_argument("--T", type=int, default=0, help="override the chain length (debug runs; invalid as a bench number)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--op-table", default="", help="write the per-op-class CUDA-event table to this file")
     ap.add_argument("--no-op-profile", action="store_true", help="skip the per-op CUDA-event pass (ncu runs)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

@@ -24,13 +24,18 @@ __global__ void __launch_bounds__(QT) attention_ffma_kernel(const T *__restrict_
     const int b = blockIdx.z, h = blockIdx.y;
     const int qi = blockIdx.x * QT + threadIdx.x;
     const int C3 = heads * 3 * D;
-    const T *base = qkv + size_t(b) * Ttok * C3 + h * 3 * D;
+    // fp32: token-major [B, T, 3C]; bf16: plane-major [B][3C/8][T][8] (see conv_ffma.cu act_off)
+    constexpr bool PM = sizeof(T) == 2;
+    auto qoff = [&](int tok, int ch) -> size_t {  // ch = channel inside this head's q|k|v block of 3*D
+        const int c = h * 3 * D + ch;
+        return PM ? ((size_t(b) * (C3 >> 3) + (c >> 3)) * Ttok + tok) * 8 + (c & 7) : (size_t(b) * Ttok + tok) * C3 + c;
+    };
 
     float q[D], acc[D];
     const bool active = qi < Ttok;
 #pragma unroll
     for (int d = 0; d < D; d += 4) {
-        float4 v = active ? load4<T>(base + size_t(qi) * C3 + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v = active ? load4<T>(qkv + qoff(qi, d)) : make_float4(0.f, 0.f, 0.f, 0.f);
         q[d] = v.x * scale; q[d + 1] = v.y * scale; q[d + 2] = v.z * scale; q[d + 3] = v.w * scale;
         acc[d] = acc[d + 1] = acc[d + 2] = acc[d + 3] = 0.f;
     }
@@ -41,7 +46,7 @@ __global__ void __launch_bounds__(QT) attention_ffma_kernel(const T *__restrict_
         for (int e = threadIdx.x; e < KT * (2 * D / 4); e += QT) {
             int j = e / (2 * D / 4), f = (e % (2 * D / 4)) * 4;  // f in [0, 2D): k then v
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k0 + j < Ttok) v = load4<T>(base + size_t(k0 + j) * C3 + D + f);
+            if (k0 + j < Ttok) v = load4<T>(qkv + qoff(k0 + j, D + f));
             if (f < D) {
                 sK[j][f] = v.x * scale; sK[j][f + 1] = v.y * scale; sK[j][f + 2] = v.z * scale; sK[j][f + 3] = v.w * scale;
             } else {
@@ -76,10 +81,13 @@ __global__ void __launch_bounds__(QT) attention_ffma_kernel(const T *__restrict_
     }
     if (active) {
         const float inv = 1.0f / l;
-        T *o = out + (size_t(b) * Ttok + qi) * (heads * D) + h * D;
+        const int C = heads * D;
 #pragma unroll
-        for (int d = 0; d < D; d += 4)
-            store4<T>(o + d, make_float4(acc[d] * inv, acc[d + 1] * inv, acc[d + 2] * inv, acc[d + 3] * inv));
+        for (int d = 0; d < D; d += 4) {
+            const int c = h * D + d;
+            T *o = out + (PM ? ((size_t(b) * (C >> 3) + (c >> 3)) * Ttok + qi) * 8 + (c & 7) : (size_t(b) * Ttok + qi) * C + c);
+            store4<T>(o, make_float4(acc[d] * inv, acc[d + 1] * inv, acc[d + 2] * inv, acc[d + 3] * inv));
+        }
     }
 }
 

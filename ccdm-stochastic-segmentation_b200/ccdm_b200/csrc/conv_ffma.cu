@@ -50,6 +50,20 @@ struct ConvP {
     int tiles_x, tiles_y;
 };
 
+// Element offset of channels c..c+3 of pixel `pix` (index inside the sample) of sample b in an activation
+// tensor with C channels and HW pixels per sample: fp32 tensors are NHWC, bf16 tensors are plane-major
+// [B][C/8][H][W][8] (the tensor-core kernels' layout: one 16-byte row of a UMMA core matrix per pixel).
+template <typename T>
+__device__ __forceinline__ size_t act_off(int b, size_t HW, int C, size_t pix, int c);
+template <>
+__device__ __forceinline__ size_t act_off<float>(int b, size_t HW, int C, size_t pix, int c) {
+    return (size_t(b) * HW + pix) * C + c;
+}
+template <>
+__device__ __forceinline__ size_t act_off<__nv_bfloat16>(int b, size_t HW, int C, size_t pix, int c) {
+    return ((size_t(b) * (C >> 3) + (c >> 3)) * HW + pix) * 8 + (c & 7);
+}
+
 template <int KS, int STRIDE>
 struct Geo {
     static constexpr int IH = (TH - 1) * STRIDE + KS;
@@ -133,7 +147,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_ffma_kernel(const ConvP p) {
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (iy >= 0 && iy < Hc && ix >= 0 && ix < Wc) {
                     int sy = p.upsample ? (iy >> 1) : iy, sx = p.upsample ? (ix >> 1) : ix;
-                    v = load4<T>(src + ((size_t(b) * p.Hin + sy) * p.Win + sx) * Cs + cs0 + q * 4);
+                    v = load4<T>(src + act_off<T>(b, size_t(p.Hin) * p.Win, Cs, size_t(sy) * p.Win + sx, cs0 + q * 4));
                     if (p.gn) {
                         int c = c0 + q * 4;
                         v.x = v.x * sA[c] + sB[c];
@@ -218,7 +232,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_ffma_kernel(const ConvP p) {
                 int oy = oy0 + py, ox = ox0 + px;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (oy < p.Hout && ox < p.Wout)
-                    v = load4<T>(src + ((size_t(b) * p.Hout + oy) * p.Wout + ox) * Cs + cs0 + q * 4);
+                    v = load4<T>(src + act_off<T>(b, size_t(p.Hout) * p.Wout, Cs, size_t(oy) * p.Wout + ox, cs0 + q * 4));
                 float *d = sIn + (q * 4) * G::PLANE + pix;
                 d[0] = v.x;
                 d[G::PLANE] = v.y;
@@ -267,9 +281,10 @@ __global__ void __launch_bounds__(NTHREADS) conv_ffma_kernel(const ConvP p) {
         const int ox = ox0 + pcol0 + j;
         if (oy < p.Hout && ox < p.Wout) {
             float4 v = make_float4(acc[j][0] + add.x, acc[j][1] + add.y, acc[j][2] + add.z, acc[j][3] + add.w);
-            const size_t pix = (size_t(b) * p.Hout + oy) * p.Wout + ox;
+            const size_t hw = size_t(p.Hout) * p.Wout, pin = size_t(oy) * p.Wout + ox;
+            const size_t pix = size_t(b) * hw + pin;
             if (p.res != nullptr) {
-                float4 r = load4<T>(reinterpret_cast<const T *>(p.res) + pix * p.Cout + co);
+                float4 r = load4<T>(reinterpret_cast<const T *>(p.res) + act_off<T>(b, hw, p.Cout, pin, co));
                 v.x += r.x;
                 v.y += r.y;
                 v.z += r.z;
@@ -277,7 +292,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_ffma_kernel(const ConvP p) {
             }
             if (co + 3 < p.Cout) {
                 v = p.out_f32 ? store4<float>(reinterpret_cast<float *>(p.out) + pix * p.Cout + co, v)
-                              : store4<T>(reinterpret_cast<T *>(p.out) + pix * p.Cout + co, v);
+                              : store4<T>(reinterpret_cast<T *>(p.out) + act_off<T>(b, hw, p.Cout, pin, co), v);
             } else {  // ragged channel tail (Cout = K classes): fp32 logits only
                 float vv[4] = {v.x, v.y, v.z, v.w};
                 for (int i = 0; i < 4; ++i)
@@ -332,7 +347,15 @@ int launch_t(const ConvP &p, cudaStream_t s) {
     using G = Geo<KS, STRIDE>;
     size_t smem = sizeof(float) * (size_t(CK) * G::PLANE + size_t(KS) * KS * CK * COT + 16 * COT * 2 + 2 * size_t(p.Cin));
     auto kern = conv_ffma_kernel<T, KS, STRIDE>;
-    if (smem > 48 * 1024) CCDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    // function-level attribute: set once per instantiation to a fixed ceiling (captured graphs replay nodes
+    // after later launches; a per-launch value would leave the function with whatever came last)
+    constexpr size_t kMaxSmem = 96 * 1024;
+    if (smem > kMaxSmem) CCDM_FAIL(-3, "conv_ffma: %zu bytes of shared memory needed (Cin too large)", smem);
+    static bool attr_done = false;
+    if (!attr_done) {
+        CCDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxSmem)));
+        attr_done = true;
+    }
     dim3 grid(p.tiles_x * p.tiles_y, p.CoutP / COT, p.B);
     kern<<<grid, NTHREADS, smem, s>>>(p);
     CCDM_LAUNCH_CHECK("conv_ffma_kernel");

@@ -29,6 +29,7 @@
 //                          they fit (resident), else one chunk per stage.
 // All hand-offs are mbarriers; nothing in the main loop is a CTA-wide barrier.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace ccdm {
 namespace {
@@ -61,113 +62,10 @@ struct WsP {
     int upsample, gn, silu, S0, S1, emb_off, emb_cols, emb_bstride, out_f32;
     int R, Wt, P, MB, WN, tiles_x, tiles, taps, pad;
     int n_main, n_skip, NS, resident, acc2, tmem_cols, n_items;
+    int ips, slots;  // items per sample; statistics slots per sample (CTAs whose item range can touch one sample)
     uint32_t a_stage, w_stage, w_main_bytes, w_skip_bytes, magicP;
     uint32_t idesc;
 };
-
-// ---- PTX wrappers ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// Waits for the phase with the given parity.  A protocol bug must not hang the GPU: after ~2 s
-// of spinning the kernel traps (the launch then fails loudly instead of wedging the device).
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t ok;
-    long long t0 = 0;
-    for (;;) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (ok) break;
-        const long long now = clock64();
-        if (t0 == 0) t0 = now;
-        else if (now - t0 > 4000000000ll) {
-            printf("conv_ws: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, addr, parity);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-}
-// K-major, SWIZZLE_NONE smem descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return uint64_t((saddr & 0x3FFFF) >> 4) | (uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16) | (uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32) |
-           (uint64_t(1) << 46);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-// 1-D bulk async copy global -> shared (TMA engine, no tensor map), completion on an mbarrier.
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ uint4 ldg_nc16(const void *p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
-
-__device__ __forceinline__ float tanh_approx(float x) {
-    float y;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t *>(&h);
-}
-__device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
-    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xFFFF0000u));
-}
 
 struct Item {
     int b, tile, cc, y0, x0, co0;
@@ -185,35 +83,6 @@ __device__ __forceinline__ Item decode_item(const WsP &p, int it) {
     return r;
 }
 
-// Transpose-reduce: on entry every lane holds 16 per-channel partial sums; on exit lane l holds
-// the warp total of channel ((l>>4)&1)*8 + ((l>>3)&1)*4 + ((l>>2)&1)*2 + ((l>>1)&1) (both lanes
-// of a pair hold the same value).  Fixed order of additions -> deterministic.
-__device__ __forceinline__ float warp_transpose_reduce16(float (&v)[16], int lane) {
-    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
-    float a8[8], a4[4], a2[2], a1;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float keep = b4 ? v[i + 8] : v[i], send = b4 ? v[i] : v[i + 8];
-        a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float keep = b3 ? a8[i + 4] : a8[i], send = b3 ? a8[i] : a8[i + 4];
-        a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float keep = b2 ? a4[i + 2] : a4[i], send = b2 ? a4[i] : a4[i + 2];
-        a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-    {
-        const float keep = b1 ? a2[1] : a2[0], send = b1 ? a2[0] : a2[1];
-        a1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-    return a1;
-}
-
 // ---- the kernel -------------------------------------------------------------------------------
 // PL = planes (8-channel groups) per K chunk: KC = 8*PL channels per pipeline stage.
 template <int PL>
@@ -229,8 +98,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
     const size_t w_region = p.resident ? size_t(p.w_main_bytes) + p.w_skip_bytes : size_t(NS) * p.w_stage;
     float *sAff = reinterpret_cast<float *>(sW + w_region);             // [2][Cin] GN scale / shift (producers)
     float *sAdd = sAff + 2 * p.Cin;                                     // [NT] bias (+ embedding) (epilogue)
-    float *sRed = sAdd + NT;                                            // [4 warps][NT][2]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sRed + EPI_WARPS * NT * 2);
+    float *sRed = sAdd + NT;                                            // [4 warps][CoutP][2] running statistics
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sRed + EPI_WARPS * p.CoutP * 2);
     uint64_t *full_a = bars, *full_w = bars + MAX_STAGES, *empty = bars + 2 * MAX_STAGES;
     uint64_t *acc_full = bars + 3 * MAX_STAGES, *acc_empty = acc_full + 2, *w_res = acc_empty + 2;
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(w_res + 1);
@@ -262,9 +131,60 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
 
     if (warp < EPI_WARPS) {
         // =========================== epilogue ===================================================
-        int acc_it = 0, cur_b = -1, cur_cc = -1;
+        // GroupNorm statistics of the output: per-thread sums over an item -> warp transpose-reduce ->
+        // per-warp running sums in shared memory (sAcc), flushed to global ONCE per (CTA, sample): a CTA's
+        // items are contiguous, so this is one or two partial rows per CTA instead of one per item.
+        float *sAcc = sRed;  // [EPI_WARPS][CoutP][2]
+        const int CoutP = p.CoutP;
+        if (p.ostat != nullptr) {
+            for (int e = lane; e < CoutP * 2; e += 32) sAcc[warp * CoutP * 2 + e] = 0.f;
+            __syncwarp();
+        }
+        auto flush_stats = [&](int b, int n_done) {
+            named_bar_sync(2, EPI_THREADS);
+            const int c_first = int((((long long)b * p.ips + 1) * gridDim.x - 1) / p.n_items);
+            const int slot = int(blockIdx.x) - c_first;
+            for (int e = tid; e < CoutP * 2; e += EPI_THREADS) {
+                float s = 0.f;
+#pragma unroll
+                for (int r = 0; r < EPI_WARPS; ++r) {
+                    s += sAcc[r * CoutP * 2 + e];
+                    sAcc[r * CoutP * 2 + e] = 0.f;
+                }
+                p.part[(size_t(b) * p.slots + slot) * CoutP * 2 + e] = s;
+            }
+            __threadfence();
+            named_bar_sync(2, EPI_THREADS);
+            if (tid == 0) {
+                const unsigned int prev = atomicAdd(p.ticket + b, unsigned(n_done));
+                *s_last = (prev + unsigned(n_done) == unsigned(p.ips));
+            }
+            named_bar_sync(2, EPI_THREADS);
+            if (*s_last) {
+                // every item of this sample is done somewhere on the chip: fold the per-CTA partial rows in
+                // slot order, in double (the consumer's GroupNorm reads these sums) -- a fixed order, so the
+                // result does not depend on which CTA finishes last
+                __threadfence();
+                const int c_last = int(((long long)(b + 1) * p.ips * gridDim.x - 1) / p.n_items);
+                const int n_slots = c_last - c_first + 1;
+                for (int e = tid; e < p.Cout * 2; e += EPI_THREADS) {
+                    const float *pp = p.part + size_t(b) * p.slots * CoutP * 2 + e;
+                    double s = 0.0;
+                    for (int t = 0; t < n_slots; ++t) s += double(__ldcg(pp + size_t(t) * CoutP * 2));
+                    p.ostat[size_t(b) * p.Cout * 2 + e] = s;
+                }
+                if (tid == 0) p.ticket[b] = 0u;  // self-reset for the next launch
+            }
+            named_bar_sync(2, EPI_THREADS);  // s_last is reused by the next flush
+        };
+
+        int acc_it = 0, cur_b = -1, cur_cc = -1, n_pending = 0;
         for (int it = it_begin; it < it_end; ++it, ++acc_it) {
             const Item I = decode_item(p, it);
+            if (I.b != cur_b && n_pending > 0) {
+                if (p.ostat != nullptr) flush_stats(cur_b, n_pending);
+                n_pending = 0;
+            }
             if (I.b != cur_b || I.cc != cur_cc) {
                 named_bar_sync(2, EPI_THREADS);
                 for (int c = tid; c < NT; c += EPI_THREADS) {
@@ -281,30 +201,61 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
             }
             const int buf = p.acc2 ? (acc_it & 1) : 0;
             const uint32_t aph = p.acc2 ? uint32_t((acc_it >> 1) & 1) : uint32_t(acc_it & 1);
+            // pixel of accumulator row (mb, this thread) and whether it is a real output
+            auto coords = [&](int mb, size_t &pix) -> bool {
+                const int j = mb * 128 + warp * 32 + lane;
+                const int o = int((uint32_t(j) * p.magicP) >> 20), c = j - o * P;
+                const int y = I.y0 + o, x = I.x0 + c;
+                pix = size_t(y) * p.W + x;  // pixel inside the sample
+                return o < p.R && c < p.Wt && y < p.H && x < p.W;
+            };
+            // the residual of the first row block can be fetched before the accumulators are ready
+            const size_t hw = size_t(p.H) * p.W;
+            size_t pix_n;
+            bool valid_n = coords(0, pix_n);
+            uint4 res_n[CGW / 8];
+            auto fetch_res = [&](int cobase) {
+                if (p.res != nullptr && valid_n) {
+                    // plane-major: 16 bytes per (plane, pixel); a warp's 32 rows are 32 consecutive pixels
+                    const __nv_bfloat16 *rp = p.res + ((size_t(I.b) * (p.Cout >> 3) + (cobase >> 3)) * hw + pix_n) * 8;
+#pragma unroll
+                    for (int h2 = 0; h2 < CGW / 8; ++h2) res_n[h2] = ldg_nc16(rp + size_t(h2) * hw * 8);
+                }
+            };
+            fetch_res(I.co0);
             mbar_wait(acc_full + buf, aph);
             tc_fence_after();
             const uint32_t tbase = tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(buf * p.MB * NT);
-            for (int cg = 0; cg < NT / CGW; ++cg) {
+            const int n_cg = NT / CGW;
+            for (int cg = 0; cg < n_cg; ++cg) {
                 float s1[CGW], s2[CGW];
 #pragma unroll
                 for (int i = 0; i < CGW; ++i) s1[i] = 0.f, s2[i] = 0.f;
                 const int cobase = I.co0 + cg * CGW;
                 for (int mb = 0; mb < p.MB; ++mb) {
+                    const bool valid = valid_n;
+                    const size_t pix = pix_n;
+                    uint4 rr[CGW / 8];
+#pragma unroll
+                    for (int h2 = 0; h2 < CGW / 8; ++h2) rr[h2] = res_n[h2];
+                    // software pipeline: issue the residual fetch of the NEXT row block (or of the next
+                    // channel group's first block) before touching this block's accumulators
+                    if (mb + 1 < p.MB) {
+                        valid_n = coords(mb + 1, pix_n);
+                        fetch_res(cobase);
+                    } else if (cg + 1 < n_cg) {
+                        valid_n = coords(0, pix_n);
+                        fetch_res(cobase + CGW);
+                    }
                     float v[CGW];
                     tmem_ld16(tbase + uint32_t(mb * NT + cg * CGW), v);
-                    const int j = mb * 128 + warp * 32 + lane;
-                    const int o = int((uint32_t(j) * p.magicP) >> 20), c = j - o * P;
-                    const int y = I.y0 + o, x = I.x0 + c;
-                    if (o < p.R && c < p.Wt && y < p.H && x < p.W) {
-                        const size_t pix = (size_t(I.b) * p.H + y) * p.W + x;
+                    if (valid) {
 #pragma unroll
                         for (int i = 0; i < CGW; ++i) v[i] += sAdd[cg * CGW + i];
                         if (p.res != nullptr) {
-                            const uint4 *rp = reinterpret_cast<const uint4 *>(p.res + pix * p.Cout + cobase);
 #pragma unroll
                             for (int h2 = 0; h2 < CGW / 8; ++h2) {
-                                const uint4 rr = ldg_nc16(rp + h2);
-                                const uint32_t w4[4] = {rr.x, rr.y, rr.z, rr.w};
+                                const uint32_t w4[4] = {rr[h2].x, rr[h2].y, rr[h2].z, rr[h2].w};
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) {
                                     float2 f = unpack_bf16(w4[i]);
@@ -314,12 +265,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
                             }
                         }
                         if (p.out_f32) {
-                            float *op = reinterpret_cast<float *>(p.out) + pix * p.Cout + cobase;
+                            float *op = reinterpret_cast<float *>(p.out) + (size_t(I.b) * hw + pix) * p.Cout + cobase;  // fp32 logits stay NHWC
 #pragma unroll
                             for (int i = 0; i < CGW; ++i)
                                 if (cobase + i < p.Cout) op[i] = v[i];
                         } else {
-                            uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + pix * p.Cout + cobase);
+                            __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(p.out) + ((size_t(I.b) * (p.Cout >> 3) + (cobase >> 3)) * hw + pix) * 8;
 #pragma unroll
                             for (int h2 = 0; h2 < CGW / 8; ++h2) {
                                 uint32_t pk[4];
@@ -330,7 +281,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
                                     v[h2 * 8 + 2 * i] = f.x;
                                     v[h2 * 8 + 2 * i + 1] = f.y;
                                 }
-                                op[h2] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                                *reinterpret_cast<uint4 *>(op + size_t(h2) * hw * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                             }
                         }
 #pragma unroll
@@ -345,56 +296,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
                     const float r2 = warp_transpose_reduce16(s2, lane);
                     if ((lane & 1) == 0) {
                         const int ch = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                        sRed[(warp * NT + cg * CGW + ch) * 2 + 0] = r1;
-                        sRed[(warp * NT + cg * CGW + ch) * 2 + 1] = r2;
+                        float *a = sAcc + (warp * CoutP + cobase + ch) * 2;
+                        a[0] += r1;
+                        a[1] += r2;
                     }
                 }
             }
-            // accumulator buffer drained: hand it back to the MMA warp before the (slow) statistics tail
+            // accumulator buffer drained: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + buf);
-            if (p.ostat == nullptr) continue;
-
-            named_bar_sync(2, EPI_THREADS);
-            for (int e = tid; e < NT * 2; e += EPI_THREADS) {
-                const int c = e >> 1, w = e & 1;
-                float s = 0.f;
-#pragma unroll
-                for (int r = 0; r < EPI_WARPS; ++r) s += sRed[(r * NT + c) * 2 + w];
-                p.part[((size_t(I.b) * p.tiles + I.tile) * p.CoutP + I.co0 + c) * 2 + w] = s;
-            }
-            __threadfence();
-            named_bar_sync(2, EPI_THREADS);
-            if (tid == 0) {
-                const unsigned int total = unsigned(p.tiles * p.n_cc);
-                const unsigned int prev = atomicAdd(p.ticket + I.b, 1u);
-                *s_last = (prev == total - 1);
-            }
-            named_bar_sync(2, EPI_THREADS);
-            if (*s_last) {
-                // last item of this sample anywhere on the chip: fold the per-tile partials in a fixed
-                // order, in double (GroupNorm of the consumer reads these sums)
-                __threadfence();
-                for (int e = tid; e < p.Cout * 2; e += EPI_THREADS) {
-                    const int c = e >> 1, w = e & 1;
-                    const float *pp = p.part + (size_t(I.b) * p.tiles * p.CoutP + c) * 2 + w;
-                    double s = 0.0;
-                    int t = 0;
-                    for (; t + 8 <= p.tiles; t += 8) {
-                        float f[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) f[u] = __ldcg(pp + size_t(t + u) * p.CoutP * 2);
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) s += double(f[u]);
-                    }
-                    for (; t < p.tiles; ++t) s += double(__ldcg(pp + size_t(t) * p.CoutP * 2));
-                    p.ostat[(size_t(I.b) * p.Cout + c) * 2 + w] = s;
-                }
-                if (tid == 0) p.ticket[I.b] = 0u;  // self-reset for the next launch
-            }
-            named_bar_sync(2, EPI_THREADS);  // s_last / sRed are reused by the next item
+            ++n_pending;
         }
+        if (p.ostat != nullptr && n_pending > 0) flush_stats(cur_b, n_pending);
     } else if (warp < WARP_MMA) {
         // =========================== producers ==================================================
         const int pt = tid - EPI_THREADS;
@@ -458,7 +372,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
                 // the skip conv is a 1x1 on the block input at the output resolution (no x2)
                 const int srcH = is_skip ? p.H : p.Hin, srcW = is_skip ? p.W : p.Win;
                 const bool ups = p.upsample && !is_skip;
-                const __nv_bfloat16 *sbase = src + size_t(I.b) * srcH * srcW * Cs + cs;
+                // plane-major activations [B][C/8][H][W][8]: this thread's 8-channel plane of the source
+                const __nv_bfloat16 *sbase = src + (size_t(I.b) * (Cs >> 3) + (cs >> 3)) * srcH * srcW * 8;
                 const int yb = I.y0 - p.pad, xb = I.x0 - p.pad;
 
                 mbar_wait(empty + stage, phase ^ 1u);
@@ -475,7 +390,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
                             const int y = yb + r, x = xb + c;
                             if (unsigned(y) < unsigned(p.H) && unsigned(x) < unsigned(p.W)) {
                                 const int sy = ups ? (y >> 1) : y, sx = ups ? (x >> 1) : x;
-                                raw[u] = ldg_nc16(sbase + (size_t(sy) * srcW + sx) * Cs);
+                                raw[u] = ldg_nc16(sbase + (size_t(sy) * srcW + sx) * 8);
                                 ok |= 1u << u;
                             }
                         }
@@ -534,54 +449,73 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
         }
     } else if (warp == WARP_MMA) {
         // =========================== MMA issue ==================================================
-        if (lane == 0) {
+        // One thread issues every tcgen05.mma.  Descriptors are kept as 32-bit halves: hi = SBO (128 B) |
+        // version, lo = address/16 | LBO/16 << 16, and since every operand offset is a whole number of
+        // 16-byte rows the lo word advances by plain integer adds (no carry into the LBO field: shared
+        // memory addresses stay below 2^18).
+        {
             int stage = 0, acc_it = 0;
             uint32_t phase = 0;
             if (p.resident) mbar_wait(w_res, 0);
-            const uint32_t a0 = smem_u32(sA), w0 = smem_u32(sW);
+            const uint32_t desc_hi = 8u | (1u << 14);
+            const uint32_t a0 = (smem_u32(sA) >> 4) | (uint32_t(WN) << 16);
+            const uint32_t w0 = smem_u32(sW) >> 4;
+            const uint32_t a_stage16 = p.a_stage >> 4, w_stage16 = p.w_stage >> 4;
+            const uint32_t kA = 2u * uint32_t(WN);  // two 8-channel planes per K = 16 step
             for (int it = it_begin; it < it_end; ++it, ++acc_it) {
                 const int buf = p.acc2 ? (acc_it & 1) : 0;
                 const uint32_t aph = p.acc2 ? uint32_t((acc_it >> 1) & 1) : uint32_t(acc_it & 1);
                 mbar_wait(acc_empty + buf, aph ^ 1u);
                 tc_fence_after();
+                const uint32_t d0 = tmem_base + uint32_t(buf * p.MB * NT);
                 for (int kc = 0; kc < n_chunks; ++kc) {
                     const bool is_skip = kc >= p.n_main;
                     const int ntap = is_skip ? 1 : p.taps;
                     mbar_wait(full_a + stage, phase);
                     if (!p.resident) mbar_wait(full_w + stage, phase);
                     tc_fence_after();
-                    const uint32_t aaddr = a0 + uint32_t(stage) * p.a_stage;
+                    const uint32_t aaddr = a0 + uint32_t(stage) * a_stage16;
                     uint32_t waddr;
                     if (p.resident)
-                        waddr = is_skip ? w0 + p.w_main_bytes + uint32_t((kc - p.n_main) * PL * NT) * 16 : w0 + uint32_t(kc * PL * ntap * NT) * 16;
+                        waddr = is_skip ? w0 + (p.w_main_bytes >> 4) + uint32_t((kc - p.n_main) * PL * NT) : w0 + uint32_t(kc * PL * ntap * NT);
                     else
-                        waddr = w0 + uint32_t(stage) * p.w_stage;
-                    const uint32_t wlbo = uint32_t(ntap * NT) * 16;
-                    for (int mb = 0; mb < p.MB; ++mb) {
-                        const uint32_t d = tmem_base + uint32_t(buf * p.MB * NT + mb * NT);
-                        for (int tap = 0; tap < ntap; ++tap) {
-                            int shift;
-                            if (is_skip) {
-                                shift = p.pad * P + p.pad;  // centre tap
-                            } else {
-                                const int dy = p.taps == 9 ? tap / 3 : 0, dx = p.taps == 9 ? tap - dy * 3 : 0;
-                                shift = dy * P + dx;
-                            }
+                        waddr = w0 + uint32_t(stage) * w_stage16;
+                    waddr |= uint32_t(ntap * NT) << 16;  // LBO of B: one 8-channel plane = ntap * NT rows of 16 bytes
+                    const uint32_t kB = 2u * uint32_t(ntap * NT);
+                    if (ntap == 9) {
+                        for (int mb = 0; mb < p.MB; ++mb) {
+                            const uint32_t d = d0 + uint32_t(mb * NT);
+                            const uint32_t arow = aaddr + uint32_t(mb * 128);
+                            uint32_t acc = kc > 0 ? 1u : 0u;
 #pragma unroll
-                            for (int k16 = 0; k16 < PL / 2; ++k16) {
-                                const uint64_t ad = make_desc(aaddr + uint32_t((2 * k16) * WN + mb * 128 + shift) * 16, uint32_t(WN) * 16, 128);
-                                const uint64_t bd = make_desc(waddr + uint32_t((2 * k16) * ntap + tap) * NT * 16, wlbo, 128);
-                                umma_bf16(d, ad, bd, p.idesc, (kc > 0 || tap > 0 || k16 > 0) ? 1u : 0u);
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const uint32_t at = arow + uint32_t((tap / 3) * P + (tap % 3));
+                                const uint32_t bt = waddr + uint32_t(tap * NT);
+#pragma unroll
+                                for (int k16 = 0; k16 < PL / 2; ++k16) {
+                                    umma_bf16_split(d, at + k16 * kA, desc_hi, bt + k16 * kB, desc_hi, p.idesc, acc);
+                                    acc = 1u;
+                                }
                             }
                         }
+                    } else {
+                        // 1x1 conv, or the fused 1x1 skip conv of a 3x3 block (centre tap of the window)
+                        const uint32_t shift = is_skip ? uint32_t(p.pad * P + p.pad) : 0u;
+                        for (int mb = 0; mb < p.MB; ++mb) {
+                            const uint32_t d = d0 + uint32_t(mb * NT);
+                            const uint32_t at = aaddr + uint32_t(mb * 128) + shift;
+#pragma unroll
+                            for (int k16 = 0; k16 < PL / 2; ++k16)
+                                umma_bf16_split(d, at + k16 * kA, desc_hi, waddr + k16 * kB, desc_hi, p.idesc, (kc > 0 || k16 > 0) ? 1u : 0u);
+                        }
                     }
-                    umma_commit(empty + stage);
+                    umma_commit_elect(empty + stage);
                     if (++stage == NS) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                umma_commit(acc_full + buf);
+                umma_commit_elect(acc_full + buf);
             }
         }
     } else {
@@ -626,7 +560,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
 
 // ---- host-side configuration --------------------------------------------------------------------
 struct WsCfg {
-    int PL, R, Wt, P, MB, WN, NT, n_cc, NS, resident, acc2, tmem_cols, tiles_x, tiles, n_main, n_skip, n_items, grid;
+    int PL, R, Wt, P, MB, WN, NT, n_cc, NS, resident, acc2, tmem_cols, tiles_x, tiles, n_main, n_skip, n_items, grid, ips, slots;
     uint32_t a_stage, w_stage, w_main_bytes, w_skip_bytes, magicP;
     size_t smem;
 };
@@ -642,7 +576,9 @@ int ws_nt(int Cout) {
     return 16;
 }
 
-size_t ws_fixed_smem(int Cin, int NT) { return sizeof(float) * (2 * size_t(Cin) + NT + size_t(EPI_WARPS) * NT * 2) + (3 * MAX_STAGES + 5) * 8 + 64; }
+size_t ws_fixed_smem(int Cin, int NT, int CoutP) {
+    return sizeof(float) * (2 * size_t(Cin) + NT + size_t(EPI_WARPS) * CoutP * 2) + (3 * MAX_STAGES + 5) * 8 + 64;
+}
 
 bool ws_configure(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout, int ksize, WsCfg &best) {
     const int Cin = C0 + C1, Sk = S0 + S1;
@@ -667,7 +603,7 @@ bool ws_configure(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout,
     const size_t w_total = size_t(c.w_main_bytes) + c.w_skip_bytes;
     c.resident = (c.n_cc == 1 && w_total <= kResidentMax) ? 1 : 0;
     c.w_stage = c.resident ? 0u : uint32_t(c.PL * taps * c.NT * 16);
-    const size_t fixed = ws_fixed_smem(Cin, c.NT) + (c.resident ? w_total : 0);
+    const size_t fixed = ws_fixed_smem(Cin, c.NT, CoutP) + (c.resident ? w_total : 0);
     double best_cost = 1e300;
     bool found = false;
     for (int R = 1; R <= H; ++R) {
@@ -708,6 +644,16 @@ bool ws_configure(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout,
             found = true;
         }
     }
+    if (found) {
+        // statistics slots: the most CTAs whose contiguous item range touches one sample
+        best.ips = best.tiles * best.n_cc;
+        best.slots = 1;
+        for (int b = 0; b < B; ++b) {
+            const int c_first = int((((long long)b * best.ips + 1) * best.grid - 1) / best.n_items);
+            const int c_last = int(((long long)(b + 1) * best.ips * best.grid - 1) / best.n_items);
+            if (c_last - c_first + 1 > best.slots) best.slots = c_last - c_first + 1;
+        }
+    }
     return found;
 }
 
@@ -741,7 +687,7 @@ int conv_tc_config(const ccdm_op &op, int32_t *out) {
 size_t conv_tc_part_floats(const ccdm_op &op) {
     WsCfg c;
     if (!ws_configure_op(op, c)) return 0;
-    return size_t(op.B) * c.tiles * ((op.Cout + 15) / 16 * 16) * 2;
+    return size_t(op.B) * c.slots * ((op.Cout + 15) / 16 * 16) * 2;
 }
 
 int launch_conv_tc(const ccdm_op &op, cudaStream_t s) {
@@ -765,7 +711,7 @@ int launch_conv_tc(const ccdm_op &op, cudaStream_t s) {
     p.R = c.R; p.Wt = c.Wt; p.P = c.P; p.MB = c.MB; p.WN = c.WN; p.tiles_x = c.tiles_x; p.tiles = c.tiles;
     p.taps = op.ksize * op.ksize; p.pad = op.ksize / 2;
     p.n_main = c.n_main; p.n_skip = c.n_skip; p.NS = c.NS; p.resident = c.resident; p.acc2 = c.acc2;
-    p.tmem_cols = c.tmem_cols; p.n_items = c.n_items;
+    p.tmem_cols = c.tmem_cols; p.n_items = c.n_items; p.ips = c.ips; p.slots = c.slots;
     p.a_stage = c.a_stage; p.w_stage = c.w_stage; p.w_main_bytes = c.w_main_bytes; p.w_skip_bytes = c.w_skip_bytes;
     p.magicP = c.magicP;
     // cute::UMMA::InstrDescriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major both, N>>3 at 17, M>>4 at 24
@@ -781,7 +727,14 @@ int launch_conv_tc(const ccdm_op &op, cudaStream_t s) {
         if (expH != op.Hout || expW != op.Wout) CCDM_FAIL(-2, "conv_ws: inconsistent shapes");
     }
     auto kern = c.PL == 4 ? conv_ws_kernel<4> : conv_ws_kernel<2>;
-    CCDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(c.smem)));
+    // The opt-in shared memory limit is a property of the FUNCTION, not of a launch: set it once to the
+    // budget (never per launch -- a captured graph replays nodes long after a later launch lowered it).
+    static bool attr_done = false;
+    if (!attr_done) {
+        CCDM_CUDA(cudaFuncSetAttribute(conv_ws_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBudget)));
+        CCDM_CUDA(cudaFuncSetAttribute(conv_ws_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBudget)));
+        attr_done = true;
+    }
     kern<<<c.grid, WS_THREADS, c.smem, s>>>(p);
     CCDM_LAUNCH_CHECK("conv_ws_kernel");
     return 0;

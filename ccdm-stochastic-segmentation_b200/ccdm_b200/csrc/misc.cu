@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_stats_kernel(const float *__
             float v = tile[tx][j];
             if (sizeof(T) == 2) {
                 __nv_bfloat16 h = __float2bfloat16_rn(v);
-                reinterpret_cast<__nv_bfloat16 *>(dst)[(size_t(b) * HW + p) * C + c] = h;
+                // bf16 activations are plane-major [B][C/8][HW][8]
+                reinterpret_cast<__nv_bfloat16 *>(dst)[((size_t(b) * (C >> 3) + (c >> 3)) * HW + p) * 8 + (c & 7)] = h;
                 tile[tx][j] = __bfloat162float(h);
             } else {
                 reinterpret_cast<float *>(dst)[(size_t(b) * HW + p) * C + c] = v;

@@ -111,6 +111,19 @@ def pack_conv_weight_tc(w: torch.Tensor, nt: Optional[int] = None) -> torch.Tens
     return out.to(torch.bfloat16)
 
 
+def to_pm(x_nhwc: torch.Tensor) -> torch.Tensor:
+    """NHWC [B,H,W,C] -> the bf16 kernels' plane-major layout [B, C/8, H, W, 8] (contiguous)."""
+    B, H, W, C = x_nhwc.shape
+    assert C % 8 == 0
+    return x_nhwc.reshape(B, H, W, C // 8, 8).permute(0, 3, 1, 2, 4).contiguous()
+
+
+def from_pm(x_pm: torch.Tensor) -> torch.Tensor:
+    """plane-major [B, C/8, H, W, 8] -> NHWC [B,H,W,C] (contiguous)."""
+    B, G, H, W, _ = x_pm.shape
+    return x_pm.permute(0, 2, 3, 1, 4).reshape(B, H, W, G * 8).contiguous()
+
+
 def pack_bias(b: torch.Tensor) -> torch.Tensor:
     out = torch.zeros(_ceil(b.numel(), 32), dtype=torch.float32, device=b.device)
     out[:b.numel()] = b.float()
@@ -730,7 +743,11 @@ class UNetEngine:
         return out
 
     def tensor_view(self, prog: Program, t: Ten) -> torch.Tensor:
+        """NHWC view (fp32 tensors) or NHWC copy (bf16 tensors, stored plane-major) of a workspace tensor."""
         dtype = torch.float32 if t.esize == 4 else torch.bfloat16
         off = t.addr - prog.workspace.data_ptr()
         n = prog.B * t.H * t.W * t.C * t.esize
-        return prog.workspace[off:off + n].view(dtype).view(prog.B, t.H, t.W, t.C)
+        flat = prog.workspace[off:off + n].view(dtype)
+        if t.esize == 4:
+            return flat.view(prog.B, t.H, t.W, t.C)
+        return from_pm(flat.view(prog.B, t.C // 8, t.H, t.W, 8))

@@ -14,8 +14,14 @@
  *  - no allocation of caller-visible memory, no host synchronisation, every
  *    launch goes to the `stream` argument (a cudaStream_t passed as void*).
  *  - return 0 on success, negative on error; ccdm_last_error() describes it.
- *  - activations are NHWC ("pixel-major, channel-minor"), fp32 or bf16
- *    (`CCDM_DT_*`); label maps are uint8 [B,H,W]; GroupNorm statistics travel
+ *  - fp32 activations (`CCDM_DT_F32`, the exact kernels) are NHWC ("pixel-major,
+ *    channel-minor"); bf16 activations (`CCDM_DT_BF16`, the tensor-core kernels)
+ *    are PLANE-MAJOR [B][C/8][H][W][8]: one 16-byte row of a tcgen05 "K-major,
+ *    no swizzle" core matrix per (8-channel plane, pixel), so a TMA box of a
+ *    tile lands in shared memory already in the MMA operand layout and a warp
+ *    of epilogue threads writes 512 contiguous bytes per plane.  fp32 logits
+ *    [B,H,W,K] are NHWC in both modes.
+ *  - label maps are uint8 [B,H,W]; GroupNorm statistics travel
  *    beside every activation as per-(sample,channel) double2 {sum, sum of
  *    squares} written by the producing kernel.
  *  - one process per GPU; a plan is not re-entrant.

@@ -6,7 +6,7 @@ import torch
 import torch.nn.functional as F
 
 from ccdm_b200 import _lib
-from ccdm_b200.engine import pack_bias, pack_conv_weight, pack_conv_weight_tc
+from ccdm_b200.engine import from_pm, pack_bias, pack_conv_weight, pack_conv_weight_tc, to_pm
 
 
 def sp():
@@ -42,13 +42,21 @@ def run_conv(srcs, weight, bias, *, gn=None, silu=False, ksize=3, stride=1, upsa
     L = _lib.lib()
     dev = "cuda"
     one_hot_in = labels is not None
+    # bf16 activations live in the kernels' plane-major layout; this helper keeps NHWC at its surface
+    pm = dtype == torch.bfloat16
+    shapes = [tuple(s.shape) for s in srcs]
+    if pm:
+        nh = list(srcs)
+        srcs = [to_pm(s) for s in srcs]
+        skip = [to_pm(s) for s in skip] if skip is not None else None
+        res = to_pm(res) if res is not None else None
     if one_hot_in:
         B, Hin, Win = labels.shape
         C_img = image.shape[1]
         cin = K + C_img
     else:
-        B, Hin, Win, _ = srcs[0].shape
-        cin = sum(s.shape[3] for s in srcs)
+        B, Hin, Win, _ = shapes[0]
+        cin = sum(sh[3] for sh in shapes)
     Cout = weight.shape[0]
     Hout = Hin * 2 if upsample else ((Hin + 1) // 2 if stride == 2 else Hin)
     Wout = Win * 2 if upsample else ((Win + 1) // 2 if stride == 2 else Win)
@@ -76,11 +84,11 @@ def run_conv(srcs, weight, bias, *, gn=None, silu=False, ksize=3, stride=1, upsa
         keep += [lab, img]
         op.labels_in, op.image = lab.data_ptr(), img.data_ptr()
     else:
-        op.src0, op.C0 = srcs[0].data_ptr(), srcs[0].shape[3]
+        op.src0, op.C0 = srcs[0].data_ptr(), shapes[0][3]
         if len(srcs) > 1:
-            op.src1, op.C1 = srcs[1].data_ptr(), srcs[1].shape[3]
+            op.src1, op.C1 = srcs[1].data_ptr(), shapes[1][3]
         if gn is not None:
-            st = [stats_of(s) for s in srcs]
+            st = [stats_of(s) for s in (nh if pm else srcs)]
             keep += st
             op.stat0 = st[0].data_ptr()
             if len(srcs) > 1:
@@ -91,9 +99,9 @@ def run_conv(srcs, weight, bias, *, gn=None, silu=False, ksize=3, stride=1, upsa
     if skip is not None:
         sw = pack_conv_weight_tc(skip_w.to(dev)).contiguous() if tc else skip_w.to(dev).float()[:, :, 0, 0].t().contiguous()
         keep.append(sw)
-        op.skip0, op.S0 = skip[0].data_ptr(), skip[0].shape[3]
+        op.skip0, op.S0 = skip[0].data_ptr(), (skip[0].shape[1] * 8 if pm else skip[0].shape[3])
         if len(skip) > 1:
-            op.skip1, op.S1 = skip[1].data_ptr(), skip[1].shape[3]
+            op.skip1, op.S1 = skip[1].data_ptr(), (skip[1].shape[1] * 8 if pm else skip[1].shape[3])
         op.skip_w = sw.data_ptr()
     if res is not None:
         op.res = res.data_ptr()
@@ -119,6 +127,8 @@ def run_conv(srcs, weight, bias, *, gn=None, silu=False, ksize=3, stride=1, upsa
     torch.cuda.synchronize()
     if want_stat:
         assert int(ticket.abs().sum()) == 0, "ticket counters must self-reset"
+    if pm and out_dtype == torch.bfloat16:
+        out = from_pm(out.view(B, Cout // 8, Hout, Wout, 8))
     return out, ostat
 
 
