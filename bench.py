@@ -202,40 +202,36 @@ def op_class(o):
     if o.kind == _lib.OP_INPUT_CONV:
         return f"input_conv {o.K}+{o.C_img}->{o.Cout} @{o.Hout}x{o.Wout}"
     tag = "conv%dx%d" % (o.ksize, o.ksize) + ("/s2" if o.stride == 2 else "") + ("/up" if o.upsample else "")
-    return f"{tag} {o.C0 + o.C1}->{o.Cout}{'+skip' if o.S0 else ''} @{o.Hout}x{o.Wout}"
+    return (f"{tag} {o.C0 + o.C1}->{o.Cout}{'+skip' if o.S0 else ''}{'+res' if o.res else ''} @{o.Hout}x{o.Wout}"
+            + (" [ffma]" if (o.exact and o.dtype == _lib.DT_BF16) else ""))
 
 
 def per_op_profile(engine, prog, n_iter=3):
-    """CUDA-event duration of every launch of one reverse step (eager launches on the engine stream),
-    averaged over n_iter steps; returns rows aggregated per op class."""
+    """Device time of every launch of one reverse step (ccdm_plan_profile: each op replayed n_iter times as a
+    one-node CUDA graph between two events, so host launch overhead is excluded); returns rows aggregated
+    per op class and the sum over the step."""
     import ctypes
     from ccdm_b200 import _lib
     L = _lib.lib()
-    sp = _lib.stream_ptr(engine.stream)
     n = prog.n_ops
-    acc = [0.0] * n
-    with torch.cuda.stream(engine.stream):
-        for it in range(n_iter + 1 if n_iter else 0):
+    acc = [1e-3] * n
+    if n_iter:
+        buf = (ctypes.c_float * n)()
+        with torch.cuda.stream(engine.stream):
             prog.step_counter.zero_()
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
-            ev[0].record(engine.stream)
-            for i in range(n):
-                _lib.check(L.ccdm_launch_op(ctypes.byref(prog._op_array[i]), sp), f"op {i}")
-                ev[i + 1].record(engine.stream)
+            _lib.check(L.ccdm_plan_profile(prog.plan, n_iter, buf, _lib.stream_ptr(engine.stream)), "plan_profile")
             engine.stream.synchronize()
-            if it:  # first pass is warm-up
-                for i in range(n):
-                    acc[i] += ev[i].elapsed_time(ev[i + 1]) / n_iter
+        acc = [float(v) for v in buf]
     esize = prog.esize
     rows = {}
     for i in range(n):
         o = prog._op_array[i]
         r = rows.setdefault(op_class(o), dict(ms=0.0, launches=0, bytes=0, flops=0.0))
-        r["ms"] += acc[i] if n_iter else 1e-3
+        r["ms"] += acc[i]
         r["launches"] += 1
         r["bytes"] += op_bytes(o, esize)
         r["flops"] += op_flops(o)
-    return rows, (sum(acc) if n_iter else 1e-3 * n)
+    return rows, sum(acc)
 
 
 def run_gpu_arm(args, wl):
@@ -321,7 +317,7 @@ def run_gpu_arm(args, wl):
     line = None
     if rank == 0:
         peaks = measured_peaks()
-        rows, step_ms_eager = per_op_profile(engine, prog, n_iter=0 if args.no_op_profile else 3)
+        rows, step_ms_eager = per_op_profile(engine, prog, n_iter=0 if args.no_op_profile else 5)
         if args.op_table:
             os.makedirs(os.path.dirname(os.path.abspath(args.op_table)), exist_ok=True)
             with open(args.op_table, "w") as fh:
@@ -331,7 +327,7 @@ def run_gpu_arm(args, wl):
                     by = v["bytes"] / v["launches"]
                     fh.write(f"{k} | {v['launches']} | {us:.1f} | {by / peaks['hbm_gbs'] / 1e3:.1f} | {by / us / 1e3:.0f} | "
                              f"{v['flops'] / v['launches'] / us / 1e6:.1f} | {v['ms'] / step_ms_eager:.3f}\n")
-                fh.write(f"eager step total {step_ms_eager:.3f} ms; graph step {ms_step / T:.3f} ms; ops {prog.n_ops}\n")
+                fh.write(f"sum of per-op times {step_ms_eager:.3f} ms; graph step {ms_step / T:.3f} ms; ops {prog.n_ops}\n")
         top = max(rows.items(), key=lambda kv: kv[1]["ms"])
         per_launch_ms = top[1]["ms"] / top[1]["launches"]
         per_launch_bytes = top[1]["bytes"] / top[1]["launches"]

@@ -68,6 +68,7 @@ def lib():
     L.ccdm_plan_set_noise.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
     L.ccdm_plan_step.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
     L.ccdm_plan_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    L.ccdm_plan_profile.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.c_void_p]
     L.ccdm_launch_op.argtypes = [ctypes.POINTER(Op), ctypes.c_void_p]
     L.ccdm_sizeof_op.restype = ctypes.c_size_t
     L.ccdm_sizeof_step_entry.restype = ctypes.c_size_t
@@ -85,6 +86,7 @@ def lib():
     L.ccdm_op_part_floats.restype = ctypes.c_size_t
     L.ccdm_op_part_floats.argtypes = [ctypes.POINTER(Op)]
     L.ccdm_conv_uses_tc.argtypes = [ctypes.POINTER(Op)]
+    L.ccdm_conv_uses_tma.argtypes = [ctypes.POINTER(Op)]
     L.ccdm_conv_tc_nt.argtypes = [ctypes.c_int]
     L.ccdm_conv_tc_config.argtypes = [ctypes.POINTER(Op), ctypes.POINTER(ctypes.c_int32)]
     L.ccdm_conv_part_floats.restype = ctypes.c_size_t

@@ -114,6 +114,12 @@ int launch_attention_ffma(const ccdm_op &op, cudaStream_t s) {
     }
 }
 
-int launch_attention(const ccdm_op &op, cudaStream_t s) { return launch_attention_ffma(op, s); }
+bool attention_tc_supported(const ccdm_op &op);
+int launch_attention_tc(const ccdm_op &op, cudaStream_t s);
+
+int launch_attention(const ccdm_op &op, cudaStream_t s) {
+    if (attention_tc_supported(op)) return launch_attention_tc(op, s);
+    return launch_attention_ffma(op, s);
+}
 
 }  // namespace ccdm

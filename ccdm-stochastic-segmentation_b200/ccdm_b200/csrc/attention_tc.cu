@@ -1,0 +1,264 @@
+// QKVAttentionLegacy (reference unet.py:343-360) on the 5th-generation tensor cores, for bf16 activations
+// in the plane-major layout and head_dim = 32 (every shipped configuration: num_head_channels = 32).
+//
+//   softmax((q*s)(k*s)^T) v,  s = 32^-1/4, per (sample, head), never materialising the [T,T] scores.
+//
+// One CTA = one (sample, head, tile of 128 queries), 128 threads; key/value tiles of NK keys stream through
+// shared memory (double buffered, cp.async.bulk + mbarrier).  Because qkv is stored plane-major,
+// [B][3C/8][T][8], a tile of q, k or v is four contiguous runs (one per 8-channel plane) and lands in
+// shared memory ALREADY in a tcgen05 operand layout -- no transpose, no staging through registers:
+//     q, k : "K-major, no swizzle"  (rows = tokens, 16-byte rows of 8 channels; LBO = plane stride)
+//     v    : "MN-major, no swizzle" (N = channels contiguous inside a 16-byte row, K = keys 16 B apart,
+//                                    LBO = 128 B between groups of 8 keys, SBO = plane stride)
+// Per key tile:  S = Q K^T (tcgen05.mma, fp32 in TMEM)  ->  every thread owns one query row: tcgen05.ld,
+// running max / sum, P = exp2((S - m) * log2(e)/sqrt(32)) as bf16 into shared memory (K-major A operand)
+// ->  O_tile = P V (tcgen05.mma)  ->  o = o * corr + O_tile in registers.  Several CTAs are resident per
+// SM (TMEM: 256 of 512 columns each at NK = 128), so one CTA's softmax overlaps another's MMAs and loads.
+//
+// Output: [B][C/8][T][8] bf16, channel(h, d) = h*32 + d (unet.py:360).
+#include "tc_common.cuh"
+
+namespace ccdm {
+namespace {
+
+constexpr int AT_D = 32;       // head_dim
+constexpr int AT_QT = 128;     // queries per CTA = threads = MMA M
+constexpr int AT_PLANES = AT_D / 8;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct AtP {
+    const __nv_bfloat16 *qkv;  // [B][3C/8][T][8]
+    __nv_bfloat16 *out;        // [B][C/8][T][8]
+    int T, heads, q_tiles;
+    float scale_log2;          // log2(e) / sqrt(head_dim)
+    uint32_t idesc_s, idesc_pv;
+};
+
+template <int NK>
+__global__ void __launch_bounds__(AT_QT) attention_tc_kernel(const AtP p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr uint32_t Q_BYTES = AT_PLANES * AT_QT * 16;  // 8 KB
+    constexpr uint32_t KV_BYTES = AT_PLANES * NK * 16;    // per tensor per buffer
+    constexpr uint32_t P_BYTES = (NK / 8) * AT_QT * 16;
+    uint8_t *sQ = smem;
+    uint8_t *sK = sQ + Q_BYTES;        // [2][KV_BYTES]
+    uint8_t *sV = sK + 2 * KV_BYTES;   // [2][KV_BYTES]
+    uint8_t *sP = sV + 2 * KV_BYTES;   // [NK/8 planes][128 rows][16 B]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sP + P_BYTES);
+    uint64_t *kv_full = bars, *s_done = bars + 2, *o_done = bars + 3;
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 4);
+    constexpr uint32_t TMEM_COLS = NK + 32 <= 64 ? 64 : (NK + 32 <= 128 ? 128 : 256);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int qt = blockIdx.x % p.q_tiles, bh = blockIdx.x / p.q_tiles;
+    const int h = bh % p.heads, b = bh / p.heads;
+    const int T = p.T, q0 = qt * AT_QT;
+    const int nq = min(AT_QT, T - q0);
+    const int n_tiles = (T + NK - 1) / NK;
+    const int planes3 = p.heads * 3 * AT_PLANES;  // planes of the qkv tensor
+    // plane g of (which = 0 q | 1 k | 2 v) of this head: channel h*96 + which*32 + 8g
+    auto plane_ptr = [&](int which, int g) { return p.qkv + ((size_t(b) * planes3 + h * 3 * AT_PLANES + which * AT_PLANES + g) * T) * 8; };
+
+    if (warp == 0) tmem_alloc(s_tmem, TMEM_COLS);
+    if (tid == 0) {
+        mbar_init(kv_full + 0, 1);
+        mbar_init(kv_full + 1, 1);
+        mbar_init(s_done, 1);
+        mbar_init(o_done, 1);
+        fence_barrier_init();
+    }
+    // rows of a partial tile that no copy overwrites must hold finite values (0 * NaN would poison P V)
+    for (uint32_t i = tid * 16; i < Q_BYTES + 4 * KV_BYTES; i += AT_QT * 16) *reinterpret_cast<uint4 *>(smem + i) = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_s = *s_tmem, tmem_o = tmem_s + NK;
+    const uint32_t trow = uint32_t(warp * 32) << 16;  // this warp's TMEM lane quarter
+
+    auto load_kv = [&](int t, int buf, uint32_t extra_bytes) {  // thread 0
+        const int k0 = t * NK, nk = min(NK, T - k0);
+        mbar_expect_tx(kv_full + buf, uint32_t(2 * AT_PLANES * nk * 16) + extra_bytes);
+#pragma unroll
+        for (int g = 0; g < AT_PLANES; ++g) {
+            bulk_g2s(sK + buf * KV_BYTES + g * NK * 16, plane_ptr(1, g) + size_t(k0) * 8, uint32_t(nk * 16), kv_full + buf);
+            bulk_g2s(sV + buf * KV_BYTES + g * NK * 16, plane_ptr(2, g) + size_t(k0) * 8, uint32_t(nk * 16), kv_full + buf);
+        }
+    };
+    if (tid == 0) {
+        load_kv(0, 0, uint32_t(AT_PLANES * nq * 16));
+#pragma unroll
+        for (int g = 0; g < AT_PLANES; ++g) bulk_g2s(sQ + g * AT_QT * 16, plane_ptr(0, g) + size_t(q0) * 8, uint32_t(nq * 16), kv_full + 0);
+    }
+
+    const uint32_t desc_hi = 8u | (1u << 14);                                   // SBO 128 B, version 1
+    const uint32_t q_lo = (smem_u32(sQ) >> 4) | (uint32_t(AT_QT) << 16);        // LBO = plane stride (128 rows)
+    const uint32_t p_lo = (smem_u32(sP) >> 4) | (uint32_t(AT_QT) << 16);
+    const uint32_t v_hi = uint32_t(NK) | (1u << 14);                            // MN-major: SBO = plane stride (NK rows)
+
+    float o[AT_D];
+#pragma unroll
+    for (int d = 0; d < AT_D; ++d) o[d] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    const float c = p.scale_log2;
+
+    for (int t = 0; t < n_tiles; ++t) {
+        const int buf = t & 1;
+        const int nk = min(NK, T - t * NK);
+        if (tid == 0) {
+            if (t + 1 < n_tiles) load_kv(t + 1, buf ^ 1, 0u);  // that buffer's last reader (P V of tile t-1) has completed
+            mbar_wait(kv_full + buf, uint32_t(t >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t k_lo = (smem_u32(sK + buf * KV_BYTES) >> 4) | (uint32_t(NK) << 16);
+#pragma unroll
+            for (int j = 0; j < AT_D / 16; ++j)
+                umma_bf16(tmem_s, (uint64_t(desc_hi) << 32) | (q_lo + uint32_t(j * 2 * AT_QT)), (uint64_t(desc_hi) << 32) | (k_lo + uint32_t(j * 2 * NK)),
+                          p.idesc_s, j > 0 ? 1u : 0u);
+            umma_commit(s_done);
+        }
+        mbar_wait(s_done, uint32_t(t) & 1u);
+        tc_fence_after();
+        // pass 1: row maximum of the tile
+        float tmax = -INFINITY;
+#pragma unroll
+        for (int c0 = 0; c0 < NK; c0 += 32) {
+            if (c0 < nk) {
+                float s[32];
+                tmem_ld32(tmem_s + trow + uint32_t(c0), s);
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (c0 + i < nk) tmax = fmaxf(tmax, s[i]);
+            }
+        }
+        const float m_new = fmaxf(m, tmax);
+        const float corr = ex2_approx((m - m_new) * c);  // m = -inf on the first tile -> 0
+        const float mc = m_new * c;
+        float rsum = 0.f;
+        // pass 2: P = exp2(S*c - m*c) as bf16, K-major rows for the P V product
+#pragma unroll
+        for (int c0 = 0; c0 < NK; c0 += 32) {
+            uint32_t pk[16];
+            if (c0 < nk) {
+                float s[32];
+                tmem_ld32(tmem_s + trow + uint32_t(c0), s);
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float p0 = (c0 + i < nk) ? ex2_approx(fmaf(s[i], c, -mc)) : 0.f;
+                    float p1 = (c0 + i + 1 < nk) ? ex2_approx(fmaf(s[i + 1], c, -mc)) : 0.f;
+                    pk[i / 2] = pack_bf16(p0, p1);
+                    const float2 f = unpack_bf16(pk[i / 2]);  // the sum of what the MMA will actually see
+                    rsum += f.x + f.y;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pk[i] = 0u;
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g)  // key planes c0/8 .. c0/8+3, this thread's row
+                *reinterpret_cast<uint4 *>(sP + (size_t(c0 / 8 + g) * AT_QT + tid) * 16) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+        }
+        l = l * corr + rsum;
+        m = m_new;
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();  // P complete and visible to the tensor core; every thread is done reading S
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t v_lo = (smem_u32(sV + buf * KV_BYTES) >> 4) | (8u << 16);  // LBO = 128 B between groups of 8 keys
+#pragma unroll
+            for (int j = 0; j < NK / 16; ++j)
+                umma_bf16(tmem_o, (uint64_t(desc_hi) << 32) | (p_lo + uint32_t(j * 2 * AT_QT)), (uint64_t(v_hi) << 32) | (v_lo + uint32_t(j * 16)),
+                          p.idesc_pv, j > 0 ? 1u : 0u);
+            umma_commit(o_done);
+        }
+        mbar_wait(o_done, uint32_t(t) & 1u);
+        tc_fence_after();
+        {
+            float ot[32];
+            tmem_ld32(tmem_o + trow, ot);
+#pragma unroll
+            for (int d = 0; d < AT_D; ++d) o[d] = fmaf(o[d], corr, ot[d]);
+        }
+        // No CTA barrier here: the next S MMA overwrites S, which every thread finished reading before the
+        // barrier above; the next P V overwrites O only after the next iteration's barrier, which every
+        // thread reaches after this read; the K/V buffer refilled next was last read by MMAs that completed.
+        tc_fence_before();
+    }
+
+    if (tid < nq) {
+        const float inv = 1.0f / l;
+        const int planes = p.heads * AT_PLANES;
+#pragma unroll
+        for (int g = 0; g < AT_PLANES; ++g) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pk[i] = pack_bf16(o[8 * g + 2 * i] * inv, o[8 * g + 2 * i + 1] * inv);
+            __nv_bfloat16 *dst = p.out + ((size_t(b) * planes + h * AT_PLANES + g) * T + q0 + tid) * 8;
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_s, TMEM_COLS);
+    }
+}
+
+template <int NK>
+int launch_nk(const AtP &p, int grid, cudaStream_t s) {
+    constexpr size_t smem = AT_PLANES * AT_QT * 16 + 4 * AT_PLANES * NK * 16 + (NK / 8) * AT_QT * 16 + 64;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CCDM_CUDA(cudaFuncSetAttribute(attention_tc_kernel<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        attr_done = true;
+    }
+    attention_tc_kernel<NK><<<grid, AT_QT, smem, s>>>(p);
+    CCDM_LAUNCH_CHECK("attention_tc_kernel");
+    return 0;
+}
+
+}  // namespace
+
+bool attention_tc_supported(const ccdm_op &op) { return op.dtype == CCDM_DT_BF16 && op.head_dim == AT_D && !op.exact && op.heads > 0; }
+
+int launch_attention_tc(const ccdm_op &op, cudaStream_t s) {
+    const int T = op.Hin * op.Win;
+    if (op.C0 != op.heads * AT_D * 3) CCDM_FAIL(-2, "attention_tc: qkv channels %d != 3*heads*32", op.C0);
+    AtP p{};
+    p.qkv = (const __nv_bfloat16 *)op.src0;
+    p.out = (__nv_bfloat16 *)op.out;
+    p.T = T;
+    p.heads = op.heads;
+    p.q_tiles = (T + AT_QT - 1) / AT_QT;
+    p.scale_log2 = float(1.4426950408889634 / sqrt(double(AT_D)));  // unet.py:354: q and k are each scaled by 32^-1/4
+    const int NK = T <= 64 ? 64 : 128;
+    // cute::UMMA::InstrDescriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), b_major = MN (bit 16), N>>3 at 17, M>>4 at 24
+    const uint32_t base = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(128 >> 4) << 24);
+    p.idesc_s = base | (uint32_t(NK >> 3) << 17);
+    p.idesc_pv = base | (uint32_t(AT_D >> 3) << 17) | (1u << 16);
+    const int grid = op.B * op.heads * p.q_tiles;
+    if (!p.qkv || !p.out || T <= 0 || grid <= 0) CCDM_FAIL(-2, "attention_tc: missing tensors");
+    return NK == 64 ? launch_nk<64>(p, grid, s) : launch_nk<128>(p, grid, s);
+}
+
+}  // namespace ccdm

@@ -18,6 +18,8 @@
 // GroupNorm scale/shift and SiLU are applied while staging, and out-of-image halo
 // elements are written as exact zeros AFTER the activation (zero padding happens
 // after GN+SiLU in the reference: conv2d(padding=1) sees SiLU(GN(x)) padded with 0).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ccdm {
@@ -374,15 +376,31 @@ bool conv_tc_supported(const ccdm_op &op);
 size_t conv_tc_part_floats(const ccdm_op &op);
 int launch_conv_tc(const ccdm_op &op, cudaStream_t s);
 
-bool conv_uses_tc(const ccdm_op &op) { return !op.exact && op.kind == CCDM_OP_CONV && conv_tc_supported(op); }
+bool conv_tma_supported(const ccdm_op &op);
+size_t conv_tma_part_floats(const ccdm_op &op);
+int launch_conv_tma(const ccdm_op &op, cudaStream_t s);
+
+// CCDM_CONV_TMA=0 routes every tensor-core conv to the LDG-fed kernel (A/B measurements)
+static bool tma_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("CCDM_CONV_TMA");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+bool conv_uses_tma(const ccdm_op &op) { return !op.exact && op.kind == CCDM_OP_CONV && tma_enabled() && conv_tma_supported(op); }
+bool conv_uses_tc(const ccdm_op &op) { return !op.exact && op.kind == CCDM_OP_CONV && (conv_uses_tma(op) || conv_tc_supported(op)); }
 
 size_t op_part_floats(const ccdm_op &op) {
     if (op.kind != CCDM_OP_CONV && op.kind != CCDM_OP_INPUT_CONV) return 0;
+    if (conv_uses_tma(op)) return conv_tma_part_floats(op);
     if (conv_uses_tc(op)) return conv_tc_part_floats(op);
     return conv_part_floats(op.B, op.Hout, op.Wout, op.Cout);
 }
 
 int launch_conv(const ccdm_op &op, cudaStream_t s) {
+    if (conv_uses_tma(op)) return launch_conv_tma(op, s);
     if (conv_uses_tc(op)) return launch_conv_tc(op, s);
     ConvP p{};
     p.src0 = (const void *)op.src0; p.src1 = (const void *)op.src1;

@@ -1,0 +1,268 @@
+// Pieces shared by the two tcgen05 conv kernels (conv_tma.cu: TMA-fed, conv_ws.cu: LDG-fed): the launch
+// parameter block, the work-item decoding and the epilogue role (TMEM -> registers -> +bias +embedding
+// +residual -> plane-major bf16 / NHWC fp32 store + GroupNorm statistics of the output).
+#pragma once
+
+#include "tc_common.cuh"
+
+namespace ccdm {
+namespace {
+
+constexpr int EPI_WARPS = 4;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int MAX_STAGES = 8;
+constexpr int CGW = 16;  // accumulator columns per tcgen05.ld
+
+struct WsP {
+    const __nv_bfloat16 *src0, *src1;
+    const double *stat0, *stat1;
+    const float *gamma, *beta;
+    const __nv_bfloat16 *weight;  // [cc][Cin/8][tap][NT][8]
+    const float *bias, *emb;
+    const __nv_bfloat16 *skip0, *skip1;
+    const __nv_bfloat16 *skip_w;  // [cc][S/8][NT][8]
+    const __nv_bfloat16 *res;
+    void *out;
+    double *ostat;
+    float *part;
+    unsigned int *ticket;
+    const ccdm_step_entry *steps;
+    const int *step_ptr;
+    int B, Hin, Win, H, W;  // H, W: conv-input == output space (after the optional x2)
+    int C0, C1, Cin, Cout, CoutP, NT, n_cc;
+    int upsample, gn, silu, S0, S1, emb_off, emb_cols, emb_bstride, out_f32;
+    int R, Wt, P, MB, WN, tiles_x, tiles, taps, pad;
+    int n_main, n_skip, NS, resident, acc2, tmem_cols, n_items;
+    int ips, slots;  // items per sample; statistics slots per sample (CTAs whose item range can touch one sample)
+    int RW, NQ, xf;  // conv_tma: window rows, window positions (= plane stride in 16-byte rows), 1 if chunks are transformed in smem
+    uint32_t a_stage, w_stage, w_main_bytes, w_skip_bytes, magicP;
+    uint32_t idesc;
+};
+
+struct Item {
+    int b, tile, cc, y0, x0, co0;
+};
+__device__ __forceinline__ Item decode_item(const WsP &p, int it) {
+    Item r;
+    r.cc = it % p.n_cc;
+    const int t = it / p.n_cc;
+    r.tile = t % p.tiles;
+    r.b = t / p.tiles;
+    const int ty = r.tile / p.tiles_x, tx = r.tile - ty * p.tiles_x;
+    r.y0 = ty * p.R;
+    r.x0 = tx * p.Wt;
+    r.co0 = r.cc * p.NT;
+    return r;
+}
+
+
+// Epilogue role: warps 0..NEW-1 of the CTA, NEW = 4 or 8.  Warp w may only touch TMEM lanes
+// 32*(w%4)..+31 (= accumulator rows 32*(w%4)+lane of every M block); with 8 warps the two warps of a lane
+// quarter split the 16-column groups of the accumulator between them.  Named barrier 2 is private to
+// these NEW*32 threads.
+template <int NEW>
+__device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, float *sRed, int *s_last, uint64_t *acc_full,
+                                                   uint64_t *acc_empty, uint32_t tmem_base, int it_begin, int it_end) {
+    constexpr int NTHR = NEW * 32;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int quarter = warp & 3, half = warp >> 2;
+    constexpr int NHALF = NEW / 4;
+    const int NT = p.NT, P = p.P;
+    // GroupNorm statistics of the output: per-thread sums over an item -> warp transpose-reduce ->
+    // per-warp running sums in shared memory (sAcc), flushed to global ONCE per (CTA, sample): a CTA's
+    // items are contiguous, so this is one or two partial rows per CTA instead of one per item.
+    float *sAcc = sRed;  // [NEW][CoutP][2]
+    const int CoutP = p.CoutP;
+    if (p.ostat != nullptr) {
+        for (int e = lane; e < CoutP * 2; e += 32) sAcc[warp * CoutP * 2 + e] = 0.f;
+        __syncwarp();
+    }
+    auto flush_stats = [&](int b, int n_done) {
+        named_bar_sync(2, NTHR);
+        const int c_first = int((((long long)b * p.ips + 1) * gridDim.x - 1) / p.n_items);
+        const int slot = int(blockIdx.x) - c_first;
+        for (int e = tid; e < CoutP * 2; e += NTHR) {
+            float s = 0.f;
+#pragma unroll
+            for (int r = 0; r < NEW; ++r) {
+                s += sAcc[r * CoutP * 2 + e];
+                sAcc[r * CoutP * 2 + e] = 0.f;
+            }
+            p.part[(size_t(b) * p.slots + slot) * CoutP * 2 + e] = s;
+        }
+        __threadfence();
+        named_bar_sync(2, NTHR);
+        if (tid == 0) {
+            const unsigned int prev = atomicAdd(p.ticket + b, unsigned(n_done));
+            *s_last = (prev + unsigned(n_done) == unsigned(p.ips));
+        }
+        named_bar_sync(2, NTHR);
+        if (*s_last) {
+            // every item of this sample is done somewhere on the chip: fold the per-CTA partial rows in
+            // slot order, in double (the consumer's GroupNorm reads these sums) -- a fixed order, so the
+            // result does not depend on which CTA finishes last
+            __threadfence();
+            const int c_last = int(((long long)(b + 1) * p.ips * gridDim.x - 1) / p.n_items);
+            const int n_slots = c_last - c_first + 1;
+            for (int e = tid; e < p.Cout * 2; e += NTHR) {
+                const float *pp = p.part + size_t(b) * p.slots * CoutP * 2 + e;
+                double s = 0.0;
+                for (int t = 0; t < n_slots; ++t) s += double(__ldcg(pp + size_t(t) * CoutP * 2));
+                p.ostat[size_t(b) * p.Cout * 2 + e] = s;
+            }
+            if (tid == 0) p.ticket[b] = 0u;  // self-reset for the next launch
+        }
+        named_bar_sync(2, NTHR);  // s_last is reused by the next flush
+    };
+
+    // accumulator row of this thread inside an M block, as (window row, window column); M blocks advance
+    // it by 128 positions = (d128r, d128c) with one carry
+    const int j0 = quarter * 32 + lane;
+    const int o0 = int((uint32_t(j0) * p.magicP) >> 20), c0 = j0 - o0 * P;
+    const int d128r = int((128u * p.magicP) >> 20), d128c = 128 - d128r * P;
+    const size_t hw = size_t(p.H) * p.W;
+    const int n_cg = NT / CGW;
+
+    int acc_it = 0, cur_b = -1, cur_cc = -1, n_pending = 0;
+    for (int it = it_begin; it < it_end; ++it, ++acc_it) {
+        const Item I = decode_item(p, it);
+        if (I.b != cur_b && n_pending > 0) {
+            if (p.ostat != nullptr) flush_stats(cur_b, n_pending);
+            n_pending = 0;
+        }
+        if (I.b != cur_b || I.cc != cur_cc) {
+            named_bar_sync(2, NTHR);
+            for (int c = tid; c < NT; c += NTHR) {
+                float v = p.bias[I.co0 + c];
+                if (p.emb != nullptr && I.co0 + c < p.Cout) {
+                    const ccdm_step_entry &se = p.steps[*p.step_ptr];
+                    v += p.emb[(size_t(se.emb_row) + size_t(I.b) * p.emb_bstride) * p.emb_cols + p.emb_off + I.co0 + c];
+                }
+                sAdd[c] = v;
+            }
+            named_bar_sync(2, NTHR);
+            cur_b = I.b;
+            cur_cc = I.cc;
+        }
+        const int buf = p.acc2 ? (acc_it & 1) : 0;
+        const uint32_t aph = p.acc2 ? uint32_t((acc_it >> 1) & 1) : uint32_t(acc_it & 1);
+        const uint32_t tbase = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * p.MB * NT);
+        const int ylim = min(p.R, p.H - I.y0), xlim = min(p.Wt, p.W - I.x0);  // rows / columns of real outputs
+        const size_t pix0 = size_t(I.y0) * p.W + I.x0;
+        bool waited = false;
+        for (int cg = half; cg < n_cg; cg += NHALF) {
+            const int cobase = I.co0 + cg * CGW;
+            float add[CGW];
+#pragma unroll
+            for (int i = 0; i < CGW; i += 4) {
+                const float4 t = *reinterpret_cast<const float4 *>(sAdd + cg * CGW + i);
+                add[i] = t.x; add[i + 1] = t.y; add[i + 2] = t.z; add[i + 3] = t.w;
+            }
+            // plane-major bases of this thread's two 8-channel planes (bf16 in/out) or the NHWC fp32 row
+            const size_t plane0 = (size_t(I.b) * (p.Cout >> 3) + (cobase >> 3)) * hw + pix0;
+            const __nv_bfloat16 *resb = p.res != nullptr ? p.res + plane0 * 8 : nullptr;
+            __nv_bfloat16 *outb = reinterpret_cast<__nv_bfloat16 *>(p.out) + plane0 * 8;
+            float *outf = reinterpret_cast<float *>(p.out) + (size_t(I.b) * hw + pix0) * p.Cout + cobase;
+            float s1[CGW], s2[CGW];
+#pragma unroll
+            for (int i = 0; i < CGW; ++i) s1[i] = 0.f, s2[i] = 0.f;
+            int o = o0, c = c0;
+            // software pipeline: the residual of row block mb+1 is fetched while block mb is processed
+            uint4 res_n[CGW / 8];
+            bool valid_n = o < ylim && c < xlim;
+            int off_n = o * p.W + c;
+            if (resb != nullptr && valid_n) {
+#pragma unroll
+                for (int h2 = 0; h2 < CGW / 8; ++h2) res_n[h2] = ldg_nc16(resb + (size_t(h2) * hw + off_n) * 8);
+            }
+            if (!waited) {
+                mbar_wait(acc_full + buf, aph);
+                tc_fence_after();
+                waited = true;
+            }
+            for (int mb = 0; mb < p.MB; ++mb) {
+                const bool valid = valid_n;
+                const int off = off_n;
+                uint4 rr[CGW / 8];
+#pragma unroll
+                for (int h2 = 0; h2 < CGW / 8; ++h2) rr[h2] = res_n[h2];
+                if (mb + 1 < p.MB) {
+                    c += d128c;
+                    o += d128r;
+                    if (c >= P) {
+                        c -= P;
+                        ++o;
+                    }
+                    valid_n = o < ylim && c < xlim;
+                    off_n = o * p.W + c;
+                    if (resb != nullptr && valid_n) {
+#pragma unroll
+                        for (int h2 = 0; h2 < CGW / 8; ++h2) res_n[h2] = ldg_nc16(resb + (size_t(h2) * hw + off_n) * 8);
+                    }
+                }
+                float v[CGW];
+                tmem_ld16(tbase + uint32_t(mb * NT + cg * CGW), v);
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < CGW; ++i) v[i] += add[i];
+                    if (resb != nullptr) {
+#pragma unroll
+                        for (int h2 = 0; h2 < CGW / 8; ++h2) {
+                            const uint32_t w4[4] = {rr[h2].x, rr[h2].y, rr[h2].z, rr[h2].w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                float2 f = unpack_bf16(w4[i]);
+                                v[h2 * 8 + 2 * i] += f.x;
+                                v[h2 * 8 + 2 * i + 1] += f.y;
+                            }
+                        }
+                    }
+                    if (p.out_f32) {  // fp32 logits stay NHWC
+                        float *op = outf + size_t(off) * p.Cout;
+#pragma unroll
+                        for (int i = 0; i < CGW; ++i)
+                            if (cobase + i < p.Cout) op[i] = v[i];
+                    } else {
+#pragma unroll
+                        for (int h2 = 0; h2 < CGW / 8; ++h2) {
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) pk[i] = pack_bf16(v[h2 * 8 + 2 * i], v[h2 * 8 + 2 * i + 1]);
+                            *reinterpret_cast<uint4 *>(outb + (size_t(h2) * hw + off) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        }
+                    }
+                    // statistics of the fp32 values (the bf16 rounding error is zero-mean: over >= 64 pixels
+                    // per channel it changes the sums far below the GroupNorm epsilon)
+#pragma unroll
+                    for (int i = 0; i < CGW; ++i) {
+                        s1[i] += v[i];
+                        s2[i] = fmaf(v[i], v[i], s2[i]);
+                    }
+                }
+            }
+            if (p.ostat != nullptr) {
+                const float r1 = warp_transpose_reduce16(s1, lane);
+                const float r2 = warp_transpose_reduce16(s2, lane);
+                if ((lane & 1) == 0) {
+                    const int ch = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                    float *a = sAcc + (warp * CoutP + cobase + ch) * 2;
+                    a[0] += r1;
+                    a[1] += r2;
+                }
+            }
+        }
+        if (!waited) {  // a warp without a column group of its own still has to observe the phase
+            mbar_wait(acc_full + buf, aph);
+            tc_fence_after();
+        }
+        // accumulator buffer drained: hand it back to the MMA warps
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty + buf);
+        ++n_pending;
+    }
+    if (p.ostat != nullptr && n_pending > 0) flush_stats(cur_b, n_pending);
+}
+
+}  // namespace
+}  // namespace ccdm

@@ -1,0 +1,588 @@
+// Fused GroupNorm + SiLU + conv (3x3 / 1x1, stride 1) on the 5th-generation tensor cores, fed by TMA.
+//
+// Same arithmetic and same "flattened padded tile" implicit GEMM as conv_ws.cu (see there), but the data
+// path is the one the hardware is built for:
+//
+//   * bf16 activations live in HBM PLANE-MAJOR, [B][C/8][H][W][8]: 16 bytes per (8-channel plane, pixel),
+//     i.e. exactly one row of a tcgen05 "K-major, no swizzle" core matrix.  A 4-D TMA box
+//     {window width, window rows, planes of the K chunk, sample} therefore lands in shared memory ALREADY
+//     in the MMA operand layout (plane stride = LBO), zero-filled outside the image, with one instruction
+//     issued by one thread -- no register staging, no address arithmetic, any number of stages in flight.
+//   * GroupNorm-apply + SiLU is an IN-PLACE pass over the landed stage (LDS.128 -> fp32 affine, tanh.approx
+//     -> bf16 -> STS.128, conflict-free), done by 8 warps that never see global-memory latency.  Raw chunks
+//     (1x1 skip conv, convs without a norm) skip the pass: TMA -> MMA directly.
+//   * tcgen05.mma is issued by TWO warps (even / odd M blocks): at N = 32 a single issuing thread
+//     cannot keep the tensor pipe fed (measured: ~90 cycles of issue per 16-cycle MMA).
+//   * epilogue (conv_tc_common.cuh): TMEM -> registers -> +bias +embedding +residual -> plane-major store
+//     (a warp writes 512 contiguous bytes per plane) + GroupNorm statistics of the output.
+//
+// Replaces (reference unet.py): ResBlock convs :242-262 (with GroupNorm32 nn.py:93-100 + SiLU), the 1x1
+// skip_connection :221-228,262, attention qkv / proj_out :305-311, the output conv :701-705.
+//
+// Roles (608 threads, one CTA per SM, each CTA walks a contiguous range of work items):
+//   warps 0-7   epilogue | warps 8-15 in-place transform | warps 16-17 MMA issue | warp 18 TMA.
+// All hand-offs are mbarriers; nothing in the main loop is a CTA-wide barrier.
+#include <cuda.h>
+
+#include "conv_tc_common.cuh"
+
+namespace ccdm {
+namespace {
+
+constexpr int TM_EPI_WARPS = 8, XF_WARPS = 8, MMA_WARPS = 2;
+constexpr int XF_THREADS = XF_WARPS * 32;
+constexpr int WARP_XF0 = TM_EPI_WARPS, WARP_MMA0 = WARP_XF0 + XF_WARPS, WARP_TMA = WARP_MMA0 + MMA_WARPS;
+constexpr int TM_THREADS = (WARP_TMA + 2) * 32;  // 640: five warpgroups (the last warp only pads the fifth)
+
+struct alignas(64) TmP {
+    CUtensorMap map[4];  // src0, src1, skip0, skip1 (plane-major tensors, see make_map)
+    WsP w;
+};
+
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr));
+    return r;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// GroupNorm affine (+ SiLU as h + h*tanh(h), h = x/2 with the 1/2 folded into fa/fb) of one 16-byte row
+// (8 channels of one pixel), fp32 maths, bf16 in and out.
+template <bool SILU>
+__device__ __forceinline__ uint4 xf_row(uint4 raw, const float (&fa)[8], const float (&fb)[8]) {
+    const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+    uint32_t r4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 v = unpack_bf16(w4[i]);
+        float h0 = fmaf(v.x, fa[2 * i], fb[2 * i]);
+        float h1 = fmaf(v.y, fa[2 * i + 1], fb[2 * i + 1]);
+        if (SILU) {
+            h0 = fmaf(h0, tanh_approx(h0), h0);
+            h1 = fmaf(h1, tanh_approx(h1), h1);
+        }
+        r4[i] = pack_bf16(h0, h1);
+    }
+    return make_uint4(r4[0], r4[1], r4[2], r4[3]);
+}
+
+// In-place pass of one thread over its rows q0, q0 + STEP, ... < NQ of one plane of a landed stage.  MASK:
+// the tile touches the image border; halo rows outside the image were zero-filled by TMA and must STAY
+// zero (the reference pads after GroupNorm + SiLU), so they are skipped; (r, c) tracks the window
+// coordinates of the current row incrementally.
+template <int STEP, bool MASK, bool SILU>
+__device__ __forceinline__ void xf_pass(uint32_t addr, int q, int NQ, int r, int c, int dr, int dc, int P, int ymin, int xmin, int H,
+                                        int W, const float (&fa)[8], const float (&fb)[8]) {
+    auto advance = [&]() {
+        if (MASK) {
+            c += dc;
+            r += dr;
+            if (c >= P) {
+                c -= P;
+                ++r;
+            }
+        }
+    };
+    auto ok = [&]() -> bool { return !MASK || (unsigned(ymin + r) < unsigned(H) && unsigned(xmin + c) < unsigned(W)); };
+    for (; q + 3 * STEP < NQ; q += 4 * STEP, addr += 4u * STEP * 16u) {
+        uint4 raw[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) raw[u] = lds128(addr + uint32_t(u) * STEP * 16u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (ok()) sts128(addr + uint32_t(u) * STEP * 16u, xf_row<SILU>(raw[u], fa, fb));
+            advance();
+        }
+    }
+    for (; q < NQ; q += STEP, addr += uint32_t(STEP) * 16u) {
+        const uint4 raw = lds128(addr);
+        if (ok()) sts128(addr, xf_row<SILU>(raw, fa, fb));
+        advance();
+    }
+}
+
+// PL = planes (8-channel groups) per K chunk: KC = 8*PL channels per pipeline stage.
+template <int PL>
+__global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_constant__ TmP P_) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const WsP &p = P_.w;
+    constexpr int KC = 8 * PL;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NT = p.NT, P = p.P, NS = p.NS, NQ = p.NQ;
+
+    // smem carve-up: [NS] activation stages (+ over-read slack) | weights | GN affine | bias | stats | barriers
+    uint8_t *sA = smem_raw;
+    const size_t slack = size_t(128 + 2 * p.pad * P + 2 * p.pad) * 16;
+    uint8_t *sW = sA + size_t(NS) * p.a_stage + ((slack + 127) & ~size_t(127));
+    const size_t w_region = p.resident ? size_t(p.w_main_bytes) + p.w_skip_bytes : size_t(NS) * p.w_stage;
+    float *sAff = reinterpret_cast<float *>(sW + w_region);  // [2][Cin]
+    float *sAdd = sAff + 2 * p.Cin;                          // [NT]
+    float *sRed = sAdd + NT;                                 // [8][CoutP][2]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sRed + TM_EPI_WARPS * p.CoutP * 2);
+    uint64_t *raw_full = bars, *xf_full = bars + MAX_STAGES, *empty = bars + 2 * MAX_STAGES;
+    uint64_t *acc_full = bars + 3 * MAX_STAGES, *acc_empty = acc_full + 2, *w_res = acc_empty + 2;
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(w_res + 1);
+    int *s_last = reinterpret_cast<int *>(s_tmem + 1);
+
+    if (warp == WARP_MMA0) tmem_alloc(s_tmem, uint32_t(p.tmem_cols));
+    if (tid == WARP_TMA * 32) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(raw_full + s, 1);
+            mbar_init(xf_full + s, XF_WARPS);
+            mbar_init(empty + s, MMA_WARPS);
+        }
+        mbar_init(acc_full + 0, MMA_WARPS);
+        mbar_init(acc_full + 1, MMA_WARPS);
+        mbar_init(acc_empty + 0, TM_EPI_WARPS);
+        mbar_init(acc_empty + 1, TM_EPI_WARPS);
+        mbar_init(w_res, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&P_.map[0]);
+        if (p.C1) tma_prefetch_desc(&P_.map[1]);
+        if (p.S0) tma_prefetch_desc(&P_.map[2]);
+        if (p.S1) tma_prefetch_desc(&P_.map[3]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+    if (tid == 0 && (smem_u32(sA) & 127u)) {
+        printf("conv_tma: dynamic shared memory is not 128-byte aligned\n");
+        __trap();
+    }
+
+    const int it_begin = int((long long)blockIdx.x * p.n_items / gridDim.x);
+    const int it_end = int((long long)(blockIdx.x + 1) * p.n_items / gridDim.x);
+    const int n_chunks = p.n_main + p.n_skip;
+
+    // Register budget per role (setmaxnreg works on whole warpgroups of 4 warps): the kernel launches with
+    // 96 registers per thread; the epilogue warpgroups grow to 128, the others shrink and donate theirs.
+    if (warp < TM_EPI_WARPS) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+        conv_epilogue_role<TM_EPI_WARPS>(p, sAdd, sRed, s_last, acc_full, acc_empty, tmem_base, it_begin, it_end);
+    } else if (warp < WARP_MMA0) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        // =========================== in-place GroupNorm + SiLU ======================================
+        // Warp xw owns plane (xw % PL) of every transformed stage, so its 8 scale/shift pairs are warp
+        // uniform and live in registers; the XF_WARPS/PL warps of a plane interleave blocks of 32 positions.
+        if (p.xf) {
+            const int xw = warp - WARP_XF0, pt = tid - WARP_XF0 * 32;
+            const int plane = xw & (PL - 1), sub = xw / PL;
+            constexpr int NSUB = XF_WARPS / PL;
+            constexpr int STEP = NSUB * 32;
+            const int dr = int((uint32_t(STEP) * p.magicP) >> 20), dc = STEP - dr * P;
+            int stage = 0, cur_b = -1;
+            uint32_t phase = 0;
+            const uint32_t sA32 = smem_u32(sA);
+            for (int it = it_begin; it < it_end; ++it) {
+                const Item I = decode_item(p, it);
+                if (p.gn && I.b != cur_b) {
+                    // GroupNorm scale/shift of the (concatenated) input of sample b; the SiLU's 0.5 is
+                    // folded in: silu(x) = h + h*tanh(h), h = x/2.
+                    named_bar_sync(1, XF_THREADS);
+                    const int cpg = p.Cin / kGnGroups;
+                    const double n = double(cpg) * double(p.Hin) * double(p.Win);
+                    const float half = p.silu ? 0.5f : 1.0f;
+                    for (int c = pt; c < p.Cin; c += XF_THREADS) {
+                        const int g0 = (c / cpg) * cpg;
+                        double s = 0.0, q = 0.0;
+                        for (int j = 0; j < cpg; ++j) {
+                            const int cc = g0 + j;
+                            const double *st = cc < p.C0 ? p.stat0 + (size_t(I.b) * p.C0 + cc) * 2 : p.stat1 + (size_t(I.b) * p.C1 + (cc - p.C0)) * 2;
+                            s += st[0];
+                            q += st[1];
+                        }
+                        const double mean = s / n;
+                        double var = q / n - mean * mean;
+                        var = var < 0.0 ? 0.0 : var;
+                        const float rstd = float(1.0 / sqrt(var + double(kGnEps)));
+                        const float a = p.gamma[c] * rstd;
+                        sAff[c] = half * a;
+                        sAff[p.Cin + c] = half * (p.beta[c] - float(mean) * a);
+                    }
+                    named_bar_sync(1, XF_THREADS);
+                    cur_b = I.b;
+                }
+                // halo positions outside the image were zero-filled by TMA and must stay zero (the
+                // reference pads AFTER GroupNorm + SiLU): interior tiles skip the test altogether
+                const int ymin = I.y0 - p.pad, xmin = I.x0 - p.pad;
+                const bool need_mask = ymin < 0 || ymin + p.RW > p.H || xmin < 0 || xmin + P > p.W;
+                const int q0 = sub * 32 + lane;
+                const int r0 = int((uint32_t(q0) * p.magicP) >> 20), c0 = q0 - r0 * P;
+                for (int kc = 0; kc < n_chunks; ++kc) {
+                    // every chunk is acknowledged on xf_full (raw skip-conv chunks without touching them), so
+                    // that barrier completes exactly one phase per use of the stage, like the others; waiting
+                    // for the TMA first also keeps these warps from running ahead of the ring
+                    if (kc >= p.n_main) {
+                        mbar_wait(raw_full + stage, phase);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(xf_full + stage);
+                    } else {
+                        float fa[8], fb[8];
+                        if (p.gn) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                fa[i] = sAff[kc * KC + 8 * plane + i];
+                                fb[i] = sAff[p.Cin + kc * KC + 8 * plane + i];
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) fa[i] = p.silu ? 0.5f : 1.0f, fb[i] = 0.f;
+                        }
+                        mbar_wait(raw_full + stage, phase);
+                        const uint32_t addr = sA32 + uint32_t(stage) * p.a_stage + (uint32_t(plane) * uint32_t(NQ) + uint32_t(q0)) * 16u;
+                        if (need_mask) {
+                            if (p.silu) xf_pass<STEP, true, true>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
+                            else xf_pass<STEP, true, false>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
+                        } else {
+                            if (p.silu) xf_pass<STEP, false, true>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
+                            else xf_pass<STEP, false, false>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(xf_full + stage);
+                    }
+                    if (++stage == NS) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp < WARP_TMA) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        // =========================== MMA issue (two warps: M blocks mw, mw+2, ...) ==================
+        const int mw = warp - WARP_MMA0;
+        int stage = 0, acc_it = 0;
+        uint32_t phase = 0;
+        if (p.resident) mbar_wait(w_res, 0);
+        const uint32_t desc_hi = 8u | (1u << 14);  // SBO = 128 B, descriptor version 1
+        const uint32_t a0 = (smem_u32(sA) >> 4) | (uint32_t(NQ) << 16);  // LBO of A: plane stride = NQ rows
+        const uint32_t w0 = smem_u32(sW) >> 4;
+        const uint32_t a_stage16 = p.a_stage >> 4, w_stage16 = p.w_stage >> 4;
+        const uint32_t kA = 2u * uint32_t(NQ);
+        for (int it = it_begin; it < it_end; ++it, ++acc_it) {
+            const int buf = p.acc2 ? (acc_it & 1) : 0;
+            const uint32_t aph = p.acc2 ? uint32_t((acc_it >> 1) & 1) : uint32_t(acc_it & 1);
+            mbar_wait(acc_empty + buf, aph ^ 1u);
+            tc_fence_after();
+            const uint32_t d0 = tmem_base + uint32_t(buf * p.MB * NT);
+            for (int kc = 0; kc < n_chunks; ++kc) {
+                const bool is_skip = kc >= p.n_main;
+                const int ntap = is_skip ? 1 : p.taps;
+                mbar_wait((p.xf ? xf_full : raw_full) + stage, phase);
+                tc_fence_after();
+                const uint32_t aaddr = a0 + uint32_t(stage) * a_stage16;
+                uint32_t waddr;
+                if (p.resident)
+                    waddr = is_skip ? w0 + (p.w_main_bytes >> 4) + uint32_t((kc - p.n_main) * PL * NT) : w0 + uint32_t(kc * PL * ntap * NT);
+                else
+                    waddr = w0 + uint32_t(stage) * w_stage16;
+                waddr |= uint32_t(ntap * NT) << 16;  // LBO of B: one 8-channel plane = ntap * NT rows of 16 bytes
+                const uint32_t kB = 2u * uint32_t(ntap * NT);
+                if (ntap == 9) {
+                    for (int mb = mw; mb < p.MB; mb += MMA_WARPS) {
+                        const uint32_t d = d0 + uint32_t(mb * NT);
+                        const uint32_t arow = aaddr + uint32_t(mb * 128);
+                        uint32_t acc = kc > 0 ? 1u : 0u;
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const uint32_t at = arow + uint32_t((tap / 3) * P + (tap % 3));
+                            const uint32_t bt = waddr + uint32_t(tap * NT);
+#pragma unroll
+                            for (int k16 = 0; k16 < PL / 2; ++k16) {
+                                umma_bf16_split(d, at + k16 * kA, desc_hi, bt + k16 * kB, desc_hi, p.idesc, acc);
+                                acc = 1u;
+                            }
+                        }
+                    }
+                } else {
+                    // 1x1 conv, or the fused 1x1 skip conv of a 3x3 block (centre tap of the window)
+                    const uint32_t shift = is_skip ? uint32_t(p.pad * P + p.pad) : 0u;
+                    for (int mb = mw; mb < p.MB; mb += MMA_WARPS) {
+                        const uint32_t d = d0 + uint32_t(mb * NT);
+                        const uint32_t at = aaddr + uint32_t(mb * 128) + shift;
+#pragma unroll
+                        for (int k16 = 0; k16 < PL / 2; ++k16)
+                            umma_bf16_split(d, at + k16 * kA, desc_hi, waddr + k16 * kB, desc_hi, p.idesc, (kc > 0 || k16 > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit_elect(empty + stage);
+                if (++stage == NS) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+            umma_commit_elect(acc_full + buf);
+        }
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        // =========================== TMA: activation windows + weights ============================
+        if (warp == WARP_TMA && lane == 0 && it_begin < it_end) {
+            if (p.resident) {
+                mbar_expect_tx(w_res, p.w_main_bytes + p.w_skip_bytes);
+                bulk_g2s(sW, p.weight, p.w_main_bytes, w_res);
+                if (p.w_skip_bytes) bulk_g2s(sW + p.w_main_bytes, p.skip_w, p.w_skip_bytes, w_res);
+            }
+            int stage = 0;
+            uint32_t phase = 0;
+            const int planes_main = p.Cin / 8, planes_skip = (p.S0 + p.S1) / 8;
+            const uint32_t a_bytes = uint32_t(PL) * uint32_t(NQ) * 16u;
+            for (int it = it_begin; it < it_end; ++it) {
+                const Item I = decode_item(p, it);
+                for (int kc = 0; kc < n_chunks; ++kc) {
+                    const bool is_skip = kc >= p.n_main;
+                    const int cbase = is_skip ? (kc - p.n_main) * KC : kc * KC;
+                    const int CA = is_skip ? p.S0 : p.C0;
+                    const bool first = cbase < CA;
+                    const CUtensorMap *map = &P_.map[(is_skip ? 2 : 0) + (first ? 0 : 1)];
+                    const int g0 = (first ? cbase : cbase - CA) >> 3;
+                    uint32_t bytes = a_bytes;
+                    const __nv_bfloat16 *wsrc = nullptr;
+                    uint32_t wbytes = 0;
+                    if (!p.resident) {
+                        wbytes = uint32_t(PL * (is_skip ? 1 : p.taps) * NT) * 16;
+                        wsrc = is_skip ? p.skip_w + (size_t(I.cc) * planes_skip + size_t(kc - p.n_main) * PL) * NT * 8
+                                       : p.weight + (size_t(I.cc) * planes_main + size_t(kc) * PL) * p.taps * NT * 8;
+                        bytes += wbytes;
+                    }
+                    mbar_wait(empty + stage, phase ^ 1u);
+                    mbar_expect_tx(raw_full + stage, bytes);
+                    // box {2P x 8-byte elements, RW rows, PL planes, 1 sample}; x is counted in 8-byte units
+                    tma_load_4d(sA + size_t(stage) * p.a_stage, map, 2 * (I.x0 - p.pad), I.y0 - p.pad, g0, I.b, raw_full + stage);
+                    if (wbytes) bulk_g2s(sW + size_t(stage) * p.w_stage, wsrc, wbytes, raw_full + stage);
+                    if (++stage == NS) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == WARP_MMA0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, uint32_t(p.tmem_cols));
+    }
+}
+
+// ---- host-side configuration --------------------------------------------------------------------
+struct TmCfg {
+    int PL, R, RW, NQ, Wt, P, MB, NT, n_cc, NS, resident, acc2, tmem_cols, tiles_x, tiles, n_main, n_skip, n_items, grid, ips, slots;
+    uint32_t a_stage, w_stage, w_main_bytes, w_skip_bytes, magicP;
+    size_t smem;
+};
+
+constexpr size_t kTmSmemBudget = 224 * 1024;  // of the 227 KB a CTA may opt in to
+constexpr size_t kTmResidentMax = 80 * 1024;  // weights kept in smem for the whole launch when they fit
+constexpr int kTmNumSMs = 148;
+
+int tm_nt(int Cout) {
+    const int CoutP = (Cout + 15) / 16 * 16;
+    for (int nt = 64; nt >= 16; nt -= 16)
+        if (CoutP % nt == 0) return nt;
+    return 16;
+}
+
+bool tm_configure(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout, int ksize, TmCfg &best) {
+    const int Cin = C0 + C1, Sk = S0 + S1;
+    if (Cin <= 0 || (C0 % 16) || (C1 % 16) || (S0 % 16) || (S1 % 16)) return false;
+    const int pad = ksize / 2, taps = ksize * ksize;
+    const int CoutP = (Cout + 15) / 16 * 16;
+    TmCfg c{};
+    c.NT = tm_nt(Cout);
+    c.n_cc = CoutP / c.NT;
+    const bool all32 = !(C0 % 32) && !(C1 % 32) && !(S0 % 32) && !(S1 % 32);
+    c.PL = all32 ? 4 : 2;
+    const int KC = 8 * c.PL;
+    c.n_main = Cin / KC;
+    c.n_skip = Sk / KC;
+    const int n_chunks = c.n_main + c.n_skip;
+    c.Wt = W > 64 ? 64 : W;
+    c.P = c.Wt + 2 * pad;
+    if (2 * c.P > 256) return false;  // TMA box limit (8-byte elements)
+    c.magicP = uint32_t(((1u << 20) + c.P - 1) / c.P);
+    c.tiles_x = (W + c.Wt - 1) / c.Wt;
+    c.w_main_bytes = uint32_t(size_t(Cin) * taps * c.NT * 2);
+    c.w_skip_bytes = uint32_t(size_t(Sk) * c.NT * 2);
+    const size_t w_total = size_t(c.w_main_bytes) + c.w_skip_bytes;
+    c.resident = (c.n_cc == 1 && w_total <= kTmResidentMax) ? 1 : 0;
+    c.w_stage = c.resident ? 0u : uint32_t(c.PL * taps * c.NT * 16);
+    const size_t slack = (size_t(128 + 2 * pad * c.P + 2 * pad) * 16 + 127) & ~size_t(127);
+    const size_t fixed = sizeof(float) * (2 * size_t(Cin) + c.NT + size_t(TM_EPI_WARPS) * CoutP * 2) + (3 * MAX_STAGES + 5) * 8 + 64 + slack +
+                         (c.resident ? w_total : 0) + 1024;
+    double best_cost = 1e300;
+    bool found = false;
+    for (int R = 1; R <= H && R + 2 * pad <= 256; ++R) {
+        const int MB = (R * c.P + 127) / 128;
+        if (MB * c.NT > 512) break;
+        const int RW = R + 2 * pad, NQ = RW * c.P;
+        bool magic_ok = true;
+        for (int q = 0; q < NQ + 256; ++q)
+            if (int((uint32_t(q) * c.magicP) >> 20) != q / c.P) magic_ok = false;
+        if (!magic_ok) continue;
+        const size_t a_stage = (size_t(c.PL) * NQ * 16 + 127) & ~size_t(127);
+        if (fixed + 2 * (a_stage + c.w_stage) > kTmSmemBudget) break;
+        int NS = int((kTmSmemBudget - fixed) / (a_stage + c.w_stage));
+        NS = NS > MAX_STAGES ? MAX_STAGES : NS;
+        const int tiles = ((H + R - 1) / R) * c.tiles_x;
+        const long long items = (long long)B * tiles * c.n_cc;
+        const int grid = int(items < kTmNumSMs ? items : kTmNumSMs);
+        const long long per_cta = (items + grid - 1) / grid;
+        // transform work per item (window positions x channels, skip chunks are only copied) + M-block padding
+        // + a fixed per-item hand-off cost
+        const double item_cost = double(NQ) * (Cin + 0.25 * Sk) + double(MB * 128) * (0.15 * (Cin + Sk)) + 3000.0;
+        double cost = double(per_cta) * item_cost;
+        if (NS < 3) cost *= 1.5;
+        else if (NS < 4) cost *= 1.1;
+        if (2 * MB * c.NT > 512) cost *= 1.15;  // single accumulator buffer: epilogue not overlapped
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = c;
+            best.R = R; best.RW = RW; best.NQ = NQ; best.MB = MB; best.NS = NS; best.a_stage = uint32_t(a_stage);
+            best.acc2 = 2 * MB * c.NT <= 512;
+            best.tiles = tiles; best.n_items = int(items); best.grid = grid;
+            int cols = 32;
+            while (cols < (best.acc2 ? 2 : 1) * MB * c.NT) cols *= 2;
+            best.tmem_cols = cols;
+            best.smem = fixed + size_t(NS) * (a_stage + c.w_stage);
+            found = true;
+        }
+    }
+    (void)n_chunks;
+    if (found) {
+        best.ips = best.tiles * best.n_cc;
+        best.slots = 1;
+        for (int b = 0; b < B; ++b) {
+            const int c_first = int((((long long)b * best.ips + 1) * best.grid - 1) / best.n_items);
+            const int c_last = int(((long long)(b + 1) * best.ips * best.grid - 1) / best.n_items);
+            if (c_last - c_first + 1 > best.slots) best.slots = c_last - c_first + 1;
+        }
+    }
+    return found;
+}
+
+bool tm_configure_op(const ccdm_op &op, TmCfg &c) {
+    return tm_configure(op.B, op.Hout, op.Wout, op.C0, op.C1, op.S0, op.S1, op.Cout, op.ksize, c);
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// Tensor map of a plane-major bf16 activation [B][C/8][H][W][8], viewed as 8-byte elements so that a
+// window row is ONE contiguous run of the innermost dimension: dims {2W, H, C/8, B}, box {2P, RW, PL, 1}.
+int make_map(CUtensorMap *m, const void *base, int B, int C, int H, int W, int P, int RW, int PL) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) CCDM_FAIL(-5, "conv_tma: cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[4] = {cuuint64_t(2) * W, cuuint64_t(H), cuuint64_t(C / 8), cuuint64_t(B)};
+    const cuuint64_t strides[3] = {cuuint64_t(W) * 16, cuuint64_t(H) * W * 16, cuuint64_t(C / 8) * H * W * 16};
+    const cuuint32_t box[4] = {cuuint32_t(2 * P), cuuint32_t(RW), cuuint32_t(PL), 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) CCDM_FAIL(-5, "conv_tma: cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d,%d] box %dx%dx%d", int(r), B, C, H, W, P, RW, PL);
+    return 0;
+}
+
+}  // namespace
+
+bool conv_tma_supported(const ccdm_op &op) {
+    if (op.dtype != CCDM_DT_BF16 || op.src_kind != 0 || op.stride != 1 || op.upsample) return false;
+    if (op.ksize != 1 && op.ksize != 3) return false;
+    if ((op.C0 % 16) || (op.C1 % 16) || (op.S0 % 16) || (op.S1 % 16)) return false;
+    if (op.out_dtype == CCDM_DT_BF16 && (op.Cout % 16)) return false;
+    if (op.Hin != op.Hout || op.Win != op.Wout) return false;
+    TmCfg c;
+    return tm_configure_op(op, c);
+}
+
+// {PL, R, Wt, MB, NQ, NT, n_cc, NS, resident, acc2, tmem_cols, tiles, n_items, grid, smem bytes, n_chunks}
+int conv_tma_config(const ccdm_op &op, int32_t *out) {
+    TmCfg c;
+    if (!conv_tma_supported(op) || !tm_configure_op(op, c)) return -1;
+    const int32_t v[16] = {c.PL, c.R, c.Wt, c.MB, c.NQ, c.NT, c.n_cc, c.NS, c.resident, c.acc2, c.tmem_cols, c.tiles, c.n_items, c.grid,
+                           int32_t(c.smem), c.n_main + c.n_skip};
+    for (int i = 0; i < 16; ++i) out[i] = v[i];
+    return 0;
+}
+
+size_t conv_tma_part_floats(const ccdm_op &op) {
+    TmCfg c;
+    if (!tm_configure_op(op, c)) return 0;
+    return size_t(op.B) * c.slots * ((op.Cout + 15) / 16 * 16) * 2;
+}
+
+int launch_conv_tma(const ccdm_op &op, cudaStream_t s) {
+    TmCfg c;
+    if (!conv_tma_supported(op) || !tm_configure_op(op, c)) CCDM_FAIL(-3, "conv_tma: unsupported configuration");
+    TmP P{};
+    WsP &p = P.w;
+    p.src0 = (const __nv_bfloat16 *)op.src0; p.src1 = (const __nv_bfloat16 *)op.src1;
+    p.stat0 = (const double *)op.stat0; p.stat1 = (const double *)op.stat1;
+    p.gamma = (const float *)op.gamma; p.beta = (const float *)op.beta;
+    p.weight = (const __nv_bfloat16 *)op.weight; p.bias = (const float *)op.bias; p.emb = (const float *)op.emb;
+    p.skip0 = (const __nv_bfloat16 *)op.skip0; p.skip1 = (const __nv_bfloat16 *)op.skip1;
+    p.skip_w = (const __nv_bfloat16 *)op.skip_w; p.res = (const __nv_bfloat16 *)op.res;
+    p.out = (void *)op.out; p.ostat = (double *)op.ostat; p.part = (float *)op.part; p.ticket = (unsigned int *)op.ticket;
+    p.steps = (const ccdm_step_entry *)op.steps; p.step_ptr = (const int *)op.step_ptr;
+    p.B = op.B; p.Hin = op.Hin; p.Win = op.Win; p.H = op.Hout; p.W = op.Wout;
+    p.C0 = op.C0; p.C1 = op.C1; p.Cin = op.C0 + op.C1; p.Cout = op.Cout; p.CoutP = (op.Cout + 15) / 16 * 16;
+    p.NT = c.NT; p.n_cc = c.n_cc;
+    p.upsample = 0; p.gn = op.gn; p.silu = op.silu; p.S0 = op.S0; p.S1 = op.S1;
+    p.emb_off = op.emb_off; p.emb_cols = op.emb_cols; p.emb_bstride = op.emb_bstride;
+    p.out_f32 = op.out_dtype == CCDM_DT_F32;
+    p.R = c.R; p.Wt = c.Wt; p.P = c.P; p.MB = c.MB; p.WN = c.NQ; p.tiles_x = c.tiles_x; p.tiles = c.tiles;
+    p.taps = op.ksize * op.ksize; p.pad = op.ksize / 2;
+    p.n_main = c.n_main; p.n_skip = c.n_skip; p.NS = c.NS; p.resident = c.resident; p.acc2 = c.acc2;
+    p.tmem_cols = c.tmem_cols; p.n_items = c.n_items; p.ips = c.ips; p.slots = c.slots;
+    p.RW = c.RW; p.NQ = c.NQ; p.xf = (op.gn || op.silu) ? 1 : 0;
+    p.a_stage = c.a_stage; p.w_stage = c.w_stage; p.w_main_bytes = c.w_main_bytes; p.w_skip_bytes = c.w_skip_bytes;
+    p.magicP = c.magicP;
+    // cute::UMMA::InstrDescriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major both, N>>3 at 17, M>>4 at 24
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(c.NT >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+
+    if (op.gn && (!op.stat0 || (op.C1 && !op.stat1) || !op.gamma || !op.beta)) CCDM_FAIL(-2, "conv_tma: gn without stats/affine");
+    if (op.gn && (p.Cin % kGnGroups)) CCDM_FAIL(-2, "conv_tma: GroupNorm needs Cin %% 32 == 0");
+    if (op.ostat && (!op.part || !op.ticket)) CCDM_FAIL(-2, "conv_tma: ostat without scratch");
+    if (op.emb && (!op.steps || !op.step_ptr || op.emb_off < 0)) CCDM_FAIL(-2, "conv_tma: emb without step table");
+    if (op.S0 > 0 && (!op.skip0 || !op.skip_w)) CCDM_FAIL(-2, "conv_tma: bad skip configuration");
+    if (!op.src0 || (op.C1 && !op.src1) || (op.S1 && !op.skip1)) CCDM_FAIL(-2, "conv_tma: missing source tensor");
+
+    int rc = make_map(&P.map[0], (const void *)op.src0, op.B, op.C0, op.Hout, op.Wout, c.P, c.RW, c.PL);
+    if (rc == 0 && op.C1) rc = make_map(&P.map[1], (const void *)op.src1, op.B, op.C1, op.Hout, op.Wout, c.P, c.RW, c.PL);
+    if (rc == 0 && op.S0) rc = make_map(&P.map[2], (const void *)op.skip0, op.B, op.S0, op.Hout, op.Wout, c.P, c.RW, c.PL);
+    if (rc == 0 && op.S1) rc = make_map(&P.map[3], (const void *)op.skip1, op.B, op.S1, op.Hout, op.Wout, c.P, c.RW, c.PL);
+    if (rc != 0) return rc;
+
+    static bool attr_done = false;
+    if (!attr_done) {
+        CCDM_CUDA(cudaFuncSetAttribute(conv_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTmSmemBudget)));
+        CCDM_CUDA(cudaFuncSetAttribute(conv_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTmSmemBudget)));
+        attr_done = true;
+    }
+    if (c.PL == 4)
+        conv_tma_kernel<4><<<c.grid, TM_THREADS, c.smem, s>>>(P);
+    else
+        conv_tma_kernel<2><<<c.grid, TM_THREADS, c.smem, s>>>(P);
+    CCDM_LAUNCH_CHECK("conv_tma_kernel");
+    return 0;
+}
+
+}  // namespace ccdm

@@ -29,59 +29,16 @@
 //                          they fit (resident), else one chunk per stage.
 // All hand-offs are mbarriers; nothing in the main loop is a CTA-wide barrier.
 #include "common.cuh"
-#include "tc_common.cuh"
+#include "conv_tc_common.cuh"
 
 namespace ccdm {
 namespace {
 
-constexpr int EPI_WARPS = 4, PROD_WARPS = 8;
-constexpr int PROD_THREADS = PROD_WARPS * 32, EPI_THREADS = EPI_WARPS * 32;
+constexpr int PROD_WARPS = 8;
+constexpr int PROD_THREADS = PROD_WARPS * 32;
 constexpr int WARP_MMA = EPI_WARPS + PROD_WARPS, WARP_LOAD = WARP_MMA + 1;
 constexpr int WS_THREADS = (WARP_LOAD + 1) * 32;  // 448
-constexpr int MAX_STAGES = 8;
 constexpr int UB = 4;    // loads per producer batch (two batches in flight)
-constexpr int CGW = 16;  // accumulator columns per tcgen05.ld
-
-struct WsP {
-    const __nv_bfloat16 *src0, *src1;
-    const double *stat0, *stat1;
-    const float *gamma, *beta;
-    const __nv_bfloat16 *weight;  // [cc][Cin/8][tap][NT][8]
-    const float *bias, *emb;
-    const __nv_bfloat16 *skip0, *skip1;
-    const __nv_bfloat16 *skip_w;  // [cc][S/8][NT][8]
-    const __nv_bfloat16 *res;
-    void *out;
-    double *ostat;
-    float *part;
-    unsigned int *ticket;
-    const ccdm_step_entry *steps;
-    const int *step_ptr;
-    int B, Hin, Win, H, W;  // H, W: conv-input == output space (after the optional x2)
-    int C0, C1, Cin, Cout, CoutP, NT, n_cc;
-    int upsample, gn, silu, S0, S1, emb_off, emb_cols, emb_bstride, out_f32;
-    int R, Wt, P, MB, WN, tiles_x, tiles, taps, pad;
-    int n_main, n_skip, NS, resident, acc2, tmem_cols, n_items;
-    int ips, slots;  // items per sample; statistics slots per sample (CTAs whose item range can touch one sample)
-    uint32_t a_stage, w_stage, w_main_bytes, w_skip_bytes, magicP;
-    uint32_t idesc;
-};
-
-struct Item {
-    int b, tile, cc, y0, x0, co0;
-};
-__device__ __forceinline__ Item decode_item(const WsP &p, int it) {
-    Item r;
-    r.cc = it % p.n_cc;
-    const int t = it / p.n_cc;
-    r.tile = t % p.tiles;
-    r.b = t / p.tiles;
-    const int ty = r.tile / p.tiles_x, tx = r.tile - ty * p.tiles_x;
-    r.y0 = ty * p.R;
-    r.x0 = tx * p.Wt;
-    r.co0 = r.cc * p.NT;
-    return r;
-}
 
 // ---- the kernel -------------------------------------------------------------------------------
 // PL = planes (8-channel groups) per K chunk: KC = 8*PL channels per pipeline stage.
@@ -130,185 +87,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
     const int n_chunks = p.n_main + p.n_skip;
 
     if (warp < EPI_WARPS) {
-        // =========================== epilogue ===================================================
-        // GroupNorm statistics of the output: per-thread sums over an item -> warp transpose-reduce ->
-        // per-warp running sums in shared memory (sAcc), flushed to global ONCE per (CTA, sample): a CTA's
-        // items are contiguous, so this is one or two partial rows per CTA instead of one per item.
-        float *sAcc = sRed;  // [EPI_WARPS][CoutP][2]
-        const int CoutP = p.CoutP;
-        if (p.ostat != nullptr) {
-            for (int e = lane; e < CoutP * 2; e += 32) sAcc[warp * CoutP * 2 + e] = 0.f;
-            __syncwarp();
-        }
-        auto flush_stats = [&](int b, int n_done) {
-            named_bar_sync(2, EPI_THREADS);
-            const int c_first = int((((long long)b * p.ips + 1) * gridDim.x - 1) / p.n_items);
-            const int slot = int(blockIdx.x) - c_first;
-            for (int e = tid; e < CoutP * 2; e += EPI_THREADS) {
-                float s = 0.f;
-#pragma unroll
-                for (int r = 0; r < EPI_WARPS; ++r) {
-                    s += sAcc[r * CoutP * 2 + e];
-                    sAcc[r * CoutP * 2 + e] = 0.f;
-                }
-                p.part[(size_t(b) * p.slots + slot) * CoutP * 2 + e] = s;
-            }
-            __threadfence();
-            named_bar_sync(2, EPI_THREADS);
-            if (tid == 0) {
-                const unsigned int prev = atomicAdd(p.ticket + b, unsigned(n_done));
-                *s_last = (prev + unsigned(n_done) == unsigned(p.ips));
-            }
-            named_bar_sync(2, EPI_THREADS);
-            if (*s_last) {
-                // every item of this sample is done somewhere on the chip: fold the per-CTA partial rows in
-                // slot order, in double (the consumer's GroupNorm reads these sums) -- a fixed order, so the
-                // result does not depend on which CTA finishes last
-                __threadfence();
-                const int c_last = int(((long long)(b + 1) * p.ips * gridDim.x - 1) / p.n_items);
-                const int n_slots = c_last - c_first + 1;
-                for (int e = tid; e < p.Cout * 2; e += EPI_THREADS) {
-                    const float *pp = p.part + size_t(b) * p.slots * CoutP * 2 + e;
-                    double s = 0.0;
-                    for (int t = 0; t < n_slots; ++t) s += double(__ldcg(pp + size_t(t) * CoutP * 2));
-                    p.ostat[size_t(b) * p.Cout * 2 + e] = s;
-                }
-                if (tid == 0) p.ticket[b] = 0u;  // self-reset for the next launch
-            }
-            named_bar_sync(2, EPI_THREADS);  // s_last is reused by the next flush
-        };
-
-        int acc_it = 0, cur_b = -1, cur_cc = -1, n_pending = 0;
-        for (int it = it_begin; it < it_end; ++it, ++acc_it) {
-            const Item I = decode_item(p, it);
-            if (I.b != cur_b && n_pending > 0) {
-                if (p.ostat != nullptr) flush_stats(cur_b, n_pending);
-                n_pending = 0;
-            }
-            if (I.b != cur_b || I.cc != cur_cc) {
-                named_bar_sync(2, EPI_THREADS);
-                for (int c = tid; c < NT; c += EPI_THREADS) {
-                    float v = p.bias[I.co0 + c];
-                    if (p.emb != nullptr && I.co0 + c < p.Cout) {
-                        const ccdm_step_entry &se = p.steps[*p.step_ptr];
-                        v += p.emb[(size_t(se.emb_row) + size_t(I.b) * p.emb_bstride) * p.emb_cols + p.emb_off + I.co0 + c];
-                    }
-                    sAdd[c] = v;
-                }
-                named_bar_sync(2, EPI_THREADS);
-                cur_b = I.b;
-                cur_cc = I.cc;
-            }
-            const int buf = p.acc2 ? (acc_it & 1) : 0;
-            const uint32_t aph = p.acc2 ? uint32_t((acc_it >> 1) & 1) : uint32_t(acc_it & 1);
-            // pixel of accumulator row (mb, this thread) and whether it is a real output
-            auto coords = [&](int mb, size_t &pix) -> bool {
-                const int j = mb * 128 + warp * 32 + lane;
-                const int o = int((uint32_t(j) * p.magicP) >> 20), c = j - o * P;
-                const int y = I.y0 + o, x = I.x0 + c;
-                pix = size_t(y) * p.W + x;  // pixel inside the sample
-                return o < p.R && c < p.Wt && y < p.H && x < p.W;
-            };
-            // the residual of the first row block can be fetched before the accumulators are ready
-            const size_t hw = size_t(p.H) * p.W;
-            size_t pix_n;
-            bool valid_n = coords(0, pix_n);
-            uint4 res_n[CGW / 8];
-            auto fetch_res = [&](int cobase) {
-                if (p.res != nullptr && valid_n) {
-                    // plane-major: 16 bytes per (plane, pixel); a warp's 32 rows are 32 consecutive pixels
-                    const __nv_bfloat16 *rp = p.res + ((size_t(I.b) * (p.Cout >> 3) + (cobase >> 3)) * hw + pix_n) * 8;
-#pragma unroll
-                    for (int h2 = 0; h2 < CGW / 8; ++h2) res_n[h2] = ldg_nc16(rp + size_t(h2) * hw * 8);
-                }
-            };
-            fetch_res(I.co0);
-            mbar_wait(acc_full + buf, aph);
-            tc_fence_after();
-            const uint32_t tbase = tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(buf * p.MB * NT);
-            const int n_cg = NT / CGW;
-            for (int cg = 0; cg < n_cg; ++cg) {
-                float s1[CGW], s2[CGW];
-#pragma unroll
-                for (int i = 0; i < CGW; ++i) s1[i] = 0.f, s2[i] = 0.f;
-                const int cobase = I.co0 + cg * CGW;
-                for (int mb = 0; mb < p.MB; ++mb) {
-                    const bool valid = valid_n;
-                    const size_t pix = pix_n;
-                    uint4 rr[CGW / 8];
-#pragma unroll
-                    for (int h2 = 0; h2 < CGW / 8; ++h2) rr[h2] = res_n[h2];
-                    // software pipeline: issue the residual fetch of the NEXT row block (or of the next
-                    // channel group's first block) before touching this block's accumulators
-                    if (mb + 1 < p.MB) {
-                        valid_n = coords(mb + 1, pix_n);
-                        fetch_res(cobase);
-                    } else if (cg + 1 < n_cg) {
-                        valid_n = coords(0, pix_n);
-                        fetch_res(cobase + CGW);
-                    }
-                    float v[CGW];
-                    tmem_ld16(tbase + uint32_t(mb * NT + cg * CGW), v);
-                    if (valid) {
-#pragma unroll
-                        for (int i = 0; i < CGW; ++i) v[i] += sAdd[cg * CGW + i];
-                        if (p.res != nullptr) {
-#pragma unroll
-                            for (int h2 = 0; h2 < CGW / 8; ++h2) {
-                                const uint32_t w4[4] = {rr[h2].x, rr[h2].y, rr[h2].z, rr[h2].w};
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    float2 f = unpack_bf16(w4[i]);
-                                    v[h2 * 8 + 2 * i] += f.x;
-                                    v[h2 * 8 + 2 * i + 1] += f.y;
-                                }
-                            }
-                        }
-                        if (p.out_f32) {
-                            float *op = reinterpret_cast<float *>(p.out) + (size_t(I.b) * hw + pix) * p.Cout + cobase;  // fp32 logits stay NHWC
-#pragma unroll
-                            for (int i = 0; i < CGW; ++i)
-                                if (cobase + i < p.Cout) op[i] = v[i];
-                        } else {
-                            __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(p.out) + ((size_t(I.b) * (p.Cout >> 3) + (cobase >> 3)) * hw + pix) * 8;
-#pragma unroll
-                            for (int h2 = 0; h2 < CGW / 8; ++h2) {
-                                uint32_t pk[4];
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    pk[i] = pack_bf16(v[h2 * 8 + 2 * i], v[h2 * 8 + 2 * i + 1]);
-                                    float2 f = unpack_bf16(pk[i]);  // statistics of the values as stored
-                                    v[h2 * 8 + 2 * i] = f.x;
-                                    v[h2 * 8 + 2 * i + 1] = f.y;
-                                }
-                                *reinterpret_cast<uint4 *>(op + size_t(h2) * hw * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                            }
-                        }
-#pragma unroll
-                        for (int i = 0; i < CGW; ++i) {
-                            s1[i] += v[i];
-                            s2[i] = fmaf(v[i], v[i], s2[i]);
-                        }
-                    }
-                }
-                if (p.ostat != nullptr) {
-                    const float r1 = warp_transpose_reduce16(s1, lane);
-                    const float r2 = warp_transpose_reduce16(s2, lane);
-                    if ((lane & 1) == 0) {
-                        const int ch = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                        float *a = sAcc + (warp * CoutP + cobase + ch) * 2;
-                        a[0] += r1;
-                        a[1] += r2;
-                    }
-                }
-            }
-            // accumulator buffer drained: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + buf);
-            ++n_pending;
-        }
-        if (p.ostat != nullptr && n_pending > 0) flush_stats(cur_b, n_pending);
+        conv_epilogue_role<EPI_WARPS>(p, sAdd, sRed, s_last, acc_full, acc_empty, tmem_base, it_begin, it_end);
     } else if (warp < WARP_MMA) {
         // =========================== producers ==================================================
         const int pt = tid - EPI_THREADS;

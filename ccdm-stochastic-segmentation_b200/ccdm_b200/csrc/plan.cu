@@ -55,8 +55,12 @@ extern "C" size_t ccdm_conv_part_floats(int B, int Hout, int Wout, int Cout) { r
 namespace ccdm { bool conv_uses_tc(const ccdm_op &op); size_t op_part_floats(const ccdm_op &op); int conv_tc_nt(int Cout); }
 extern "C" int ccdm_conv_uses_tc(const ccdm_op *op) { return op && ccdm::conv_uses_tc(*op) ? 1 : 0; }
 extern "C" int ccdm_conv_tc_nt(int Cout) { return ccdm::conv_tc_nt(Cout); }
-namespace ccdm { int conv_tc_config(const ccdm_op &op, int32_t *out); }
-extern "C" int ccdm_conv_tc_config(const ccdm_op *op, int32_t *out16) { return op && out16 ? ccdm::conv_tc_config(*op, out16) : -1; }
+namespace ccdm { int conv_tc_config(const ccdm_op &op, int32_t *out); int conv_tma_config(const ccdm_op &op, int32_t *out); bool conv_uses_tma(const ccdm_op &op); }
+extern "C" int ccdm_conv_tc_config(const ccdm_op *op, int32_t *out16) {
+    if (!op || !out16) return -1;
+    return ccdm::conv_uses_tma(*op) ? ccdm::conv_tma_config(*op, out16) : ccdm::conv_tc_config(*op, out16);
+}
+extern "C" int ccdm_conv_uses_tma(const ccdm_op *op) { return op && ccdm::conv_uses_tma(*op) ? 1 : 0; }
 extern "C" size_t ccdm_op_part_floats(const ccdm_op *op) { return op ? ccdm::op_part_floats(*op) : 0; }
 
 extern "C" int ccdm_check_device(void) {
@@ -165,4 +169,58 @@ extern "C" int ccdm_plan_run(ccdm_plan *plan, int n_steps, int use_graph, void *
         if (rc != 0) return rc;
     }
     return 0;
+}
+
+// Per-op device time of one reverse step: every op is captured into its own one-node CUDA graph and
+// replayed `iters` times between two events, so the figure is free of host launch overhead (tensor-map
+// encoding, ctypes) even for launches of a few microseconds.  Inputs of small ops are L2-resident on
+// the replays, as they are in the real chain where the producer has just written them.  The device step
+// counter is restored afterwards (the head op advances it).  Measurement aid for bench.py, not on the
+// product path.
+extern "C" int ccdm_plan_profile(ccdm_plan *plan, int iters, float *ms_per_op, void *stream) {
+    if (!plan || !ms_per_op || iters <= 0) CCDM_FAIL(-1, "plan_profile: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaEvent_t e0, e1;
+    CCDM_CUDA(cudaEventCreate(&e0));
+    CCDM_CUDA(cudaEventCreate(&e1));
+    int rc = 0;
+    int saved_step = 0;
+    const int *step_ptr = nullptr;
+    for (auto &op : plan->ops)
+        if (op.step_ptr) step_ptr = (const int *)op.step_ptr;
+    if (step_ptr) {
+        CCDM_CUDA(cudaMemcpyAsync(&saved_step, step_ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CCDM_CUDA(cudaStreamSynchronize(s));
+    }
+    for (size_t i = 0; i < plan->ops.size() && rc == 0; ++i) {
+        cudaGraph_t g = nullptr;
+        cudaGraphExec_t ex = nullptr;
+        CCDM_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        rc = launch_any(plan->ops[i], s);
+        cudaError_t e = cudaStreamEndCapture(s, &g);
+        if (rc != 0 || e != cudaSuccess) {
+            if (g) cudaGraphDestroy(g);
+            if (rc == 0) {
+                set_error("plan_profile: capture of op %d failed: %s", int(i), cudaGetErrorString(e));
+                rc = -100;
+            }
+            break;
+        }
+        CCDM_CUDA(cudaGraphInstantiate(&ex, g, 0));
+        CCDM_CUDA(cudaGraphLaunch(ex, s));  // warm-up
+        CCDM_CUDA(cudaEventRecord(e0, s));
+        for (int k = 0; k < iters; ++k) CCDM_CUDA(cudaGraphLaunch(ex, s));
+        CCDM_CUDA(cudaEventRecord(e1, s));
+        CCDM_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CCDM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        ms_per_op[i] = ms / float(iters);
+        cudaGraphExecDestroy(ex);
+        cudaGraphDestroy(g);
+        if (step_ptr) CCDM_CUDA(cudaMemcpyAsync((void *)step_ptr, &saved_step, sizeof(int), cudaMemcpyHostToDevice, s));
+    }
+    if (step_ptr) cudaStreamSynchronize(s);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return rc;
 }

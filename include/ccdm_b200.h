@@ -136,6 +136,8 @@ size_t ccdm_op_part_floats(const ccdm_op *op);
  * is NT rows of 16 bytes, the UMMA K-major no-swizzle canonical form, and a K chunk of planes is one
  * contiguous block (one cp.async.bulk). */
 int ccdm_conv_uses_tc(const ccdm_op *op);
+/* 1 if that tensor-core conv is the TMA-fed kernel (conv_tma.cu: stride 1, no upsample), 0 if the LDG-fed one. */
+int ccdm_conv_uses_tma(const ccdm_op *op);
 int ccdm_conv_tc_nt(int Cout);
 /* Tile / pipeline configuration the tcgen05 kernel would use for `op` (introspection for DESIGN.md, the
  * bench and tests): out16 = {PL, R, Wt, MB, WN, NT, n_cc, NS, resident, acc2, tmem_cols, tiles, n_items,
@@ -208,6 +210,10 @@ int ccdm_plan_set_noise(ccdm_plan *plan, int noise_mode, uint64_t seed, int32_t 
 int ccdm_plan_step(ccdm_plan *plan, int use_graph, void *stream);
 /* n_steps reverse steps back to back (the T-loop of forward_denoising, :189-212). */
 int ccdm_plan_run(ccdm_plan *plan, int n_steps, int use_graph, void *stream);
+
+/* Measurement aid (bench.py): device time of every op of the plan, each replayed `iters` times as a
+ * one-node CUDA graph between two events; ms_per_op has ccdm_plan_num_launches() entries (host memory). */
+int ccdm_plan_profile(ccdm_plan *plan, int iters, float *ms_per_op, void *stream);
 
 #ifdef __cplusplus
 }

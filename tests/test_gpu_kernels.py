@@ -270,10 +270,19 @@ def _tc_check(out, ref, ostat=None):
     got = out.float().permute(0, 3, 1, 2).cpu()
     err = (got - ref).abs()
     assert float(err.max()) < TC_MAX and float(err.mean()) < TC_MEAN, (float(err.max()), float(err.mean()))
-    if ostat is not None:  # statistics describe the bf16 values as stored
+    if ostat is not None:
+        # The statistics are accumulated from the fp32 accumulators BEFORE the bf16 rounding of the store
+        # (conv_tc_common.cuh).  Rounding errors are zero-mean with |e| <= 2^-9 |v|, so against the sums of
+        # the stored values the difference is a random walk: ~ 2^-9 * rms * sqrt(N) (x 2 rms for squares).
         gd = out.double()
-        rs = torch.stack([gd.sum(dim=(1, 2)), (gd * gd).sum(dim=(1, 2))], dim=-1).cpu().numpy()
-        np.testing.assert_allclose(ostat.cpu().numpy(), rs, rtol=1e-5, atol=1e-2)
+        n = gd.shape[1] * gd.shape[2]
+        s1, s2 = gd.sum(dim=(1, 2)), (gd * gd).sum(dim=(1, 2))
+        rms = (s2 / n).sqrt()
+        tol1 = 6 * 2.0 ** -9 * rms * n ** 0.5 + 1e-3
+        tol2 = 20 * 2.0 ** -9 * rms * rms * n ** 0.5 + 1e-3  # squares: heavier tails (sum of 2 v e)
+        got1, got2 = ostat[..., 0], ostat[..., 1]
+        assert bool(((got1 - s1).abs() <= tol1).all()), float(((got1 - s1).abs() / tol1).max())
+        assert bool(((got2 - s2).abs() <= tol2).all()), float(((got2 - s2).abs() / tol2).max())
 
 
 @pytest.mark.parametrize("B,C0,C1,Cout,H,W", [(2, 32, 0, 32, 128, 128), (1, 32, 32, 32, 64, 64), (2, 64, 32, 64, 32, 32),
@@ -354,6 +363,38 @@ def test_attention_legacy_order(L, B, heads, T):
     torch.cuda.synchronize()
     err = float((out.cpu().permute(0, 2, 1) - ref).abs().max())
     assert err < 2e-5, err  # fp32, online softmax vs two-pass softmax
+
+
+@pytest.mark.parametrize("B,heads,T", [(2, 3, 256), (3, 4, 64), (1, 2, 2048), (2, 4, 100), (1, 4, 512), (2, 1, 129)])
+def test_attention_tensor_core_bf16(L, B, heads, T):
+    """tcgen05 attention on plane-major bf16 qkv vs torch fp32 on the same bf16-rounded inputs.  P is rounded to
+    bf16 before P V and exp2 is the approximate one: |err| <= 2e-2 on O(1) outputs, mean <= 2e-3."""
+    from ccdm_b200 import _lib
+    from ccdm_b200.engine import from_pm, to_pm
+    D = 32
+    C = heads * D
+    qkv = (_rand(B, 3 * C, T, seed=63) * 1.3).to(torch.bfloat16).float()
+    q, k, v = qkv.reshape(B * heads, 3 * D, T).split(D, dim=1)
+    s = 1 / math.sqrt(math.sqrt(D))
+    wgt = torch.softmax(torch.einsum("bct,bcs->bts", q * s, k * s), dim=-1)
+    ref = torch.einsum("bts,bcs->bct", wgt, v).reshape(B, C, T)
+    src = to_pm(qkv.permute(0, 2, 1).reshape(B, 1, T, 3 * C).to(torch.bfloat16).cuda())  # [B, 3C/8, 1, T, 8]
+    out = torch.full((B, C // 8, 1, T, 8), float("nan"), dtype=torch.bfloat16, device="cuda")
+    op = _lib.Op(kind=_lib.OP_ATTENTION, dtype=_lib.DT_BF16, out_dtype=_lib.DT_BF16, B=B, Hin=1, Win=T, Hout=1, Wout=T,
+                 C0=3 * C, Cout=C, heads=heads, head_dim=D, exact=0)
+    op.src0, op.out = src.data_ptr(), out.data_ptr()
+    _lib.check(L.ccdm_launch_op(ctypes.byref(op), _sp()))
+    torch.cuda.synchronize()
+    got = from_pm(out).reshape(B, T, C).float().cpu().permute(0, 2, 1)
+    err = (got - ref).abs()
+    assert float(err.max()) < 2e-2 and float(err.mean()) < 2e-3, (float(err.max()), float(err.mean()))
+    # the exact fp32-maths kernel on the same plane-major bf16 tensors (exact=1) agrees as well
+    out2 = torch.full_like(out, float("nan"))
+    op.exact, op.out = 1, out2.data_ptr()
+    _lib.check(L.ccdm_launch_op(ctypes.byref(op), _sp()))
+    torch.cuda.synchronize()
+    err2 = (from_pm(out2).reshape(B, T, C).float().cpu().permute(0, 2, 1) - ref).abs()
+    assert float(err2.max()) < 1.2e-2, float(err2.max())
 
 
 # ---------------------------------------------------------------------------------------
