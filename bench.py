@@ -175,6 +175,8 @@ def op_bytes(o, esize):
         if o.res:
             n += o.Hout * o.Wout * o.Cout * esize
         return B * n
+    if o.kind == _lib.OP_ENCODE_INPUT:
+        return B * o.Hin * o.Win * (1 + 4 * o.C_img + o.Cout * esize)
     if o.kind == _lib.OP_ATTENTION:
         return B * o.Hin * o.Win * (o.C0 + o.Cout) * esize
     if o.kind == _lib.OP_HEAD:
@@ -199,6 +201,8 @@ def op_class(o):
         return f"attention T={o.Hin * o.Win} heads={o.heads}"
     if o.kind == _lib.OP_HEAD:
         return f"head K={o.K}"
+    if o.kind == _lib.OP_ENCODE_INPUT:
+        return f"encode_input {o.K}+{o.C_img}->{o.Cout} planes @{o.Hout}x{o.Wout}"
     if o.kind == _lib.OP_INPUT_CONV:
         return f"input_conv {o.K}+{o.C_img}->{o.Cout} @{o.Hout}x{o.Wout}"
     tag = "conv%dx%d" % (o.ksize, o.ksize) + ("/s2" if o.stride == 2 else "") + ("/up" if o.upsample else "")

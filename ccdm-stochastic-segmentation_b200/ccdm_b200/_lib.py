@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libccdm_b200.so")
 DT_F32, DT_BF16 = 0, 1
 DRAW_SAMPLE, DRAW_MAJORITY, DRAW_CONFIDENCE, DRAW_X0, DRAW_POSTERIOR = 0, 1, 2, 3, 4
 NOISE_TENSOR, NOISE_PHILOX = 0, 1
-OP_INPUT_CONV, OP_CONV, OP_ATTENTION, OP_HEAD = 1, 2, 3, 4
+OP_INPUT_CONV, OP_CONV, OP_ATTENTION, OP_HEAD, OP_ENCODE_INPUT = 1, 2, 3, 4, 5
 ABI_VERSION = 1
 
 

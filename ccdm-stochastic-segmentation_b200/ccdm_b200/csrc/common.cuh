@@ -32,6 +32,7 @@ void set_error(const char *fmt, ...);
 int launch_conv(const ccdm_op &op, cudaStream_t s);
 int launch_attention(const ccdm_op &op, cudaStream_t s);
 int launch_head(const ccdm_op &op, cudaStream_t s);
+int launch_encode_input(const ccdm_op &op, cudaStream_t s);
 
 constexpr float kGnEps = 1e-5f;  // nn.GroupNorm default (nn.py:93-100 -> GroupNorm32(32, C))
 constexpr int kGnGroups = 32;

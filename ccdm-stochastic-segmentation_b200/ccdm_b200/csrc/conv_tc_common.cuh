@@ -34,6 +34,8 @@ struct WsP {
     int R, Wt, P, MB, WN, tiles_x, tiles, taps, pad;
     int n_main, n_skip, NS, resident, acc2, tmem_cols, n_items;
     int ips, slots;  // items per sample; statistics slots per sample (CTAs whose item range can touch one sample)
+    int stride2;     // conv_tma: 3x3 stride-2 conv (Downsample): the stage holds the 4 (row, column) parity sub-images
+    uint32_t blk16;  // conv_tma, stride 2: size of one parity sub-image block in 16-byte rows (128-byte aligned for TMA)
     int RW, NQ, xf;  // conv_tma: window rows, window positions (= plane stride in 16-byte rows), 1 if chunks are transformed in smem
     uint32_t a_stage, w_stage, w_main_bytes, w_skip_bytes, magicP;
     uint32_t idesc;

@@ -289,7 +289,12 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
                         uint32_t acc = kc > 0 ? 1u : 0u;
 #pragma unroll
                         for (int tap = 0; tap < 9; ++tap) {
-                            const uint32_t at = arow + uint32_t((tap / 3) * P + (tap % 3));
+                            // stride 1: window position + (dy, dx).  stride 2: input row 2y+dy-1 lives in the
+                            // parity sub-image ((dy+1)&1, (dx+1)&1) at sub-row y-1+(dy>0), sub-column x-1+(dx>0),
+                            // and every sub-image starts one row / column before the tile
+                            const uint32_t at = arow + (p.stride2 ? uint32_t(((((tap / 3) + 1) & 1) * 2 + (((tap % 3) + 1) & 1)) * p.blk16 +
+                                                                             ((tap / 3) > 0 ? P : 0) + ((tap % 3) > 0 ? 1 : 0))
+                                                                  : uint32_t((tap / 3) * P + (tap % 3)));
                             const uint32_t bt = waddr + uint32_t(tap * NT);
 #pragma unroll
                             for (int k16 = 0; k16 < PL / 2; ++k16) {
@@ -349,9 +354,19 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
                         bytes += wbytes;
                     }
                     mbar_wait(empty + stage, phase ^ 1u);
-                    mbar_expect_tx(raw_full + stage, bytes);
-                    // box {2P x 8-byte elements, RW rows, PL planes, 1 sample}; x is counted in 8-byte units
-                    tma_load_4d(sA + size_t(stage) * p.a_stage, map, 2 * (I.x0 - p.pad), I.y0 - p.pad, g0, I.b, raw_full + stage);
+                    if (p.stride2) {
+                        // four boxes, one per (row, column) parity, each traversing the input with element
+                        // stride 2: {1 position, P sub-columns, RW sub-rows, PL planes, 1 sample}
+                        mbar_expect_tx(raw_full + stage, 4 * bytes - 3 * wbytes);
+#pragma unroll
+                        for (int par = 0; par < 4; ++par)
+                            tma_load_5d(sA + size_t(stage) * p.a_stage + size_t(par) * p.blk16 * 16, map, 0, 2 * (I.x0 - 1) + (par & 1),
+                                        2 * (I.y0 - 1) + (par >> 1), g0, I.b, raw_full + stage);
+                    } else {
+                        mbar_expect_tx(raw_full + stage, bytes);
+                        // box {2P x 8-byte elements, RW rows, PL planes, 1 sample}; x is counted in 8-byte units
+                        tma_load_4d(sA + size_t(stage) * p.a_stage, map, 2 * (I.x0 - p.pad), I.y0 - p.pad, g0, I.b, raw_full + stage);
+                    }
                     if (wbytes) bulk_g2s(sW + size_t(stage) * p.w_stage, wsrc, wbytes, raw_full + stage);
                     if (++stage == NS) {
                         stage = 0;
@@ -388,7 +403,7 @@ int tm_nt(int Cout) {
     return 16;
 }
 
-bool tm_configure(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout, int ksize, TmCfg &best) {
+bool tm_configure(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout, int ksize, int stride, TmCfg &best) {
     const int Cin = C0 + C1, Sk = S0 + S1;
     if (Cin <= 0 || (C0 % 16) || (C1 % 16) || (S0 % 16) || (S1 % 16)) return false;
     const int pad = ksize / 2, taps = ksize * ksize;
@@ -402,8 +417,9 @@ bool tm_configure(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout,
     c.n_main = Cin / KC;
     c.n_skip = Sk / KC;
     const int n_chunks = c.n_main + c.n_skip;
+    const bool s2 = stride == 2;  // H, W: OUTPUT size; the stage holds 4 parity sub-images of (R+1) x (Wt+1) positions
     c.Wt = W > 64 ? 64 : W;
-    c.P = c.Wt + 2 * pad;
+    c.P = s2 ? c.Wt + 1 : c.Wt + 2 * pad;
     if (2 * c.P > 256) return false;  // TMA box limit (8-byte elements)
     c.magicP = uint32_t(((1u << 20) + c.P - 1) / c.P);
     c.tiles_x = (W + c.Wt - 1) / c.Wt;
@@ -417,15 +433,16 @@ bool tm_configure(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout,
                          (c.resident ? w_total : 0) + 1024;
     double best_cost = 1e300;
     bool found = false;
-    for (int R = 1; R <= H && R + 2 * pad <= 256; ++R) {
+    for (int R = 1; R <= H && 2 * (R + 2 * pad) <= 256; ++R) {
         const int MB = (R * c.P + 127) / 128;
         if (MB * c.NT > 512) break;
-        const int RW = R + 2 * pad, NQ = RW * c.P;
+        const int RW = s2 ? R + 1 : R + 2 * pad, NQ = RW * c.P;
         bool magic_ok = true;
         for (int q = 0; q < NQ + 256; ++q)
             if (int((uint32_t(q) * c.magicP) >> 20) != q / c.P) magic_ok = false;
         if (!magic_ok) continue;
-        const size_t a_stage = (size_t(c.PL) * NQ * 16 + 127) & ~size_t(127);
+        const size_t blk = (size_t(c.PL) * NQ * 16 + 127) & ~size_t(127);  // one TMA box (128-byte aligned destination)
+        const size_t a_stage = (s2 ? 4 : 1) * blk;
         if (fixed + 2 * (a_stage + c.w_stage) > kTmSmemBudget) break;
         int NS = int((kTmSmemBudget - fixed) / (a_stage + c.w_stage));
         NS = NS > MAX_STAGES ? MAX_STAGES : NS;
@@ -467,7 +484,7 @@ bool tm_configure(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout,
 }
 
 bool tm_configure_op(const ccdm_op &op, TmCfg &c) {
-    return tm_configure(op.B, op.Hout, op.Wout, op.C0, op.C1, op.S0, op.S1, op.Cout, op.ksize, c);
+    return tm_configure(op.B, op.Hout, op.Wout, op.C0, op.C1, op.S0, op.S1, op.Cout, op.ksize, op.stride, c);
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
@@ -501,14 +518,32 @@ int make_map(CUtensorMap *m, const void *base, int B, int C, int H, int W, int P
     return 0;
 }
 
+// Stride-2 variant: rank 5 {8-byte halves of a position, W, H, C/8, B} with element strides {1, 2, 2, 1, 1}: one box
+// gathers every other column of every other row, i.e. one (row, column) parity sub-image of the window.
+int make_map_s2(CUtensorMap *m, const void *base, int B, int C, int H, int W, int P, int RW, int PL) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) CCDM_FAIL(-5, "conv_tma: cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[5] = {2, cuuint64_t(W), cuuint64_t(H), cuuint64_t(C / 8), cuuint64_t(B)};
+    const cuuint64_t strides[4] = {16, cuuint64_t(W) * 16, cuuint64_t(H) * W * 16, cuuint64_t(C / 8) * H * W * 16};
+    const cuuint32_t box[5] = {2u, cuuint32_t(2 * P), cuuint32_t(2 * RW), cuuint32_t(PL), 1u};
+    const cuuint32_t estr[5] = {1u, 2u, 2u, 1u, 1u};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) CCDM_FAIL(-5, "conv_tma: cuTensorMapEncodeTiled (stride 2) failed (%d) for [%d,%d,%d,%d] box %dx%dx%d", int(r), B, C, H, W, P, RW, PL);
+    return 0;
+}
+
 }  // namespace
 
 bool conv_tma_supported(const ccdm_op &op) {
-    if (op.dtype != CCDM_DT_BF16 || op.src_kind != 0 || op.stride != 1 || op.upsample) return false;
+    if (op.dtype != CCDM_DT_BF16 || op.src_kind != 0 || op.upsample) return false;
     if (op.ksize != 1 && op.ksize != 3) return false;
     if ((op.C0 % 16) || (op.C1 % 16) || (op.S0 % 16) || (op.S1 % 16)) return false;
     if (op.out_dtype == CCDM_DT_BF16 && (op.Cout % 16)) return false;
-    if (op.Hin != op.Hout || op.Win != op.Wout) return false;
+    if (op.stride == 2) {  // Downsample (unet.py:136-139): 3x3, no norm, no skip, single source
+        if (op.ksize != 3 || op.gn || op.silu || op.S0 || op.C1) return false;
+        if (op.Hout != (op.Hin + 1) / 2 || op.Wout != (op.Win + 1) / 2) return false;
+    } else if (op.stride != 1 || op.Hin != op.Hout || op.Win != op.Wout) return false;
     TmCfg c;
     return tm_configure_op(op, c);
 }
@@ -552,7 +587,8 @@ int launch_conv_tma(const ccdm_op &op, cudaStream_t s) {
     p.taps = op.ksize * op.ksize; p.pad = op.ksize / 2;
     p.n_main = c.n_main; p.n_skip = c.n_skip; p.NS = c.NS; p.resident = c.resident; p.acc2 = c.acc2;
     p.tmem_cols = c.tmem_cols; p.n_items = c.n_items; p.ips = c.ips; p.slots = c.slots;
-    p.RW = c.RW; p.NQ = c.NQ; p.xf = (op.gn || op.silu) ? 1 : 0;
+    p.RW = c.RW; p.NQ = c.NQ; p.xf = (op.gn || op.silu) ? 1 : 0; p.stride2 = op.stride == 2;
+    p.blk16 = uint32_t(((size_t(c.PL) * c.NQ * 16 + 127) & ~size_t(127)) >> 4);
     p.a_stage = c.a_stage; p.w_stage = c.w_stage; p.w_main_bytes = c.w_main_bytes; p.w_skip_bytes = c.w_skip_bytes;
     p.magicP = c.magicP;
     // cute::UMMA::InstrDescriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major both, N>>3 at 17, M>>4 at 24
@@ -565,7 +601,8 @@ int launch_conv_tma(const ccdm_op &op, cudaStream_t s) {
     if (op.S0 > 0 && (!op.skip0 || !op.skip_w)) CCDM_FAIL(-2, "conv_tma: bad skip configuration");
     if (!op.src0 || (op.C1 && !op.src1) || (op.S1 && !op.skip1)) CCDM_FAIL(-2, "conv_tma: missing source tensor");
 
-    int rc = make_map(&P.map[0], (const void *)op.src0, op.B, op.C0, op.Hout, op.Wout, c.P, c.RW, c.PL);
+    int rc = op.stride == 2 ? make_map_s2(&P.map[0], (const void *)op.src0, op.B, op.C0, op.Hin, op.Win, c.P, c.RW, c.PL)
+                            : make_map(&P.map[0], (const void *)op.src0, op.B, op.C0, op.Hout, op.Wout, c.P, c.RW, c.PL);
     if (rc == 0 && op.C1) rc = make_map(&P.map[1], (const void *)op.src1, op.B, op.C1, op.Hout, op.Wout, c.P, c.RW, c.PL);
     if (rc == 0 && op.S0) rc = make_map(&P.map[2], (const void *)op.skip0, op.B, op.S0, op.Hout, op.Wout, c.P, c.RW, c.PL);
     if (rc == 0 && op.S1) rc = make_map(&P.map[3], (const void *)op.skip1, op.B, op.S1, op.Hout, op.Wout, c.P, c.RW, c.PL);

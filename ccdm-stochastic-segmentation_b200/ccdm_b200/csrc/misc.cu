@@ -132,7 +132,46 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_stats_kernel(const float *__
     }
 }
 
+// one-hot(labels) ++ image -> plane-major bf16 [B][CP/8][HW][8], CP = ceil16(K + C_img), zero padded.
+// One thread per (pixel, plane): consecutive threads write consecutive 16-byte rows.
+__global__ void __launch_bounds__(256) encode_input_kernel(const uint8_t *__restrict__ labels, const float *__restrict__ image, int K,
+                                                           int C_img, int planes, size_t HW, size_t total, __nv_bfloat16 *__restrict__ out) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const size_t pix = i % HW;
+    const size_t bg = i / HW;
+    const int g = int(bg % planes);
+    const size_t b = bg / planes;
+    const int lab = labels[b * HW + pix];
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float v[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int c = g * 8 + 2 * j + e;
+            v[e] = c < K ? (c == lab ? 1.f : 0.f) : (c < K + C_img ? image[(b * C_img + (c - K)) * HW + pix] : 0.f);
+        }
+        __nv_bfloat162 h = __floats2bfloat162_rn(v[0], v[1]);
+        pk[j] = *reinterpret_cast<uint32_t *>(&h);
+    }
+    *reinterpret_cast<uint4 *>(out + i * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+
 }  // namespace
+
+int launch_encode_input(const ccdm_op &op, cudaStream_t s) {
+    const int CP = op.Cout;
+    if (op.dtype != CCDM_DT_BF16 || (CP % 16) || CP < op.K + op.C_img || op.K < 1) CCDM_FAIL(-2, "encode_input: bad channel counts");
+    if (!op.labels_in || !op.image || !op.out) CCDM_FAIL(-2, "encode_input: missing tensors");
+    const size_t HW = size_t(op.Hin) * op.Win, total = size_t(op.B) * (CP / 8) * HW;
+    if (total == 0) return 0;
+    encode_input_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>((const uint8_t *)op.labels_in, (const float *)op.image, op.K, op.C_img,
+                                                                     CP / 8, HW, total, (__nv_bfloat16 *)op.out);
+    CCDM_LAUNCH_CHECK("encode_input_kernel");
+    return 0;
+}
+
 }  // namespace ccdm
 
 using namespace ccdm;

@@ -29,6 +29,7 @@ static int launch_any(const ccdm_op &op, cudaStream_t s) {
         case CCDM_OP_CONV: return launch_conv(op, s);
         case CCDM_OP_ATTENTION: return launch_attention(op, s);
         case CCDM_OP_HEAD: return launch_head(op, s);
+        case CCDM_OP_ENCODE_INPUT: return launch_encode_input(op, s);
         default: CCDM_FAIL(-2, "unknown op kind %d", op.kind);
     }
 }

@@ -167,10 +167,11 @@ class PackedWeights:
             for L in blk.layers:
                 p = L.path
                 if L.kind == "conv_in":
-                    self._reserve(p + ":w", 9 * _ceil(L.cin, 8) * _ceil(L.cout, 32))
+                    # fp32: [tap][ceil8(Cin)][CoutP]; bf16: a tensor-core conv over ceil16(Cin) zero-padded channels
+                    self._reserve(p + ":w", 9 * _ceil(L.cin, 8) * _ceil(L.cout, 32), (9, _ceil(L.cin, 16), L.cout))
                     self._reserve(p + ":b", _ceil(L.cout, 32))
                 elif L.kind in ("down", "up"):
-                    self._reserve(p + ":w", 9 * L.cin * _ceil(L.cout, 32), (9, L.cin, L.cout) if L.kind == "up" else None)
+                    self._reserve(p + ":w", 9 * L.cin * _ceil(L.cout, 32), (9, L.cin, L.cout))
                     self._reserve(p + ":b", _ceil(L.cout, 32))
                 elif L.kind == "res":
                     self._reserve(p + ":g1", L.cin); self._reserve(p + ":be1", L.cin)
@@ -230,7 +231,10 @@ class PackedWeights:
             for L in blk.layers:
                 p = L.path
                 if L.kind == "conv_in":
-                    put(p + ":w", conv_w(sd[p + ".weight"], _ceil(L.cin, 8))); put(p + ":b", padded(sd[p + ".bias"]))
+                    w_in = sd[p + ".weight"]
+                    w_pad = torch.zeros((w_in.shape[0], _ceil(L.cin, 16)) + tuple(w_in.shape[2:]), dtype=w_in.dtype, device=w_in.device)
+                    w_pad[:, :L.cin] = w_in
+                    put(p + ":w", conv_w(w_in, _ceil(L.cin, 8)), w_pad); put(p + ":b", padded(sd[p + ".bias"]))
                 elif L.kind in ("down", "up"):
                     put(p + ":w", conv_w(sd[p + ".weight"]), sd[p + ".weight"]); put(p + ":b", padded(sd[p + ".bias"]))
                 elif L.kind == "res":
@@ -313,7 +317,15 @@ class Program:
                 srcs = [h, hs.pop()]
             for Ly in blk.layers:
                 p = Ly.path
-                if Ly.kind == "conv_in":
+                if Ly.kind == "conv_in" and self.exact == 0:
+                    # bf16: materialise one-hot(x_t) ++ image as a plane-major tensor (16 bytes per pixel and plane),
+                    # then input_blocks[0] is an ordinary tensor-core conv without a norm
+                    cp = _ceil(Ly.cin, 16)
+                    xin = emit(_lib.OP_ENCODE_INPUT, [], new(p + ":x", cp, ch, cw, stat=False), Hin=ch, Win=cw, Hout=ch, Wout=cw,
+                               Cout=cp, K=self.K, C_img=self.C_img, _labels=True)
+                    h = emit(_lib.OP_CONV, [xin], new(p, Ly.cout, ch, cw), ksize=3, stride=1, gn=0, silu=0, Hin=ch, Win=cw,
+                             Hout=ch, Wout=cw, Cout=Ly.cout, _src=[xin], _w=p + ":w", _b=p + ":b")
+                elif Ly.kind == "conv_in":
                     h = emit(_lib.OP_INPUT_CONV, [], new(p, Ly.cout, ch, cw), src_kind=1, ksize=3, stride=1, Hin=ch, Win=cw,
                              Hout=ch, Wout=cw, Cout=Ly.cout, K=self.K, C_img=self.C_img, _w=p + ":w", _b=p + ":b")
                 elif Ly.kind == "res":
@@ -449,7 +461,7 @@ class Program:
             fields.update(f)
             op = Op(**fields)
             src = o.get("_src", [])
-            if o["kind"] == _lib.OP_INPUT_CONV:
+            if o["kind"] in (_lib.OP_INPUT_CONV, _lib.OP_ENCODE_INPUT):
                 op.labels_in = self.addr["labels"]
                 op.image = self.addr["image"]
             if o["kind"] in (_lib.OP_CONV, _lib.OP_ATTENTION):

@@ -70,6 +70,9 @@ typedef struct ccdm_step_entry {
 #define CCDM_OP_CONV 2       /* GN+SiLU+conv3x3/1x1 (+emb +bias +residual/1x1 skip)     */
 #define CCDM_OP_ATTENTION 3  /* QKVAttentionLegacy (:343-360)                           */
 #define CCDM_OP_HEAD 4       /* softmax + theta_post_prob + clamp + draw                */
+#define CCDM_OP_ENCODE_INPUT 5 /* bf16 mode: one-hot(labels) ++ image (unet.py:760) as a plane-major bf16 tensor of
+                                  Cout = ceil16(K + C_img) channels (zero padded), the input of input_blocks[0] run as
+                                  an ordinary tensor-core conv */
 
 typedef struct ccdm_op {
     int32_t kind; /* CCDM_OP_* */

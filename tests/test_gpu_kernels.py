@@ -317,6 +317,42 @@ def test_tc_conv_second_half_with_skip_residual_and_upsample(L):
     _tc_check(out, ref_conv([h1], w, b, upsample=True), ostat)
 
 
+@pytest.mark.parametrize("B,C,H,W", [(2, 32, 128, 128), (3, 64, 32, 32), (2, 96, 16, 16), (1, 128, 8, 16), (1, 32, 21, 37)])
+def test_tc_conv_downsample_stride2(L, B, C, H, W):
+    """Downsample (unet.py:136-139) on the TMA-fed tensor-core kernel: four parity sub-images gathered by
+    TMA boxes with element stride 2; odd sizes exercise the zero fill on the right / bottom."""
+    from gpu_util import nhwc, ref_conv, run_conv
+    from ccdm_b200 import _lib
+    bf = torch.bfloat16
+    x = _bf(_rand(B, C, H, W, seed=41))
+    w, b = _bf(_rand(C, C, 3, 3, seed=42) / math.sqrt(9 * C)), _rand(C, seed=43) * 0.1
+    out, ostat = run_conv([nhwc(x, bf)], w, b, stride=2, dtype=bf, tc=True)
+    assert out.shape == (B, (H + 1) // 2, (W + 1) // 2, C)
+    _tc_check(out, ref_conv([x], w, b, stride=2), ostat)
+
+
+def test_encode_input_planes(L):
+    """bf16 mode: one-hot(labels) ++ image as a zero-padded plane-major tensor (unet.py:760)."""
+    from ccdm_b200 import _lib
+    from ccdm_b200.engine import from_pm
+    for (B, K, C_img, H, W) in [(2, 2, 1, 16, 24), (1, 20, 3, 8, 8)]:
+        CP = (K + C_img + 15) // 16 * 16
+        g = torch.Generator().manual_seed(5)
+        labels = torch.randint(0, K, (B, H, W), generator=g, dtype=torch.uint8).cuda()
+        image = torch.randn((B, C_img, H, W), generator=g).cuda()
+        out = torch.full((B, CP // 8, H, W, 8), float("nan"), dtype=torch.bfloat16, device="cuda")
+        op = _lib.Op(kind=_lib.OP_ENCODE_INPUT, dtype=_lib.DT_BF16, out_dtype=_lib.DT_BF16, B=B, Hin=H, Win=W, Hout=H, Wout=W, Cout=CP,
+                     K=K, C_img=C_img)
+        op.labels_in, op.image, op.out = labels.data_ptr(), image.data_ptr(), out.data_ptr()
+        _lib.check(L.ccdm_launch_op(ctypes.byref(op), _sp()))
+        torch.cuda.synchronize()
+        got = from_pm(out).float()  # [B,H,W,CP]
+        want = torch.zeros((B, H, W, CP), device="cuda")
+        want[..., :K] = F.one_hot(labels.long(), K).float()
+        want[..., K:K + C_img] = image.permute(0, 2, 3, 1).to(torch.bfloat16).float()
+        assert torch.equal(got, want)
+
+
 def test_tc_conv1x1_qkv_proj_and_head(L):
     from gpu_util import nhwc, ref_conv, run_conv
     bf = torch.bfloat16
