@@ -322,6 +322,10 @@ def run_gpu_arm(args, wl):
     if rank == 0:
         peaks = measured_peaks()
         rows, step_ms_eager = per_op_profile(engine, prog, n_iter=0 if args.no_op_profile else 5)
+        if args.dump_ops:
+            with open(args.dump_ops, "w") as fh:
+                json.dump([dict(index=i, op_class=op_class(prog._op_array[i]), bytes=op_bytes(prog._op_array[i], prog.esize),
+                                flops=op_flops(prog._op_array[i])) for i in range(prog.n_ops)], fh, indent=0)
         if args.op_table:
             os.makedirs(os.path.dirname(os.path.abspath(args.op_table)), exist_ok=True)
             with open(args.op_table, "w") as fh:
@@ -333,6 +337,10 @@ def run_gpu_arm(args, wl):
                              f"{v['flops'] / v['launches'] / us / 1e6:.1f} | {v['ms'] / step_ms_eager:.3f}\n")
                 fh.write(f"sum of per-op times {step_ms_eager:.3f} ms; graph step {ms_step / T:.3f} ms; ops {prog.n_ops}\n")
         top = max(rows.items(), key=lambda kv: kv[1]["ms"])
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch per op class, from the committed ncu capture
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(args.workload, {}).get(top[0])
         per_launch_ms = top[1]["ms"] / top[1]["launches"]
         per_launch_bytes = top[1]["bytes"] / top[1]["launches"]
         achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
@@ -340,6 +348,17 @@ def run_gpu_arm(args, wl):
         chain_bytes = (wl["elements"] * esize + 3 * K * H * W * 4) * B * T
         roof_chain = chain_bytes / (ms_step * 1e-3) / 1e9
         cpu = cpu_chain_rate(wl, budget_s=args.cpu_budget) if not args.no_cpu_baseline else None
+        is_attn = top[0].startswith("attention")
+        if is_attn:  # the attention kernel is bound by the tensor / MUFU pipes, not by HBM
+            tf = top[1]["flops"] / top[1]["launches"] / (per_launch_ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": top[0], "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": tf / peaks["bf16_tflops"], "traffic": traffic}
+        else:
+            roof = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
+                    "tflops": top[1]["flops"] / top[1]["launches"] / (per_launch_ms * 1e-3) / 1e12}
+        roof.update(peak_source=peaks["source"], launches_per_step=top[1]["launches"], avg_launch_ms=per_launch_ms,
+                    share_of_step=top[1]["ms"] / step_ms_eager, algorithmic_bytes_per_launch=per_launch_bytes)
         line = {
             "metric": "seg samples/sec (full T-step chain)", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -352,11 +371,7 @@ def run_gpu_arm(args, wl):
                     "ms_per_step": ms_e2e},
             "gpu_launches": prog.n_ops * T * args.steps,
             "clocks": clk,
-            "roofline": {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
-                         "launches_per_step": top[1]["launches"], "avg_launch_ms": per_launch_ms,
-                         "share_of_step": top[1]["ms"] / step_ms_eager,
-                         "tflops": top[1]["flops"] / top[1]["launches"] / (per_launch_ms * 1e-3) / 1e12},
+            "roofline": roof,
             "roofline_chain": {"bound": "hbm", "achieved": roof_chain, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                "frac": roof_chain / peaks["hbm_gbs"],
                                "bytes_per_sample_step": chain_bytes / (B * T), "tflops": wl["flops"] * B * T / (ms_step * 1e-3) / 1e12},
@@ -382,6 +397,7 @@ def main():
     ap.add_argument("--T", type=int, default=0, help="override the chain length (debug runs; invalid as a bench number)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-ops", default="", help="write the op list of one reverse step (launch order, op class, algorithmic bytes) as JSON")
     ap.add_argument("--op-table", default="", help="write the per-op-class CUDA-event table to this file")
     ap.add_argument("--no-op-profile", action="store_true", help="skip the per-op CUDA-event pass (ncu runs)")
     args = ap.parse_args()
