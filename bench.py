@@ -143,6 +143,8 @@ def run_reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core it can
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
     steps = max(1, args.steps)
     rates = []
     for i in range(args.warmup + steps):
@@ -347,7 +349,10 @@ def run_gpu_arm(args, wl):
         esize = prog.esize
         chain_bytes = (wl["elements"] * esize + 3 * K * H * W * 4) * B * T
         roof_chain = chain_bytes / (ms_step * 1e-3) / 1e9
-        cpu = cpu_chain_rate(wl, budget_s=args.cpu_budget) if not args.no_cpu_baseline else None
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:  # reported at N = 1 only (the reference arm covers N > 1)
+            torch.set_num_threads(max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
+            cpu = cpu_chain_rate(wl, budget_s=args.cpu_budget)
         is_attn = top[0].startswith("attention")
         if is_attn:  # the attention kernel is bound by the tensor / MUFU pipes, not by HBM
             tf = top[1]["flops"] / top[1]["launches"] / (per_launch_ms * 1e-3) / 1e12

@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q > gpurun_out/s3k_pytest.log 2>&1; tail -5 gpurun_out/s3k_pytest.log | cut -c1-250
-timeout 300 python bench.py --steps 1 --warmup 1 --T 10 --no-cpu-baseline --op-table gpurun_out/s3k_ops_lidc.txt > gpurun_out/s3k_lidc.json 2>&1
-head -40 gpurun_out/s3k_ops_lidc.txt; tail -1 gpurun_out/s3k_ops_lidc.txt; tail -3 gpurun_out/s3k_lidc.json | cut -c1-300
+nvidia-smi -L
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 2 --warmup 3 --cpu-budget 5 > gpurun_out/s4a_bench2.json 2> gpurun_out/s4a_bench2.err; tail -c 1500 gpurun_out/s4a_bench2.json; tail -5 gpurun_out/s4a_bench2.err
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 > gpurun_out/s4a_ref2.json 2>&1; tail -c 400 gpurun_out/s4a_ref2.json
