@@ -69,6 +69,7 @@ def lib():
     L.ccdm_plan_step.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
     L.ccdm_plan_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     L.ccdm_plan_profile.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.c_void_p]
+    L.ccdm_debug_conv_trace.argtypes = [ctypes.POINTER(ctypes.c_uint64), ctypes.c_int]
     L.ccdm_launch_op.argtypes = [ctypes.POINTER(Op), ctypes.c_void_p]
     L.ccdm_sizeof_op.restype = ctypes.c_size_t
     L.ccdm_sizeof_step_entry.restype = ctypes.c_size_t

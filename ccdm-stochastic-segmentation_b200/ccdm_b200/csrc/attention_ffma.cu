@@ -21,6 +21,8 @@ __global__ void __launch_bounds__(QT) attention_ffma_kernel(const T *__restrict_
                                                             int heads, float scale) {
     __shared__ float sK[KT][D];
     __shared__ float sV[KT][D];
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.z, h = blockIdx.y;
     const int qi = blockIdx.x * QT + threadIdx.x;
     const int C3 = heads * 3 * D;
@@ -97,7 +99,7 @@ int launch_t(const ccdm_op &op, cudaStream_t s) {
     dim3 grid((Ttok + QT - 1) / QT, op.heads, op.B);
     // unet.py:354  scale = 1 / sqrt(sqrt(ch)), applied to q and to k
     const float scale = float(1.0 / sqrt(sqrt(double(D))));
-    attention_ffma_kernel<T, D><<<grid, QT, 0, s>>>((const T *)op.src0, (T *)op.out, Ttok, op.heads, scale);
+    CCDM_CUDA(launch_pdl(attention_ffma_kernel<T, D>, grid, dim3(QT), 0, s, (const T *)op.src0, (T *)op.out, Ttok, op.heads, scale));
     CCDM_LAUNCH_CHECK("attention_ffma_kernel");
     return 0;
 }

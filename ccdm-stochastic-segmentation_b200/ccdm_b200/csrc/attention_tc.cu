@@ -16,6 +16,8 @@
 // SM (TMEM: 256 of 512 columns each at NK = 128), so one CTA's softmax overlaps another's MMAs and loads.
 //
 // Output: [B][C/8][T][8] bf16, channel(h, d) = h*32 + d (unet.py:360).
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace ccdm {
@@ -93,6 +95,8 @@ __global__ void __launch_bounds__(AT_QT) attention_tc_kernel(const AtP p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_s = *s_tmem, tmem_o = tmem_s + NK;
+    pdl_launch_dependents();
+    pdl_wait();  // qkv is written by the previous kernel of the step
     const uint32_t trow = uint32_t(warp * 32) << 16;  // this warp's TMEM lane quarter
 
     auto load_kv = [&](int t, int buf, uint32_t extra_bytes) {  // thread 0
@@ -232,7 +236,7 @@ int launch_nk(const AtP &p, int grid, cudaStream_t s) {
         CCDM_CUDA(cudaFuncSetAttribute(attention_tc_kernel<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         attr_done = true;
     }
-    attention_tc_kernel<NK><<<grid, AT_QT, smem, s>>>(p);
+    CCDM_CUDA(launch_pdl(attention_tc_kernel<NK>, dim3(grid), dim3(AT_QT), smem, s, p));
     CCDM_LAUNCH_CHECK("attention_tc_kernel");
     return 0;
 }
@@ -251,7 +255,8 @@ int launch_attention_tc(const ccdm_op &op, cudaStream_t s) {
     p.heads = op.heads;
     p.q_tiles = (T + AT_QT - 1) / AT_QT;
     p.scale_log2 = float(1.4426950408889634 / sqrt(double(AT_D)));  // unet.py:354: q and k are each scaled by 32^-1/4
-    const int NK = T <= 64 ? 64 : 128;
+    static const int env_nk = getenv("CCDM_ATT_NK") ? atoi(getenv("CCDM_ATT_NK")) : 0;  // tuning override
+    const int NK = env_nk == 64 || env_nk == 128 ? env_nk : (T <= 64 ? 64 : 128);
     // cute::UMMA::InstrDescriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), b_major = MN (bit 16), N>>3 at 17, M>>4 at 24
     const uint32_t base = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(128 >> 4) << 24);
     p.idesc_s = base | (uint32_t(NK >> 3) << 17);

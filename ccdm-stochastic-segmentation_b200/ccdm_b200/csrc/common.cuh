@@ -34,6 +34,30 @@ int launch_attention(const ccdm_op &op, cudaStream_t s);
 int launch_head(const ccdm_op &op, cudaStream_t s);
 int launch_encode_input(const ccdm_op &op, cudaStream_t s);
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------
+// Every kernel of the reverse step is launched with programmatic stream serialization: the next kernel's
+// CTAs may be scheduled (and run their prologue: barrier init, TMEM allocation, weight loads) while the
+// previous kernel drains, and block in pdl_wait() until it has COMPLETED and its writes are visible.  A
+// kernel must call pdl_wait() before its first access to anything another kernel of the step writes or
+// reads.  Captured into the step's CUDA graph as programmatic edges.  Opt-in with CCDM_PDL=1.
+bool pdl_enabled();
+template <typename Kern, typename... Args>
+cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 constexpr float kGnEps = 1e-5f;  // nn.GroupNorm default (nn.py:93-100 -> GroupNorm32(32, C))
 constexpr int kGnGroups = 32;
 

@@ -121,6 +121,8 @@ __global__ void __launch_bounds__(NTHREADS) conv_ffma_kernel(const ConvP p) {
     const int b = blockIdx.z;
     constexpr int PAD = KS / 2;
 
+    pdl_launch_dependents();
+    pdl_wait();
     if (p.gn) build_gn_affine(p, b, sA, sB);
     __syncthreads();
 
@@ -359,7 +361,7 @@ int launch_t(const ConvP &p, cudaStream_t s) {
         attr_done = true;
     }
     dim3 grid(p.tiles_x * p.tiles_y, p.CoutP / COT, p.B);
-    kern<<<grid, NTHREADS, smem, s>>>(p);
+    CCDM_CUDA(launch_pdl(kern, grid, dim3(NTHREADS), smem, s, p));
     CCDM_LAUNCH_CHECK("conv_ffma_kernel");
     return 0;
 }

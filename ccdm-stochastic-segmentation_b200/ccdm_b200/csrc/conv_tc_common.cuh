@@ -62,6 +62,11 @@ __device__ __forceinline__ Item decode_item(const WsP &p, int it) {
 // 32*(w%4)..+31 (= accumulator rows 32*(w%4)+lane of every M block); with 8 warps the two warps of a lane
 // quarter split the 16-column groups of the accumulator between them.  Named barrier 2 is private to
 // these NEW*32 threads.
+// optional milestone hook (conv_tma.cu defines CCDM_EPI_TRACE before including this header)
+#ifndef CCDM_EPI_TRACE
+#define CCDM_EPI_TRACE(slot)
+#endif
+
 template <int NEW>
 __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, float *sRed, int *s_last, uint64_t *acc_full,
                                                    uint64_t *acc_empty, uint32_t tmem_base, int it_begin, int it_end) {
@@ -261,9 +266,11 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty + buf);
+        if (tid == 0 && it == it_begin) CCDM_EPI_TRACE(6);
         ++n_pending;
     }
     if (p.ostat != nullptr && n_pending > 0) flush_stats(cur_b, n_pending);
+    if (tid == 0) CCDM_EPI_TRACE(7);
 }
 
 }  // namespace

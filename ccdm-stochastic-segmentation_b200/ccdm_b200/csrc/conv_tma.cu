@@ -23,7 +23,14 @@
 //   warps 0-7   epilogue | warps 8-15 in-place transform | warps 16-17 MMA issue | warp 18 TMA.
 // All hand-offs are mbarriers; nothing in the main loop is a CTA-wide barrier.
 #include <cuda.h>
+#include <stdlib.h>
 
+namespace ccdm {
+namespace {
+__device__ void conv_tma_trace_hook(int slot);
+}
+}  // namespace ccdm
+#define CCDM_EPI_TRACE(slot) conv_tma_trace_hook(slot)
 #include "conv_tc_common.cuh"
 
 namespace ccdm {
@@ -103,6 +110,23 @@ __device__ __forceinline__ void xf_pass(uint32_t addr, int q, int NQ, int r, int
     }
 }
 
+// Milestone time stamps of CTA 0 (debug aid, read back with ccdm_debug_conv_trace): one store per milestone.
+__device__ unsigned long long g_trace[16];
+enum { kTraceStart = 0, kTraceSetup, kTraceAffine, kTraceRaw0, kTraceXf0, kTraceMma0, kTraceEpi0, kTraceFlush, kTraceEnd };
+__device__ __forceinline__ void trace(int slot) {
+#ifdef CCDM_TRACE
+    if (blockIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_trace[slot] = t;
+    }
+#else
+    (void)slot;
+#endif
+}
+
+__device__ void conv_tma_trace_hook(int slot) { trace(slot); }
+
 // PL = planes (8-channel groups) per K chunk: KC = 8*PL channels per pipeline stage.
 template <int PL>
 __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_constant__ TmP P_) {
@@ -111,6 +135,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
     constexpr int KC = 8 * PL;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NT = p.NT, P = p.P, NS = p.NS, NQ = p.NQ;
+    if (tid == 0) trace(kTraceStart);
 
     // smem carve-up: [NS] activation stages (+ over-read slack) | weights | GN affine | bias | stats | barriers
     uint8_t *sA = smem_raw;
@@ -156,6 +181,17 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
     const int it_begin = int((long long)blockIdx.x * p.n_items / gridDim.x);
     const int it_end = int((long long)(blockIdx.x + 1) * p.n_items / gridDim.x);
     const int n_chunks = p.n_main + p.n_skip;
+
+    // Programmatic dependent launch: the prologue above overlapped the previous kernel's tail; the weights are
+    // constants of the chain and may be fetched before it completes, everything else waits for it.
+    pdl_launch_dependents();
+    if (warp == WARP_TMA && lane == 0 && it_begin < it_end && p.resident) {
+        mbar_expect_tx(w_res, p.w_main_bytes + p.w_skip_bytes);
+        bulk_g2s(sW, p.weight, p.w_main_bytes, w_res);
+        if (p.w_skip_bytes) bulk_g2s(sW + p.w_main_bytes, p.skip_w, p.w_skip_bytes, w_res);
+    }
+    pdl_wait();
+    if (tid == 0) trace(kTraceSetup);
 
     // Register budget per role (setmaxnreg works on whole warpgroups of 4 warps): the kernel launches with
     // 96 registers per thread; the epilogue warpgroups grow to 128, the others shrink and donate theirs.
@@ -203,6 +239,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
                         sAff[p.Cin + c] = half * (p.beta[c] - float(mean) * a);
                     }
                     named_bar_sync(1, XF_THREADS);
+                    if (pt == 0 && it == it_begin) trace(kTraceAffine);
                     cur_b = I.b;
                 }
                 // halo positions outside the image were zero-filled by TMA and must stay zero (the
@@ -232,6 +269,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
                             for (int i = 0; i < 8; ++i) fa[i] = p.silu ? 0.5f : 1.0f, fb[i] = 0.f;
                         }
                         mbar_wait(raw_full + stage, phase);
+                        if (pt == 0 && it == it_begin && kc == 0) trace(kTraceRaw0);
                         const uint32_t addr = sA32 + uint32_t(stage) * p.a_stage + (uint32_t(plane) * uint32_t(NQ) + uint32_t(q0)) * 16u;
                         if (need_mask) {
                             if (p.silu) xf_pass<STEP, true, true>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
@@ -243,6 +281,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
                         fence_proxy_async();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(xf_full + stage);
+                        if (pt == 0 && it == it_begin && kc == 0) trace(kTraceXf0);
                     }
                     if (++stage == NS) {
                         stage = 0;
@@ -321,16 +360,12 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
                 }
             }
             umma_commit_elect(acc_full + buf);
+            if (mw == 0 && lane == 0 && it == it_begin) trace(kTraceMma0);
         }
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         // =========================== TMA: activation windows + weights ============================
         if (warp == WARP_TMA && lane == 0 && it_begin < it_end) {
-            if (p.resident) {
-                mbar_expect_tx(w_res, p.w_main_bytes + p.w_skip_bytes);
-                bulk_g2s(sW, p.weight, p.w_main_bytes, w_res);
-                if (p.w_skip_bytes) bulk_g2s(sW + p.w_main_bytes, p.skip_w, p.w_skip_bytes, w_res);
-            }
             int stage = 0;
             uint32_t phase = 0;
             const int planes_main = p.Cin / 8, planes_skip = (p.S0 + p.S1) / 8;
@@ -383,6 +418,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
         tc_fence_after();
         tmem_dealloc(tmem_base, uint32_t(p.tmem_cols));
     }
+    if (tid == 0) trace(kTraceEnd);
 }
 
 // ---- host-side configuration --------------------------------------------------------------------
@@ -413,6 +449,13 @@ bool tm_configure(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout,
     c.n_cc = CoutP / c.NT;
     const bool all32 = !(C0 % 32) && !(C1 % 32) && !(S0 % 32) && !(S1 % 32);
     c.PL = all32 ? 4 : 2;
+    // tuning overrides (A/B runs): CCDM_TMA_PL = 2|4 planes per K chunk, CCDM_TMA_R = rows per tile (large images only)
+    static const int env_pl = getenv("CCDM_TMA_PL") ? atoi(getenv("CCDM_TMA_PL")) : 0;
+    static const int env_r = getenv("CCDM_TMA_R") ? atoi(getenv("CCDM_TMA_R")) : 0;
+    if (env_pl == 2 && W >= 64) c.PL = 2;
+    // a 32-channel input would be ONE K chunk per item at PL = 4: two chunks of 16 let the TMA, the transform and
+    // the MMAs of one item overlap (measured 73.7 -> 63.5 us on 32->32 @128x128, B = 64)
+    if (env_pl == 0 && Cin == 32 && W >= 64) c.PL = 2;
     const int KC = 8 * c.PL;
     c.n_main = Cin / KC;
     c.n_skip = Sk / KC;
@@ -457,6 +500,7 @@ bool tm_configure(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout,
         if (NS < 3) cost *= 1.5;
         else if (NS < 4) cost *= 1.1;
         if (2 * MB * c.NT > 512) cost *= 1.15;  // single accumulator buffer: epilogue not overlapped
+        if (env_r > 0 && W >= 64 && H >= 64) cost = (R == env_r) ? 0.0 : 1e290;
         if (cost < best_cost) {
             best_cost = cost;
             best = c;
@@ -534,6 +578,14 @@ int make_map_s2(CUtensorMap *m, const void *base, int B, int C, int H, int W, in
 }
 
 }  // namespace
+
+int conv_tma_read_trace(unsigned long long *out, int n) {
+    unsigned long long tmp[16];
+    if (cudaMemcpyFromSymbol(tmp, g_trace, sizeof(tmp)) != cudaSuccess) return 0;
+    const int m = n < 16 ? n : 16;
+    for (int i = 0; i < m; ++i) out[i] = tmp[i];
+    return m;
+}
 
 bool conv_tma_supported(const ccdm_op &op) {
     if (op.dtype != CCDM_DT_BF16 || op.src_kind != 0 || op.upsample) return false;
@@ -615,9 +667,9 @@ int launch_conv_tma(const ccdm_op &op, cudaStream_t s) {
         attr_done = true;
     }
     if (c.PL == 4)
-        conv_tma_kernel<4><<<c.grid, TM_THREADS, c.smem, s>>>(P);
+        CCDM_CUDA(launch_pdl(conv_tma_kernel<4>, dim3(c.grid), dim3(TM_THREADS), c.smem, s, P));
     else
-        conv_tma_kernel<2><<<c.grid, TM_THREADS, c.smem, s>>>(P);
+        CCDM_CUDA(launch_pdl(conv_tma_kernel<2>, dim3(c.grid), dim3(TM_THREADS), c.smem, s, P));
     CCDM_LAUNCH_CHECK("conv_tma_kernel");
     return 0;
 }

@@ -80,6 +80,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
+    pdl_launch_dependents();
+    pdl_wait();  // everything below reads or writes tensors of the step
 
     // contiguous item range of this CTA (vertically adjacent tiles stay on one SM: halo rows hit L2)
     const int it_begin = int((long long)blockIdx.x * p.n_items / gridDim.x);
@@ -514,7 +516,7 @@ int launch_conv_tc(const ccdm_op &op, cudaStream_t s) {
         CCDM_CUDA(cudaFuncSetAttribute(conv_ws_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBudget)));
         attr_done = true;
     }
-    kern<<<c.grid, WS_THREADS, c.smem, s>>>(p);
+    CCDM_CUDA(launch_pdl(kern, dim3(c.grid), dim3(WS_THREADS), c.smem, s, p));
     CCDM_LAUNCH_CHECK("conv_ws_kernel");
     return 0;
 }

@@ -47,6 +47,8 @@ struct HeadP {
 template <int KMAX>
 __global__ void __launch_bounds__(128) head_kernel(const HeadP p) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     float alpha = p.alpha_t, cum = p.cumalpha_tm1;
     int mode = p.mode;
     uint32_t draw = p.draw;
@@ -209,7 +211,7 @@ template <int KMAX>
 int launch_k(const HeadP &p, cudaStream_t s) {
     const int threads = 128;
     const unsigned blocks = (p.n_total + threads - 1) / threads;
-    head_kernel<KMAX><<<blocks, threads, 0, s>>>(p);
+    CCDM_CUDA(launch_pdl(head_kernel<KMAX>, dim3(blocks), dim3(threads), 0, s, p));
     CCDM_LAUNCH_CHECK("head_kernel");
     return 0;
 }

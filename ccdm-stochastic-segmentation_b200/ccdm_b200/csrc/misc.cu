@@ -137,6 +137,8 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_stats_kernel(const float *__
 __global__ void __launch_bounds__(256) encode_input_kernel(const uint8_t *__restrict__ labels, const float *__restrict__ image, int K,
                                                            int C_img, int planes, size_t HW, size_t total, __nv_bfloat16 *__restrict__ out) {
     const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     if (i >= total) return;
     const size_t pix = i % HW;
     const size_t bg = i / HW;
@@ -166,8 +168,8 @@ int launch_encode_input(const ccdm_op &op, cudaStream_t s) {
     if (!op.labels_in || !op.image || !op.out) CCDM_FAIL(-2, "encode_input: missing tensors");
     const size_t HW = size_t(op.Hin) * op.Win, total = size_t(op.B) * (CP / 8) * HW;
     if (total == 0) return 0;
-    encode_input_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>((const uint8_t *)op.labels_in, (const float *)op.image, op.K, op.C_img,
-                                                                     CP / 8, HW, total, (__nv_bfloat16 *)op.out);
+    CCDM_CUDA(launch_pdl(encode_input_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), 0, s, (const uint8_t *)op.labels_in,
+                         (const float *)op.image, op.K, op.C_img, CP / 8, HW, total, (__nv_bfloat16 *)op.out));
     CCDM_LAUNCH_CHECK("encode_input_kernel");
     return 0;
 }

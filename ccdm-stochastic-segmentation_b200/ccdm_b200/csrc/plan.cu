@@ -6,6 +6,7 @@
 // device-side counter that the head kernel advances, so the graph never needs to
 // be re-captured or patched between steps.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -21,6 +22,15 @@ void set_error(const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("CCDM_PDL");
+        v = (e && e[0] == '1') ? 1 : 0;  // opt-in: measured +2.4 % on LIDC B=64 but -10 % on Cityscapes B=8 (profiles/README.md)
+    }
+    return v == 1;
 }
 
 static int launch_any(const ccdm_op &op, cudaStream_t s) {
@@ -225,3 +235,8 @@ extern "C" int ccdm_plan_profile(ccdm_plan *plan, int iters, float *ms_per_op, v
     cudaEventDestroy(e1);
     return rc;
 }
+
+// Debug aid: nanosecond time stamps (%globaltimer) that CTA 0 of the most recent conv_tma launch took at
+// its role milestones (conv_tma.cu, kTrace*).  Returns the number of slots copied.
+namespace ccdm { int conv_tma_read_trace(unsigned long long *out, int n); }
+extern "C" int ccdm_debug_conv_trace(unsigned long long *out, int n) { return ccdm::conv_tma_read_trace(out, n); }

@@ -184,6 +184,10 @@ class PackedWeights:
                     self._reserve(p + ":g", L.cin); self._reserve(p + ":be", L.cin)
                     self._reserve(p + ":wqkv", L.cin * 3 * L.cin, (1, L.cin, 3 * L.cin)); self._reserve(p + ":bqkv", 3 * L.cin)
                     self._reserve(p + ":wproj", L.cin * L.cin, (1, L.cin, L.cin)); self._reserve(p + ":bproj", L.cin)
+        # bf16 mode folds identity residuals (ResBlock skip = Identity, attention x + proj) into the MMA as a 1x1
+        # "skip conv" with identity weights: x * I accumulates exactly in fp32 and the epilogue loses a load
+        for c in sorted({L.cout for blk in arch.blocks for L in blk.layers if L.kind in ("res", "attn")}):
+            self._reserve("ident:%d" % c, 1, (1, c, c))
         K = self.unet.out_channels
         c_head = int(self.unet.channel_mult[0] * mc)
         self._reserve("out:g", c_head); self._reserve("out:be", c_head)
@@ -254,6 +258,10 @@ class PackedWeights:
                     put(p + ":wqkv", sd[p + ".qkv.weight"][:, :, 0].t().contiguous(), sd[p + ".qkv.weight"]); put(p + ":bqkv", sd[p + ".qkv.bias"])
                     put(p + ":wproj", sd[p + ".proj_out.weight"][:, :, 0].t().contiguous(), sd[p + ".proj_out.weight"]); put(p + ":bproj", sd[p + ".proj_out.bias"])
         put("emb_w", torch.cat(emb_w, 0)); put("emb_b", torch.cat(emb_b, 0))
+        for name in self.slots16:
+            if name.startswith("ident:"):
+                c = int(name[6:])
+                put(name, torch.zeros(1, device=self.device), torch.eye(c, device=self.device).reshape(c, c, 1, 1))
         put("out:g", sd["out.0.weight"]); put("out:be", sd["out.0.bias"])
         put("out:w", conv_w(sd["out.2.weight"]), sd["out.2.weight"]); put("out:b", padded(sd["out.2.bias"]))
         self._stamp = stamp
@@ -340,6 +348,8 @@ class Program:
                              _g=p + ":g2", _be=p + ":be2", _w=p + ":w2", _b=p + ":b2")
                     if Ly.skip_conv:
                         f.update(_skip=srcs, _ws=p + ":ws")
+                    elif self.exact == 0:
+                        f.update(_skip=[srcs[0]], _ws="ident:%d" % Ly.cout)
                     else:
                         f.update(_res=srcs[0])
                     h = emit(_lib.OP_CONV, [h1] + srcs, new(p, Ly.cout, ch, cw), **f)
@@ -352,8 +362,9 @@ class Program:
                                _w=p + ":wqkv", _b=p + ":bqkv")
                     a = emit(_lib.OP_ATTENTION, [qkv], new(p + ":a", C, ch, cw, stat=False), Hin=ch, Win=cw, Hout=ch, Wout=cw,
                              Cout=C, heads=Ly.heads, head_dim=C // Ly.heads, _src=[qkv])
+                    fr = dict(_skip=[x], _ws="ident:%d" % C) if self.exact == 0 else dict(_res=x)
                     h = emit(_lib.OP_CONV, [a, x], new(p, C, ch, cw), ksize=1, stride=1, gn=0, silu=0, Hin=ch, Win=cw, Hout=ch,
-                             Wout=cw, Cout=C, _src=[a], _w=p + ":wproj", _b=p + ":bproj", _res=x)
+                             Wout=cw, Cout=C, _src=[a], _w=p + ":wproj", _b=p + ":bproj", **fr)
                     srcs = [h]
                 elif Ly.kind == "down":
                     nh, nw = (ch + 1) // 2, (cw + 1) // 2

@@ -218,6 +218,11 @@ int ccdm_plan_run(ccdm_plan *plan, int n_steps, int use_graph, void *stream);
  * one-node CUDA graph between two events; ms_per_op has ccdm_plan_num_launches() entries (host memory). */
 int ccdm_plan_profile(ccdm_plan *plan, int iters, float *ms_per_op, void *stream);
 
+/* Debug aid: %globaltimer stamps (ns) CTA 0 of the most recent conv_tma launch took at its milestones
+ * {start, setup done, GN affine ready, first TMA landed, first stage transformed, first item's MMAs committed,
+ * first item's epilogue done, statistics flushed, end}; returns the number of slots written. */
+int ccdm_debug_conv_trace(unsigned long long *out, int n);
+
 #ifdef __cplusplus
 }
 #endif

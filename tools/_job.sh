@@ -1,4 +1,9 @@
 mkdir -p gpurun_out
-nvidia-smi -L
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 2 --warmup 3 --cpu-budget 5 > gpurun_out/s4a_bench2.json 2> gpurun_out/s4a_bench2.err; tail -c 1500 gpurun_out/s4a_bench2.json; tail -5 gpurun_out/s4a_bench2.err
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 > gpurun_out/s4a_ref2.json 2>&1; tail -c 400 gpurun_out/s4a_ref2.json
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/s4e_pytest.log 2>&1; tail -5 gpurun_out/s4e_pytest.log | cut -c1-250
+timeout 300 python bench.py --steps 1 --warmup 1 --T 10 --no-cpu-baseline --op-table gpurun_out/s4e_ops_lidc.txt > gpurun_out/s4e_lidc.json 2>&1
+head -14 gpurun_out/s4e_ops_lidc.txt; tail -1 gpurun_out/s4e_ops_lidc.txt
+for NK in 128 64; do
+CCDM_ATT_NK=$NK timeout 300 python bench.py --workload cityscapes --steps 1 --warmup 1 --T 6 --no-cpu-baseline --op-table gpurun_out/s4e_ops_cs_$NK.txt > gpurun_out/s4e_cs_$NK.json 2>&1
+echo "NK=$NK"; grep attention gpurun_out/s4e_ops_cs_$NK.txt; tail -1 gpurun_out/s4e_ops_cs_$NK.txt
+done
+CCDM_ATT_NK=64 timeout 300 python bench.py --steps 1 --warmup 1 --T 10 --no-cpu-baseline --op-table gpurun_out/s4e_ops_lidc_nk64.txt > /dev/null 2>&1; grep attention gpurun_out/s4e_ops_lidc_nk64.txt
