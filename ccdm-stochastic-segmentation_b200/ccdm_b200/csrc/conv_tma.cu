@@ -195,6 +195,10 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
 
     // Register budget per role (setmaxnreg works on whole warpgroups of 4 warps): the kernel launches with
     // 96 registers per thread; the epilogue warpgroups grow to 128, the others shrink and donate theirs.
+    // The pool is the CTA's own launch allocation (640 x 96): increases must be covered by the decreases of
+    // this CTA -- (8 x 16 + 4 x 40) x 32 freed >= 8 x 32 x 32 needed -- or setmaxnreg.inc waits forever.
+    // (Measured: 12 transform warps (768 threads, 80/120/64/40 registers) are not faster than 8: 2.65 vs 2.62 ms
+    // per LIDC step -- the roles are limited by shared-memory bandwidth and issue slots, not by warp count.)
     if (warp < TM_EPI_WARPS) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
         conv_epilogue_role<TM_EPI_WARPS>(p, sAdd, sRed, s_last, acc_full, acc_empty, tmem_base, it_begin, it_end);
