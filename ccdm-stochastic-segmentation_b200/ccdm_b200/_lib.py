@@ -14,7 +14,7 @@ DT_F32, DT_BF16 = 0, 1
 DRAW_SAMPLE, DRAW_MAJORITY, DRAW_CONFIDENCE, DRAW_X0, DRAW_POSTERIOR = 0, 1, 2, 3, 4
 NOISE_TENSOR, NOISE_PHILOX = 0, 1
 OP_INPUT_CONV, OP_CONV, OP_ATTENTION, OP_HEAD, OP_ENCODE_INPUT = 1, 2, 3, 4, 5
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class StepEntry(ctypes.Structure):
@@ -25,7 +25,8 @@ class StepEntry(ctypes.Structure):
 
 _I32 = ["kind", "dtype", "B", "Hin", "Win", "Hout", "Wout", "C0", "C1", "Cout", "ksize", "stride", "upsample", "gn", "silu",
         "S0", "S1", "heads", "head_dim", "K", "C_img", "emb_off", "emb_cols", "emb_bstride", "noise_mode", "sample0",
-        "out_dtype", "src_kind", "exact", "reserved0", "reserved1"]
+        "out_dtype", "src_kind", "exact", "reserved0", "reserved1", "st_slots0", "st_slots1", "st_ips0", "st_ips1", "st_items0", "st_items1",
+        "st_grid0", "st_grid1", "st_rows0", "st_rows1", "pad_align"]
 _U64 = ["seed", "src0", "src1", "stat0", "stat1", "gamma", "beta", "weight", "bias", "emb", "skip0", "skip1", "skip_w", "res",
         "out", "ostat", "part", "ticket", "labels_in", "labels_out", "image", "noise", "probs_out", "noise_out", "steps",
         "step_ptr"]
@@ -88,6 +89,7 @@ def lib():
     L.ccdm_op_part_floats.argtypes = [ctypes.POINTER(Op)]
     L.ccdm_conv_uses_tc.argtypes = [ctypes.POINTER(Op)]
     L.ccdm_conv_uses_tma.argtypes = [ctypes.POINTER(Op)]
+    L.ccdm_conv_stat_layout.argtypes = [ctypes.POINTER(Op), ctypes.POINTER(ctypes.c_int32)]
     L.ccdm_conv_tc_nt.argtypes = [ctypes.c_int]
     L.ccdm_conv_tc_config.argtypes = [ctypes.POINTER(Op), ctypes.POINTER(ctypes.c_int32)]
     L.ccdm_conv_part_floats.restype = ctypes.c_size_t

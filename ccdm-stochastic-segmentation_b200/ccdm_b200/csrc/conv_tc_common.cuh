@@ -34,6 +34,7 @@ struct WsP {
     int R, Wt, P, MB, WN, tiles_x, tiles, taps, pad;
     int n_main, n_skip, NS, resident, acc2, tmem_cols, n_items;
     int ips, slots;  // items per sample; statistics slots per sample (CTAs whose item range can touch one sample)
+    int st_slots[2], st_ips[2], st_items[2], st_grid[2], st_rows[2];  // layout of stat0 / stat1 (ccdm_op::st_*)
     int stride2;     // conv_tma: 3x3 stride-2 conv (Downsample): the stage holds the 4 (row, column) parity sub-images
     uint32_t blk16;  // conv_tma, stride 2: size of one parity sub-image block in 16-byte rows (128-byte aligned for TMA)
     int RW, NQ, xf;  // conv_tma: window rows, window positions (= plane stride in 16-byte rows), 1 if chunks are transformed in smem
@@ -62,6 +63,55 @@ __device__ __forceinline__ Item decode_item(const WsP &p, int it) {
 // 32*(w%4)..+31 (= accumulator rows 32*(w%4)+lane of every M block); with 8 warps the two warps of a lane
 // quarter split the 16-column groups of the accumulator between them.  Named barrier 2 is private to
 // these NEW*32 threads.
+// GroupNorm scale / shift of every input channel of sample b into sAff[0..Cin) / sAff[Cin..2Cin) (the SiLU's
+// 1/2 folded in), computed by `nthreads` threads (thread index `t`).  The per-channel {sum, sum of squares}
+// of source i are either folded already (double2 [B, C], st_slots[i] == 0) or are the fp32 partial rows its
+// producer's epilogue wrote, one per CTA that touched the sample: folded here in row order, in double.
+__device__ __forceinline__ void gn_build_affine(const WsP &p, int b, float *sAff, int t, int nthreads) {
+    const int cpg = p.Cin / kGnGroups;
+    const double inv_n = 1.0 / (double(cpg) * double(p.Hin) * double(p.Win));
+    const float half = p.silu ? 0.5f : 1.0f;
+    int n_rows[2] = {0, 0};  // partial rows of sample b per source (32-bit: the host checked (B*ips+1)*grid < 2^31)
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+        if (p.st_slots[i] > 0) {
+            const unsigned ips = unsigned(p.st_ips[i]), grid = unsigned(p.st_grid[i]), items = unsigned(p.st_items[i]);
+            const unsigned c_first = ((unsigned(b) * ips + 1u) * grid - 1u) / items;
+            const unsigned c_last = ((unsigned(b) + 1u) * ips * grid - 1u) / items;
+            n_rows[i] = int(c_last - c_first) + 1;
+        }
+    for (int c = t; c < p.Cin; c += nthreads) {
+        const int g0 = (c / cpg) * cpg;
+        double s = 0.0, q = 0.0;
+        for (int j = 0; j < cpg; ++j) {
+            const int cc = g0 + j;
+            const int i = cc < p.C0 ? 0 : 1;
+            const int cs = i ? cc - p.C0 : cc;
+            const double *st = i ? p.stat1 : p.stat0;
+            if (p.st_slots[i] == 0) {
+                const double *e = st + (size_t(b) * (i ? p.C1 : p.C0) + cs) * 2;
+                s += e[0];
+                q += e[1];
+            } else {
+                const int rows = p.st_rows[i];
+                const float *pp = reinterpret_cast<const float *>(st) + (size_t(b) * p.st_slots[i] * rows + cs) * 2;
+                for (int r = 0; r < n_rows[i]; ++r) {
+                    const float2 v = __ldcg(reinterpret_cast<const float2 *>(pp + size_t(r) * rows * 2));
+                    s += double(v.x);
+                    q += double(v.y);
+                }
+            }
+        }
+        const double mean = s * inv_n;
+        double var = q * inv_n - mean * mean;
+        var = var < 0.0 ? 0.0 : var;
+        const float rstd = rsqrtf(float(var) + kGnEps);
+        const float a = p.gamma[c] * rstd;
+        sAff[c] = half * a;
+        sAff[p.Cin + c] = half * (p.beta[c] - float(mean) * a);
+    }
+}
+
 // optional milestone hook (conv_tma.cu defines CCDM_EPI_TRACE before including this header)
 #ifndef CCDM_EPI_TRACE
 #define CCDM_EPI_TRACE(slot)
@@ -80,7 +130,8 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
     // items are contiguous, so this is one or two partial rows per CTA instead of one per item.
     float *sAcc = sRed;  // [NEW][CoutP][2]
     const int CoutP = p.CoutP;
-    if (p.ostat != nullptr) {
+    const bool want_stats = p.part != nullptr;  // with ostat: folded here (ticket); without: deferred to the consumer
+    if (want_stats) {
         for (int e = lane; e < CoutP * 2; e += 32) sAcc[warp * CoutP * 2 + e] = 0.f;
         __syncwarp();
     }
@@ -96,6 +147,10 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
                 sAcc[r * CoutP * 2 + e] = 0.f;
             }
             p.part[(size_t(b) * p.slots + slot) * CoutP * 2 + e] = s;
+        }
+        if (p.ostat == nullptr) {  // deferred fold: the partial row IS the result; the kernel boundary publishes it
+            named_bar_sync(2, NTHR);
+            return;
         }
         __threadfence();
         named_bar_sync(2, NTHR);
@@ -134,7 +189,7 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
     for (int it = it_begin; it < it_end; ++it, ++acc_it) {
         const Item I = decode_item(p, it);
         if (I.b != cur_b && n_pending > 0) {
-            if (p.ostat != nullptr) flush_stats(cur_b, n_pending);
+            if (want_stats) flush_stats(cur_b, n_pending);
             n_pending = 0;
         }
         if (I.b != cur_b || I.cc != cur_cc) {
@@ -247,7 +302,7 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
                     }
                 }
             }
-            if (p.ostat != nullptr) {
+            if (want_stats) {
                 const float r1 = warp_transpose_reduce16(s1, lane);
                 const float r2 = warp_transpose_reduce16(s2, lane);
                 if ((lane & 1) == 0) {
@@ -269,7 +324,7 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
         if (tid == 0 && it == it_begin) CCDM_EPI_TRACE(6);
         ++n_pending;
     }
-    if (p.ostat != nullptr && n_pending > 0) flush_stats(cur_b, n_pending);
+    if (want_stats && n_pending > 0) flush_stats(cur_b, n_pending);
     if (tid == 0) CCDM_EPI_TRACE(7);
 }
 

@@ -222,26 +222,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
                     // GroupNorm scale/shift of the (concatenated) input of sample b; the SiLU's 0.5 is
                     // folded in: silu(x) = h + h*tanh(h), h = x/2.
                     named_bar_sync(1, XF_THREADS);
-                    const int cpg = p.Cin / kGnGroups;
-                    const double n = double(cpg) * double(p.Hin) * double(p.Win);
-                    const float half = p.silu ? 0.5f : 1.0f;
-                    for (int c = pt; c < p.Cin; c += XF_THREADS) {
-                        const int g0 = (c / cpg) * cpg;
-                        double s = 0.0, q = 0.0;
-                        for (int j = 0; j < cpg; ++j) {
-                            const int cc = g0 + j;
-                            const double *st = cc < p.C0 ? p.stat0 + (size_t(I.b) * p.C0 + cc) * 2 : p.stat1 + (size_t(I.b) * p.C1 + (cc - p.C0)) * 2;
-                            s += st[0];
-                            q += st[1];
-                        }
-                        const double mean = s / n;
-                        double var = q / n - mean * mean;
-                        var = var < 0.0 ? 0.0 : var;
-                        const float rstd = float(1.0 / sqrt(var + double(kGnEps)));
-                        const float a = p.gamma[c] * rstd;
-                        sAff[c] = half * a;
-                        sAff[p.Cin + c] = half * (p.beta[c] - float(mean) * a);
-                    }
+                    gn_build_affine(p, I.b, sAff, pt, XF_THREADS);
                     named_bar_sync(1, XF_THREADS);
                     if (pt == 0 && it == it_begin) trace(kTraceAffine);
                     cur_b = I.b;
@@ -614,6 +595,14 @@ int conv_tma_config(const ccdm_op &op, int32_t *out) {
     return 0;
 }
 
+// {slots, items per sample, items, grid, row length} of the partial statistics this op's epilogue writes
+int conv_tma_stat_layout(const ccdm_op &op, int32_t *out5) {
+    TmCfg c;
+    if (!conv_tma_supported(op) || !tm_configure_op(op, c)) return -1;
+    out5[0] = c.slots; out5[1] = c.ips; out5[2] = c.n_items; out5[3] = c.grid; out5[4] = (op.Cout + 15) / 16 * 16;
+    return 0;
+}
+
 size_t conv_tma_part_floats(const ccdm_op &op) {
     TmCfg c;
     if (!tm_configure_op(op, c)) return 0;
@@ -644,6 +633,10 @@ int launch_conv_tma(const ccdm_op &op, cudaStream_t s) {
     p.n_main = c.n_main; p.n_skip = c.n_skip; p.NS = c.NS; p.resident = c.resident; p.acc2 = c.acc2;
     p.tmem_cols = c.tmem_cols; p.n_items = c.n_items; p.ips = c.ips; p.slots = c.slots;
     p.RW = c.RW; p.NQ = c.NQ; p.xf = (op.gn || op.silu) ? 1 : 0; p.stride2 = op.stride == 2;
+    for (int i = 0; i < 2; ++i) {
+        p.st_slots[i] = op.st_slots[i]; p.st_ips[i] = op.st_ips[i]; p.st_items[i] = op.st_items[i];
+        p.st_grid[i] = op.st_grid[i]; p.st_rows[i] = op.st_rows[i];
+    }
     p.blk16 = uint32_t(((size_t(c.PL) * c.NQ * 16 + 127) & ~size_t(127)) >> 4);
     p.a_stage = c.a_stage; p.w_stage = c.w_stage; p.w_main_bytes = c.w_main_bytes; p.w_skip_bytes = c.w_skip_bytes;
     p.magicP = c.magicP;
@@ -653,6 +646,10 @@ int launch_conv_tma(const ccdm_op &op, cudaStream_t s) {
     if (op.gn && (!op.stat0 || (op.C1 && !op.stat1) || !op.gamma || !op.beta)) CCDM_FAIL(-2, "conv_tma: gn without stats/affine");
     if (op.gn && (p.Cin % kGnGroups)) CCDM_FAIL(-2, "conv_tma: GroupNorm needs Cin %% 32 == 0");
     if (op.ostat && (!op.part || !op.ticket)) CCDM_FAIL(-2, "conv_tma: ostat without scratch");
+    for (int i = 0; i < 2; ++i)
+        if (op.st_slots[i] > 0 && (op.st_ips[i] <= 0 || op.st_items[i] <= 0 || op.st_grid[i] <= 0 || op.st_rows[i] <= 0 ||
+                                   (double(op.B) * op.st_ips[i] + 1.0) * op.st_grid[i] >= 2147483648.0))
+            CCDM_FAIL(-2, "conv_tma: incomplete deferred-fold layout of stat%d", i);
     if (op.emb && (!op.steps || !op.step_ptr || op.emb_off < 0)) CCDM_FAIL(-2, "conv_tma: emb without step table");
     if (op.S0 > 0 && (!op.skip0 || !op.skip_w)) CCDM_FAIL(-2, "conv_tma: bad skip configuration");
     if (!op.src0 || (op.C1 && !op.src1) || (op.S1 && !op.skip1)) CCDM_FAIL(-2, "conv_tma: missing source tensor");

@@ -105,26 +105,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
                 // GroupNorm scale/shift of the (concatenated) input of sample b; the SiLU's 0.5 is
                 // folded in: silu(x) = h + h*tanh(h), h = x/2.
                 named_bar_sync(1, PROD_THREADS);
-                const int cpg = p.Cin / kGnGroups;
-                const double n = double(cpg) * double(p.Hin) * double(p.Win);
-                const float half = p.silu ? 0.5f : 1.0f;
-                for (int c = pt; c < p.Cin; c += PROD_THREADS) {
-                    const int g0 = (c / cpg) * cpg;
-                    double s = 0.0, q = 0.0;
-                    for (int j = 0; j < cpg; ++j) {
-                        const int cc = g0 + j;
-                        const double *st = cc < p.C0 ? p.stat0 + (size_t(I.b) * p.C0 + cc) * 2 : p.stat1 + (size_t(I.b) * p.C1 + (cc - p.C0)) * 2;
-                        s += st[0];
-                        q += st[1];
-                    }
-                    const double mean = s / n;
-                    double var = q / n - mean * mean;
-                    var = var < 0.0 ? 0.0 : var;
-                    const float rstd = float(1.0 / sqrt(var + double(kGnEps)));
-                    const float a = p.gamma[c] * rstd;
-                    sAff[c] = half * a;
-                    sAff[p.Cin + c] = half * (p.beta[c] - float(mean) * a);
-                }
+                gn_build_affine(p, I.b, sAff, pt, PROD_THREADS);
                 named_bar_sync(1, PROD_THREADS);
                 cur_b = I.b;
             }
@@ -465,6 +446,13 @@ int conv_tc_config(const ccdm_op &op, int32_t *out) {
     return 0;
 }
 
+int conv_tc_stat_layout(const ccdm_op &op, int32_t *out5) {
+    WsCfg c;
+    if (!conv_tc_supported(op) || !ws_configure_op(op, c)) return -1;
+    out5[0] = c.slots; out5[1] = c.ips; out5[2] = c.n_items; out5[3] = c.grid; out5[4] = (op.Cout + 15) / 16 * 16;
+    return 0;
+}
+
 size_t conv_tc_part_floats(const ccdm_op &op) {
     WsCfg c;
     if (!ws_configure_op(op, c)) return 0;
@@ -493,6 +481,10 @@ int launch_conv_tc(const ccdm_op &op, cudaStream_t s) {
     p.taps = op.ksize * op.ksize; p.pad = op.ksize / 2;
     p.n_main = c.n_main; p.n_skip = c.n_skip; p.NS = c.NS; p.resident = c.resident; p.acc2 = c.acc2;
     p.tmem_cols = c.tmem_cols; p.n_items = c.n_items; p.ips = c.ips; p.slots = c.slots;
+    for (int i = 0; i < 2; ++i) {
+        p.st_slots[i] = op.st_slots[i]; p.st_ips[i] = op.st_ips[i]; p.st_items[i] = op.st_items[i];
+        p.st_grid[i] = op.st_grid[i]; p.st_rows[i] = op.st_rows[i];
+    }
     p.a_stage = c.a_stage; p.w_stage = c.w_stage; p.w_main_bytes = c.w_main_bytes; p.w_skip_bytes = c.w_skip_bytes;
     p.magicP = c.magicP;
     // cute::UMMA::InstrDescriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major both, N>>3 at 17, M>>4 at 24

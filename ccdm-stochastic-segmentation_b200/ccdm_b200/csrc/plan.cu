@@ -72,6 +72,11 @@ extern "C" int ccdm_conv_tc_config(const ccdm_op *op, int32_t *out16) {
     return ccdm::conv_uses_tma(*op) ? ccdm::conv_tma_config(*op, out16) : ccdm::conv_tc_config(*op, out16);
 }
 extern "C" int ccdm_conv_uses_tma(const ccdm_op *op) { return op && ccdm::conv_uses_tma(*op) ? 1 : 0; }
+namespace ccdm { int conv_tma_stat_layout(const ccdm_op &op, int32_t *out5); int conv_tc_stat_layout(const ccdm_op &op, int32_t *out5); }
+extern "C" int ccdm_conv_stat_layout(const ccdm_op *op, int32_t *out5) {
+    if (!op || !out5 || !ccdm::conv_uses_tc(*op)) return -1;
+    return ccdm::conv_uses_tma(*op) ? ccdm::conv_tma_stat_layout(*op, out5) : ccdm::conv_tc_stat_layout(*op, out5);
+}
 extern "C" size_t ccdm_op_part_floats(const ccdm_op *op) { return op ? ccdm::op_part_floats(*op) : 0; }
 
 extern "C" int ccdm_check_device(void) {

@@ -53,6 +53,8 @@ class Ten:
     external: bool = False  # lives outside the arena (feature condition)
     addr: int = 0
     stat_addr: int = 0
+    part_addr: int = 0            # deferred-fold statistics: the producer's per-CTA partial rows (bf16 / tensor-core mode)
+    stat_layout: Optional[tuple] = None  # (slots, items per sample, items, grid, row length) of those rows
 
 
 class Arena:
@@ -465,6 +467,9 @@ class Program:
         self.emb_buf = torch.zeros(self.max_rows * max(emb_cols, 1), dtype=torch.float32, device=dev)
         self.t_buf = torch.zeros(self.max_rows, dtype=torch.float32, device=dev)
         W = eng.weights
+        self._stat_bufs = []
+        for t in self.tens.values():
+            t.part_addr, t.stat_layout = 0, None
         arr = (Op * self.n_ops)()
         for i, o in enumerate(self._op_dicts):
             f = {k: v for k, v in o.items() if not k.startswith("_")}
@@ -477,9 +482,15 @@ class Program:
                 op.image = self.addr["image"]
             if o["kind"] in (_lib.OP_CONV, _lib.OP_ATTENTION):
                 op.src0, op.C0 = src[0].addr, src[0].C
-                op.stat0 = src[0].stat_addr
                 if len(src) > 1:
-                    op.src1, op.C1, op.stat1 = src[1].addr, src[1].C, src[1].stat_addr
+                    op.src1, op.C1 = src[1].addr, src[1].C
+                for si, sten in enumerate(src[:2]):
+                    if sten.stat_layout is not None:  # the producer left per-CTA partial rows: this op folds them
+                        setattr(op, "stat%d" % si, sten.part_addr)
+                        for name, v in zip(("st_slots", "st_ips", "st_items", "st_grid", "st_rows"), sten.stat_layout):
+                            setattr(op, "%s%d" % (name, si), int(v))
+                    else:
+                        setattr(op, "stat%d" % si, sten.stat_addr)
             if "_g" in o:
                 op.gamma, op.beta = W.addr(o["_g"]), W.addr(o["_be"])
             if "_skip" in o:
@@ -507,7 +518,18 @@ class Program:
             out = o["_out"]
             if out is not None:
                 op.out = out.addr
-                if out.want_stat:
+                if out.want_stat and use_tc:
+                    # deferred fold: the epilogue only writes its per-CTA partial rows into a buffer owned by the
+                    # tensor; the consumers' GroupNorm prologue folds them (no ticket, fence or atomic in the producer)
+                    lay = (ctypes.c_int32 * 5)()
+                    _lib.check(L.ccdm_conv_stat_layout(ctypes.byref(op), lay), "conv_stat_layout")
+                    op.part = 1  # so that ccdm_op_part_floats sees a statistics-producing op
+                    nfl = int(L.ccdm_op_part_floats(ctypes.byref(op)))
+                    buf = torch.zeros(max(nfl, 2), dtype=torch.float32, device=dev)
+                    self._stat_bufs.append(buf)
+                    out.part_addr, out.stat_layout = buf.data_ptr(), tuple(int(v) for v in lay)
+                    op.part, op.ostat, op.ticket = out.part_addr, 0, 0
+                elif out.want_stat:
                     op.ostat = out.stat_addr
                     op.part = 1  # patched below once the scratch size is known
                     op.ticket = self.addr["ticket"]
@@ -521,11 +543,11 @@ class Program:
             op.steps = self.steps_buf.data_ptr()
             op.step_ptr = self.addr["step"]
             arr[i] = op
-        part_floats = max([int(L.ccdm_op_part_floats(ctypes.byref(arr[i]))) for i in range(self.n_ops)] + [1])
+        shared = [i for i in range(self.n_ops) if arr[i].part == 1]  # folded-by-producer ops share one scratch
+        part_floats = max([int(L.ccdm_op_part_floats(ctypes.byref(arr[i]))) for i in shared] + [1])
         self.part_buf = torch.zeros(part_floats, dtype=torch.float32, device=dev)
-        for i in range(self.n_ops):
-            if arr[i].part:
-                arr[i].part = self.part_buf.data_ptr()
+        for i in shared:
+            arr[i].part = self.part_buf.data_ptr()
         self.n_tc = sum(1 for i in range(self.n_ops) if arr[i].kind == _lib.OP_CONV and not arr[i].exact)
         self._op_array = arr
         self.plan = L.ccdm_plan_create(arr, self.n_ops)
@@ -756,7 +778,7 @@ class UNetEngine:
                 ten = o["_out"]
                 if ten is not None:
                     out[ten.name] = self.tensor_view(prog, ten).float().clone()
-                    if ten.want_stat:
+                    if ten.want_stat and ten.stat_layout is None:
                         soff = ten.stat_addr - prog.workspace.data_ptr()
                         out[ten.name + "#stat"] = prog.workspace[soff:soff + B * ten.C * 16].view(torch.float64).view(B, ten.C, 2).clone()
             out["probs"] = prog.probs.clone()

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define CCDM_ABI_VERSION 1
+#define CCDM_ABI_VERSION 2
 
 /* storage types of activations / packed conv weights */
 #define CCDM_DT_F32 0
@@ -98,6 +98,12 @@ typedef struct ccdm_op {
     int32_t src_kind;   /* 0: src0/src1 NHWC activations; 1: one-hot(labels_in) ++ image (unet.py:760) */
     int32_t exact;      /* 1: fp32 FFMA kernels (parity mode); 0: tensor-core kernels where available */
     int32_t reserved[2];
+    /* Layout of stat0 / stat1.  st_slots[i] == 0: double2 [B, C] {sum, sum of squares}, folded by the producer.
+     * st_slots[i] > 0 ("deferred fold", tensor-core producers): fp32 per-CTA partial rows [B][st_slots][st_rows][2] exactly
+     * as the producer's epilogue wrote them (ccdm_conv_stat_layout); the consumer folds rows
+     * [0, CTAs that touched sample b) in order, in double -- same sums, no ticket / fence / atomic in the producer. */
+    int32_t st_slots[2], st_ips[2], st_items[2], st_grid[2], st_rows[2];
+    int32_t pad_align;
     uint64_t seed;      /* Philox key */
     /* device pointers (0 = absent) */
     uint64_t src0, src1;       /* inputs NHWC                                             */
@@ -110,8 +116,8 @@ typedef struct ccdm_op {
     uint64_t skip_w;           /* packed [S0+S1][CoutP]                                   */
     uint64_t res;              /* identity residual NHWC [B,Hout,Wout,Cout]               */
     uint64_t out;              /* NHWC output                                             */
-    uint64_t ostat;            /* double2 [B,Cout] stats of `out` (0: not needed)         */
-    uint64_t part;             /* fp32 scratch for per-tile partial stats                 */
+    uint64_t ostat;            /* double2 [B,Cout] stats of `out` (0: not needed, or deferred fold: only `part` is written) */
+    uint64_t part;             /* fp32 per-CTA / per-tile partial stats (scratch, or the tensor's statistics in deferred mode) */
     uint64_t ticket;           /* uint32 [B] arrival counters (self-resetting)            */
     uint64_t labels_in;        /* uint8 [B,H,W]   (input conv, head)                      */
     uint64_t labels_out;       /* uint8 [B,H,W]   (head)                                  */
@@ -146,6 +152,9 @@ int ccdm_conv_tc_nt(int Cout);
  * bench and tests): out16 = {PL, R, Wt, MB, WN, NT, n_cc, NS, resident, acc2, tmem_cols, tiles, n_items,
  * grid, smem bytes, K chunks per item}.  Returns -1 if `op` does not run on that kernel. */
 int ccdm_conv_tc_config(const ccdm_op *op, int32_t *out16);
+/* Deferred-fold layout of the statistics a tensor-core conv `op` writes to `part`: out5 = {slots, items per sample,
+ * items, grid, row length}; the consumer's st_* fields.  Returns -1 if `op` does not run on a tensor-core kernel. */
+int ccdm_conv_stat_layout(const ccdm_op *op, int32_t *out5);
 /* 0 if the current device is compute capability 10.x, negative otherwise. */
 int ccdm_check_device(void);
 

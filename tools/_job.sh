@@ -1,9 +1,9 @@
 mkdir -p gpurun_out
-timeout 60 python tools/tiny_chain.py bf16 128 8 > gpurun_out/s4h_tiny.log 2>&1; rc=$?; echo "tiny rc=$rc"; tail -1 gpurun_out/s4h_tiny.log
+timeout 60 python tools/tiny_chain.py bf16 128 8 > gpurun_out/s4j_tiny.log 2>&1; rc=$?; echo "tiny rc=$rc"; tail -1 gpurun_out/s4j_tiny.log
 if [ $rc -eq 0 ]; then
-timeout 200 python -m pytest tests -m gpu -q -x > gpurun_out/s4h_pytest.log 2>&1; tail -3 gpurun_out/s4h_pytest.log | cut -c1-250
-timeout 120 python bench.py --steps 1 --warmup 1 --T 10 --no-cpu-baseline --op-table gpurun_out/s4h_ops_lidc.txt > gpurun_out/s4h_lidc.json 2>&1
-head -12 gpurun_out/s4h_ops_lidc.txt; tail -1 gpurun_out/s4h_ops_lidc.txt
-timeout 120 python bench.py --workload cityscapes --steps 1 --warmup 1 --T 6 --no-cpu-baseline --op-table gpurun_out/s4h_ops_cs.txt > gpurun_out/s4h_cs.json 2>&1
-head -6 gpurun_out/s4h_ops_cs.txt; tail -1 gpurun_out/s4h_ops_cs.txt
+timeout 240 python -m pytest tests -m gpu -q > gpurun_out/s4j_pytest.log 2>&1; tail -3 gpurun_out/s4j_pytest.log | cut -c1-250
+timeout 120 python bench.py --steps 1 --warmup 1 --T 10 --no-cpu-baseline --op-table gpurun_out/s4j_ops_lidc.txt > gpurun_out/s4j_lidc.json 2>&1
+grep -E "conv1x1|8x8|16x16" gpurun_out/s4j_ops_lidc.txt | head -12; tail -1 gpurun_out/s4j_ops_lidc.txt
+timeout 120 python bench.py --workload cityscapes --steps 1 --warmup 1 --T 6 --no-cpu-baseline --op-table gpurun_out/s4j_ops_cs.txt > gpurun_out/s4j_cs.json 2>&1
+tail -1 gpurun_out/s4j_ops_cs.txt
 fi
