@@ -391,7 +391,8 @@ static bool tma_enabled() {
     }
     return v == 1;
 }
-bool conv_uses_tma(const ccdm_op &op) { return !op.exact && op.kind == CCDM_OP_CONV && tma_enabled() && conv_tma_supported(op); }
+// (upsampling convs always take the TMA kernel: their packed weights are the 16 pre-summed sub-pixel tap matrices)
+bool conv_uses_tma(const ccdm_op &op) { return !op.exact && op.kind == CCDM_OP_CONV && (tma_enabled() || op.upsample) && conv_tma_supported(op); }
 bool conv_uses_tc(const ccdm_op &op) { return !op.exact && op.kind == CCDM_OP_CONV && (conv_uses_tma(op) || conv_tc_supported(op)); }
 
 size_t op_part_floats(const ccdm_op &op) {

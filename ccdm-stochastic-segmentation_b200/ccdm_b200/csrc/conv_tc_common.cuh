@@ -35,6 +35,7 @@ struct WsP {
     int n_main, n_skip, NS, resident, acc2, tmem_cols, n_items;
     int ips, slots;  // items per sample; statistics slots per sample (CTAs whose item range can touch one sample)
     int st_slots[2], st_ips[2], st_items[2], st_grid[2], st_rows[2];  // layout of stat0 / stat1 (ccdm_op::st_*)
+    int nsub;        // accumulator sets per M block: 1, or 4 output parities of a fused nearest-x2 + conv3x3 (conv_tma)
     int stride2;     // conv_tma: 3x3 stride-2 conv (Downsample): the stage holds the 4 (row, column) parity sub-images
     uint32_t blk16;  // conv_tma, stride 2: size of one parity sub-image block in 16-byte rows (128-byte aligned for TMA)
     int RW, NQ, xf;  // conv_tma: window rows, window positions (= plane stride in 16-byte rows), 1 if chunks are transformed in smem
@@ -117,7 +118,7 @@ __device__ __forceinline__ void gn_build_affine(const WsP &p, int b, float *sAff
 #define CCDM_EPI_TRACE(slot)
 #endif
 
-template <int NEW>
+template <int NEW, int NSUB = 1>
 __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, float *sRed, int *s_last, uint64_t *acc_full,
                                                    uint64_t *acc_empty, uint32_t tmem_base, int it_begin, int it_end) {
     constexpr int NTHR = NEW * 32;
@@ -182,7 +183,11 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
     const int j0 = quarter * 32 + lane;
     const int o0 = int((uint32_t(j0) * p.magicP) >> 20), c0 = j0 - o0 * P;
     const int d128r = int((128u * p.magicP) >> 20), d128c = 128 - d128r * P;
-    const size_t hw = size_t(p.H) * p.W;
+    // upsampling conv: the tile space (p.H x p.W) is the low-resolution grid, every accumulator row owns the 2x2
+    // output pixels (2y+py, 2x+px), one accumulator set per parity
+    constexpr int ups = NSUB == 4 ? 2 : 1, nsub = NSUB;  // compile-time: the common (NSUB = 1) path pays nothing for it
+    const int Wo = p.W * ups;
+    const size_t hw = size_t(p.H) * p.W * ups * ups;
     const int n_cg = NT / CGW;
 
     int acc_it = 0, cur_b = -1, cur_cc = -1, n_pending = 0;
@@ -208,11 +213,12 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
         }
         const int buf = p.acc2 ? (acc_it & 1) : 0;
         const uint32_t aph = p.acc2 ? uint32_t((acc_it >> 1) & 1) : uint32_t(acc_it & 1);
-        const uint32_t tbase = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * p.MB * NT);
+        const uint32_t tbase = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * p.MB * NT * nsub);
         const int ylim = min(p.R, p.H - I.y0), xlim = min(p.Wt, p.W - I.x0);  // rows / columns of real outputs
-        const size_t pix0 = size_t(I.y0) * p.W + I.x0;
         bool waited = false;
-        for (int cg = half; cg < n_cg; cg += NHALF) {
+        for (int cgs = half; cgs < n_cg * nsub; cgs += NHALF) {
+            const int cg = cgs / nsub, sub = cgs - cg * nsub;  // channel group, output parity (py, px) = (sub >> 1, sub & 1)
+            const size_t pix0 = size_t(I.y0 * ups + (sub >> 1)) * Wo + I.x0 * ups + (sub & 1);
             const int cobase = I.co0 + cg * CGW;
             float add[CGW];
 #pragma unroll
@@ -232,7 +238,7 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
             // software pipeline: the residual of row block mb+1 is fetched while block mb is processed
             uint4 res_n[CGW / 8];
             bool valid_n = o < ylim && c < xlim;
-            int off_n = o * p.W + c;
+            int off_n = (o * Wo + c) * ups;
             if (resb != nullptr && valid_n) {
 #pragma unroll
                 for (int h2 = 0; h2 < CGW / 8; ++h2) res_n[h2] = ldg_nc16(resb + (size_t(h2) * hw + off_n) * 8);
@@ -256,14 +262,14 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
                         ++o;
                     }
                     valid_n = o < ylim && c < xlim;
-                    off_n = o * p.W + c;
+                    off_n = (o * Wo + c) * ups;
                     if (resb != nullptr && valid_n) {
 #pragma unroll
                         for (int h2 = 0; h2 < CGW / 8; ++h2) res_n[h2] = ldg_nc16(resb + (size_t(h2) * hw + off_n) * 8);
                     }
                 }
                 float v[CGW];
-                tmem_ld16(tbase + uint32_t(mb * NT + cg * CGW), v);
+                tmem_ld16(tbase + uint32_t((mb * nsub + sub) * NT + cg * CGW), v);
                 if (valid) {
 #pragma unroll
                     for (int i = 0; i < CGW; ++i) v[i] += add[i];

@@ -480,7 +480,7 @@ int launch_conv_tc(const ccdm_op &op, cudaStream_t s) {
     p.R = c.R; p.Wt = c.Wt; p.P = c.P; p.MB = c.MB; p.WN = c.WN; p.tiles_x = c.tiles_x; p.tiles = c.tiles;
     p.taps = op.ksize * op.ksize; p.pad = op.ksize / 2;
     p.n_main = c.n_main; p.n_skip = c.n_skip; p.NS = c.NS; p.resident = c.resident; p.acc2 = c.acc2;
-    p.tmem_cols = c.tmem_cols; p.n_items = c.n_items; p.ips = c.ips; p.slots = c.slots;
+    p.tmem_cols = c.tmem_cols; p.n_items = c.n_items; p.ips = c.ips; p.slots = c.slots; p.nsub = 1;
     for (int i = 0; i < 2; ++i) {
         p.st_slots[i] = op.st_slots[i]; p.st_ips[i] = op.st_ips[i]; p.st_items[i] = op.st_items[i];
         p.st_grid[i] = op.st_grid[i]; p.st_rows[i] = op.st_rows[i];

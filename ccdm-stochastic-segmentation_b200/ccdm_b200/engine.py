@@ -126,6 +126,28 @@ def from_pm(x_pm: torch.Tensor) -> torch.Tensor:
     return x_pm.permute(0, 2, 3, 1, 4).reshape(B, H, W, G * 8).contiguous()
 
 
+def subpixel_weights(w: torch.Tensor) -> torch.Tensor:
+    """3x3 weights [Cout,Cin,3,3] of ``conv3x3(nearest_x2(x))`` -> [Cout,Cin,4,4]: for every output parity
+    p = 2*py+px the 2x2 conv on the LOW-resolution input that produces output pixels (2y+py, 2x+px); tap
+    t = 2*ry+rx reads low-res pixel (y-1+py+ry, x-1+px+rx) and carries the sum of the 3x3 weights whose upsampled
+    source pixel is that low-res pixel (Upsample, unet.py:106-116; zero padding of the upsampled image coincides
+    with zero padding of the low-res image)."""
+    rows = {(0, 0): (0,), (0, 1): (1, 2), (1, 0): (0, 1), (1, 1): (2,)}  # (parity, r) -> original taps
+    co, ci = w.shape[:2]
+    out = torch.zeros(co, ci, 4, 4, dtype=torch.float32, device=w.device)
+    wf = w.float()
+    for py in (0, 1):
+        for px in (0, 1):
+            for ry in (0, 1):
+                for rx in (0, 1):
+                    acc = 0
+                    for dy in rows[(py, ry)]:
+                        for dx in rows[(px, rx)]:
+                            acc = acc + wf[:, :, dy, dx]
+                    out[:, :, 2 * py + px, 2 * ry + rx] = acc
+    return out
+
+
 def pack_bias(b: torch.Tensor) -> torch.Tensor:
     out = torch.zeros(_ceil(b.numel(), 32), dtype=torch.float32, device=b.device)
     out[:b.numel()] = b.float()
@@ -173,7 +195,7 @@ class PackedWeights:
                     self._reserve(p + ":w", 9 * _ceil(L.cin, 8) * _ceil(L.cout, 32), (9, _ceil(L.cin, 16), L.cout))
                     self._reserve(p + ":b", _ceil(L.cout, 32))
                 elif L.kind in ("down", "up"):
-                    self._reserve(p + ":w", 9 * L.cin * _ceil(L.cout, 32), (9, L.cin, L.cout))
+                    self._reserve(p + ":w", 9 * L.cin * _ceil(L.cout, 32), (16 if L.kind == "up" else 9, L.cin, L.cout))
                     self._reserve(p + ":b", _ceil(L.cout, 32))
                 elif L.kind == "res":
                     self._reserve(p + ":g1", L.cin); self._reserve(p + ":be1", L.cin)
@@ -242,7 +264,8 @@ class PackedWeights:
                     w_pad[:, :L.cin] = w_in
                     put(p + ":w", conv_w(w_in, _ceil(L.cin, 8)), w_pad); put(p + ":b", padded(sd[p + ".bias"]))
                 elif L.kind in ("down", "up"):
-                    put(p + ":w", conv_w(sd[p + ".weight"]), sd[p + ".weight"]); put(p + ":b", padded(sd[p + ".bias"]))
+                    raw = subpixel_weights(sd[p + ".weight"]) if L.kind == "up" else sd[p + ".weight"]
+                    put(p + ":w", conv_w(sd[p + ".weight"]), raw); put(p + ":b", padded(sd[p + ".bias"]))
                 elif L.kind == "res":
                     put(p + ":g1", sd[p + ".in_layers.0.weight"]); put(p + ":be1", sd[p + ".in_layers.0.bias"])
                     put(p + ":w1", conv_w(sd[p + ".in_layers.2.weight"]), sd[p + ".in_layers.2.weight"]); put(p + ":b1", sd[p + ".in_layers.2.bias"])

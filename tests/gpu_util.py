@@ -6,7 +6,7 @@ import torch
 import torch.nn.functional as F
 
 from ccdm_b200 import _lib
-from ccdm_b200.engine import from_pm, pack_bias, pack_conv_weight, pack_conv_weight_tc, to_pm
+from ccdm_b200.engine import from_pm, pack_bias, pack_conv_weight, pack_conv_weight_tc, subpixel_weights, to_pm
 
 
 def sp():
@@ -62,7 +62,7 @@ def run_conv(srcs, weight, bias, *, gn=None, silu=False, ksize=3, stride=1, upsa
     Wout = Win * 2 if upsample else ((Win + 1) // 2 if stride == 2 else Win)
     keep = []
     if tc:
-        wp = pack_conv_weight_tc(weight.to(dev)).contiguous()
+        wp = pack_conv_weight_tc(subpixel_weights(weight.to(dev)) if upsample else weight.to(dev)).contiguous()
     else:
         wp = pack_conv_weight(weight.to(dev), (cin + 7) // 8 * 8 if one_hot_in else None).contiguous()
     b = bias.to(dev).float()

@@ -221,3 +221,25 @@ def test_live_reference_agrees_with_oracle_on_fresh_seed():
     _, probs = chain_ref.reverse_chain(ours.unet.state_dict(), labels.numpy(), image, None, ours.diffusion.alphas.numpy(),
                                        ours.diffusion.cumalphas.numpy(), 100, 10005, "confidence", K=2)
     np.testing.assert_allclose(probs, out.permute(0, 2, 3, 1).numpy(), rtol=0, atol=2e-6)
+
+
+def test_subpixel_weights_reproduce_upsample_conv():
+    """nearest x2 + conv3x3 == four 2x2 convs on the low-resolution input with pre-summed taps (Upsample, unet.py:106-116)."""
+    import torch.nn.functional as F
+    from ccdm_b200.engine import subpixel_weights
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 5, 7, 6, generator=g)
+    w = torch.randn(4, 5, 3, 3, generator=g)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, padding=1)
+    wc = subpixel_weights(w)
+    xp = F.pad(x, (1, 1, 1, 1))
+    out = torch.zeros_like(ref)
+    for py in (0, 1):
+        for px in (0, 1):
+            acc = 0
+            for ry in (0, 1):
+                for rx in (0, 1):
+                    win = xp[:, :, py + ry:py + ry + 7, px + rx:px + rx + 6]
+                    acc = acc + torch.einsum("bchw,oc->bohw", win, wc[:, :, 2 * py + px, 2 * ry + rx])
+            out[:, :, py::2, px::2] = acc
+    assert float((out - ref).abs().max()) < 1e-4
