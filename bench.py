@@ -260,6 +260,9 @@ def run_gpu_arm(args, wl):
     m, _ = build_model(wl, dev)
     m.precision, m.noise, m.seed, m.sample_offset = args.precision, "philox", 2024, rank * B
     engine = m.unet.engine(args.precision)
+    if args.lanes:
+        engine.lanes = args.lanes
+    lanes = min(engine.lanes, B)
     image, feat, labels = synthetic_inputs(B, wl["C_img"], H, W, K, 384 if wl["fce"] else 0, seed=1234 + rank)
     x_host = torch.nn.functional.one_hot(labels.long(), K).permute(0, 3, 1, 2).float().contiguous().pin_memory()
     image_host = image.pin_memory()
@@ -319,11 +322,13 @@ def run_gpu_arm(args, wl):
     h2d = x_host.numel() * 4 + image_host.numel() * 4 + (feat_host.numel() * 4 if feat_host is not None else 0)
     d2h = world * B * H * W
 
-    prog = engine.program(B, H, W)
+    # with lanes the batch runs as `lanes` sub-batch programs; the per-op table describes one of them
+    prof_engine = engine._children[0] if lanes > 1 else engine
+    prog = prof_engine.program((B + lanes - 1) // lanes if lanes > 1 else B, H, W)
     line = None
     if rank == 0:
         peaks = measured_peaks()
-        rows, step_ms_eager = per_op_profile(engine, prog, n_iter=0 if args.no_op_profile else 5)
+        rows, step_ms_eager = per_op_profile(prof_engine, prog, n_iter=0 if args.no_op_profile else 5)
         if args.dump_ops:
             with open(args.dump_ops, "w") as fh:
                 json.dump([dict(index=i, op_class=op_class(prog._op_array[i]), bytes=op_bytes(prog._op_array[i], prog.esize),
@@ -371,10 +376,10 @@ def run_gpu_arm(args, wl):
             "config": {"workload": wl["name"], "batch_per_gpu": B, "T": T, "precision": args.precision,
                        "noise": "philox (in-kernel)", "parallelism": f"sample-sharded x{world}, 1 NCCL all-gather of labels",
                        "l2_policy": "per-step activation traffic exceeds L2 (126 MB): inputs larger than L2, no flush",
-                       "cuda_graph": True},
+                       "cuda_graph": True, "lanes": lanes},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e},
-            "gpu_launches": prog.n_ops * T * args.steps,
+            "gpu_launches": prog.n_ops * T * args.steps * lanes,
             "clocks": clk,
             "roofline": roof,
             "roofline_chain": {"bound": "hbm", "achieved": roof_chain, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -402,6 +407,7 @@ def main():
     ap.add_argument("--T", type=int, default=0, help="override the chain length (debug runs; invalid as a bench number)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=0, help="sub-batch streams per chain (0: engine default, CCDM_LANES)")
     ap.add_argument("--dump-ops", default="", help="write the op list of one reverse step (launch order, op class, algorithmic bytes) as JSON")
     ap.add_argument("--op-table", default="", help="write the per-op-class CUDA-event table to this file")
     ap.add_argument("--no-op-profile", action="store_true", help="skip the per-op CUDA-event pass (ncu runs)")

@@ -620,6 +620,15 @@ class UNetEngine:
         self.programs: Dict[tuple, Program] = {}
         self.stream = None if dry_run else torch.cuda.Stream(device=self.device)
         self.use_graph = True
+        # Lanes (experimental, default 1): the batch of a chain is split into `lanes` contiguous sub-batches that run as
+        # independent programs on their own streams, in the hope that the latency chains of the ~50 small launches per
+        # step overlap across sub-batches.  Philox noise is keyed by the global sample index, so the result does not
+        # depend on the split (tested).  MEASURED: no overlap happens -- LIDC B=64 2.37 / 2.84 / 4.14 ms per step at
+        # 1 / 2 / 4 lanes (the sub-batch steps serialise; every kernel asks for most of an SM's shared memory) -- so
+        # it stays off; see DESIGN.md section 9.
+        import os
+        self.lanes = max(1, int(os.environ.get("CCDM_LANES", "1")))
+        self._children: List["UNetEngine"] = []
 
     # -- helpers ----------------------------------------------------------------------
     def program(self, B, H, W, rows_per_sample=0) -> Program:
@@ -711,8 +720,44 @@ class UNetEngine:
 
     # -- reference DenoisingModel.forward_denoising -----------------------------------------
     @torch.no_grad()
+    def _lane_engines(self, n: int) -> List["UNetEngine"]:
+        while len(self._children) < n:
+            c = UNetEngine.__new__(UNetEngine)
+            c.dry_run, c.unet, c.precision, c.device, c.weights = False, self.unet, self.precision, self.device, self.weights
+            c.programs, c.stream, c.use_graph, c.lanes, c._children = {}, torch.cuda.Stream(device=self.device), self.use_graph, 1, []
+            self._children.append(c)
+        for c in self._children:
+            c.use_graph = self.use_graph
+        return self._children[:n]
+
+    @torch.no_grad()
+    def _run_chain_lanes(self, n_lanes, x, condition, feature_condition, t_values, alphas, cumalphas, last_mode, seed, sample0):
+        B = x.shape[0]
+        cur = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            self.weights.refresh()
+        base, extra = divmod(B, n_lanes)
+        outs, b0 = [], 0
+        for j, child in enumerate(self._lane_engines(n_lanes)):
+            b1 = b0 + base + (1 if j < extra else 0)
+            fc = feature_condition[b0:b1] if feature_condition is not None else None
+            outs.append(child.run_chain(x[b0:b1], condition[b0:b1], fc, t_values, alphas, cumalphas, last_mode, noise="philox",
+                                        seed=seed, sample0=sample0 + b0, _parent_stream=self.stream))
+            b0 = b1
+        for child in self._children[:n_lanes]:
+            cur.wait_stream(child.stream)
+        for lab, pr in outs:
+            lab.record_stream(cur)
+            if pr is not None:
+                pr.record_stream(cur)
+        labels = torch.cat([o[0] for o in outs], 0)
+        probs = torch.cat([o[1] for o in outs], 0) if outs[0][1] is not None else None
+        return labels, probs
+
+    @torch.no_grad()
     def run_chain(self, x, condition, feature_condition, t_values: Sequence[int], alphas, cumalphas, last_mode: int,
-                  noise: str = "torch", seed: int = 0, sample0: int = 0, record=None):
+                  noise: str = "torch", seed: int = 0, sample0: int = 0, record=None, _parent_stream=None):
         """Runs the reverse chain; returns (labels uint8 [B,H,W], probs fp32 [B,H,W,K] or None).
 
         ``alphas``/``cumalphas``: host float lists (the DiffusionModel buffers).  ``noise``:
@@ -737,7 +782,10 @@ class UNetEngine:
             noise = "torch"
         elif noise not in ("torch", "philox"):
             raise ValueError(f"noise={noise!r}")
-        cur = torch.cuda.current_stream(self.device)
+        n_lanes = min(self.lanes, B)
+        if n_lanes > 1 and noise == "philox" and noise_list is None and record is None:
+            return self._run_chain_lanes(n_lanes, x, condition, feature_condition, t_values, alphas, cumalphas, last_mode, seed, sample0)
+        cur = _parent_stream if _parent_stream is not None else torch.cuda.current_stream(self.device)
         self.stream.wait_stream(cur)
         with torch.cuda.stream(self.stream):
             self.weights.refresh()
@@ -774,7 +822,8 @@ class UNetEngine:
                         record.append(rec)
             labels = prog.labels.clone()
             probs = prog.probs.clone() if last_mode == _lib.DRAW_CONFIDENCE and t_values[-1] == 1 else None
-        cur.wait_stream(self.stream)
+        if _parent_stream is None:
+            cur.wait_stream(self.stream)
         return labels, probs
 
     @torch.no_grad()
