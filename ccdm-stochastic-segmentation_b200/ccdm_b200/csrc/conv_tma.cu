@@ -11,7 +11,7 @@
 //   * GroupNorm-apply + SiLU is an IN-PLACE pass over the landed stage (LDS.128 -> fp32 affine, tanh.approx
 //     -> bf16 -> STS.128, conflict-free), done by 8 warps that never see global-memory latency.  Raw chunks
 //     (1x1 skip conv, convs without a norm) skip the pass: TMA -> MMA directly.
-//   * tcgen05.mma is issued by TWO warps (even / odd M blocks): at N = 32 a single issuing thread
+//   * tcgen05.mma is issued by THREE warps (M blocks mw, mw+3, ...): at N = 32 a single issuing thread
 //     cannot keep the tensor pipe fed (measured: ~90 cycles of issue per 16-cycle MMA).
 //   * epilogue (conv_tc_common.cuh): TMEM -> registers -> +bias +embedding +residual -> plane-major store
 //     (a warp writes 512 contiguous bytes per plane) + GroupNorm statistics of the output.
@@ -20,7 +20,7 @@
 // skip_connection :221-228,262, attention qkv / proj_out :305-311, the output conv :701-705.
 //
 // Roles (608 threads, one CTA per SM, each CTA walks a contiguous range of work items):
-//   warps 0-7   epilogue | warps 8-15 in-place transform | warps 16-17 MMA issue | warp 18 TMA.
+//   warps 0-7   epilogue | warps 8-15 in-place transform | warps 16-18 MMA issue | warp 19 TMA.
 // All hand-offs are mbarriers; nothing in the main loop is a CTA-wide barrier.
 #include <cuda.h>
 #include <stdlib.h>
@@ -36,10 +36,10 @@ __device__ void conv_tma_trace_hook(int slot);
 namespace ccdm {
 namespace {
 
-constexpr int TM_EPI_WARPS = 8, XF_WARPS = 8, MMA_WARPS = 2;
+constexpr int TM_EPI_WARPS = 8, XF_WARPS = 8, MMA_WARPS = 3;
 constexpr int XF_THREADS = XF_WARPS * 32;
 constexpr int WARP_XF0 = TM_EPI_WARPS, WARP_MMA0 = WARP_XF0 + XF_WARPS, WARP_TMA = WARP_MMA0 + MMA_WARPS;
-constexpr int TM_THREADS = (WARP_TMA + 2) * 32;  // 640: five warpgroups (the last warp only pads the fifth)
+constexpr int TM_THREADS = (WARP_TMA + 1) * 32;  // 640: five warpgroups of four warps
 
 struct alignas(64) TmP {
     CUtensorMap map[4];  // src0, src1, skip0, skip1 (plane-major tensors, see make_map)
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
         }
     } else if (warp < WARP_TMA) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-        // =========================== MMA issue (two warps: M blocks mw, mw+2, ...) ==================
+        // =========================== MMA issue (three warps: M blocks mw, mw+3, ...) ================
         const int mw = warp - WARP_MMA0;
         int stage = 0, acc_it = 0;
         uint32_t phase = 0;

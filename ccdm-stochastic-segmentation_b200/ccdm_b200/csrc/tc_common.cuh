@@ -36,6 +36,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "r"(addr), "r"(parity), "r"(0x989680u)
             : "memory");
         if (ok) break;
+        // back off: a polling warp is always eligible and would take issue slots from the warps that do the work
+        // on its scheduler (measured: ~30 % of all issued instructions of conv_tma were polls)
+        if (spins >= 2u) __nanosleep(spins < 16u ? 40u : 200u);
         if ((++spins & 63u) == 0u) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;
