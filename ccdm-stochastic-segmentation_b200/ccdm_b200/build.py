@@ -57,7 +57,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write("\n".join(log))
     if failed:
         raise RuntimeError("nvcc failed; see output above")
-    subprocess.check_call([NVCC, "-shared", "-o", LIB, *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+    subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-lcudart_static",
+                           "-lpthread", "-ldl", "-lrt"])
     with open(STAMP, "w") as fh:
         fh.write(digest)
     return LIB
