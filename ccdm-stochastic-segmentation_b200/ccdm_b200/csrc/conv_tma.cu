@@ -500,6 +500,8 @@ bool tm_configure(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout,
         if (fixed + 2 * (a_stage + c.w_stage) > kTmSmemBudget) break;
         int NS = int((kTmSmemBudget - fixed) / (a_stage + c.w_stage));
         NS = NS > MAX_STAGES ? MAX_STAGES : NS;
+        static const int env_maxns = getenv("CCDM_TMA_MAXNS") ? atoi(getenv("CCDM_TMA_MAXNS")) : 0;  // tuning override
+        if (env_maxns >= 2 && NS > env_maxns && H * W <= 1024) NS = env_maxns;  // small maps only: leave room for a co-resident CTA
         const int tiles = ((H + R - 1) / R) * c.tiles_x;
         const long long items = (long long)B * tiles * c.n_cc;
         const int grid = int(items < kTmNumSMs ? items : kTmNumSMs);
