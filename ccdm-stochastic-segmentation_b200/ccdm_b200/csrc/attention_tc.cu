@@ -146,7 +146,9 @@ __global__ void __launch_bounds__(AT_QT) attention_tc_kernel(const AtP p) {
         mbar_wait(s_done, uint32_t(t) & 1u);
         tc_fence_after();
         // pass 1: row maximum of the tile
-        float tmax = -INFINITY;
+        // (four independent partial maxima / sums: a single running value would be a 128-long dependent chain per
+        // tile, and with two CTAs of four warps per SM there is nothing to hide its latency behind)
+        float tm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int c0 = 0; c0 < NK; c0 += 32) {
             if (c0 < nk) {
@@ -154,13 +156,14 @@ __global__ void __launch_bounds__(AT_QT) attention_tc_kernel(const AtP p) {
                 tmem_ld32(tmem_s + trow + uint32_t(c0), s);
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
-                    if (c0 + i < nk) tmax = fmaxf(tmax, s[i]);
+                    if (c0 + i < nk) tm[i & 3] = fmaxf(tm[i & 3], s[i]);
             }
         }
+        const float tmax = fmaxf(fmaxf(tm[0], tm[1]), fmaxf(tm[2], tm[3]));
         const float m_new = fmaxf(m, tmax);
         const float corr = ex2_approx((m - m_new) * c);  // m = -inf on the first tile -> 0
         const float mc = m_new * c;
-        float rsum = 0.f;
+        float rs[4] = {0.f, 0.f, 0.f, 0.f};
         // pass 2: P = exp2(S*c - m*c) as bf16, K-major rows for the P V product
 #pragma unroll
         for (int c0 = 0; c0 < NK; c0 += 32) {
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(AT_QT) attention_tc_kernel(const AtP p) {
                     float p1 = (c0 + i + 1 < nk) ? ex2_approx(fmaf(s[i + 1], c, -mc)) : 0.f;
                     pk[i / 2] = pack_bf16(p0, p1);
                     const float2 f = unpack_bf16(pk[i / 2]);  // the sum of what the MMA will actually see
-                    rsum += f.x + f.y;
+                    rs[(i >> 1) & 3] += f.x + f.y;
                 }
             } else {
 #pragma unroll
@@ -184,7 +187,7 @@ __global__ void __launch_bounds__(AT_QT) attention_tc_kernel(const AtP p) {
             for (int g = 0; g < 4; ++g)  // key planes c0/8 .. c0/8+3, this thread's row
                 *reinterpret_cast<uint4 *>(sP + (size_t(c0 / 8 + g) * AT_QT + tid) * 16) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
         }
-        l = l * corr + rsum;
+        l = l * corr + ((rs[0] + rs[1]) + (rs[2] + rs[3]));
         m = m_new;
         fence_proxy_async();
         tc_fence_before();

@@ -6,6 +6,6 @@ timeout 200 python bench.py --steps 2 --warmup 3 --T 40 --no-cpu-baseline --op-t
 grep attention gpurun_out/s5e_ops_lidc.txt; tail -1 gpurun_out/s5e_ops_lidc.txt
 timeout 200 python bench.py --workload cityscapes --steps 2 --warmup 3 --T 30 --no-cpu-baseline --op-table gpurun_out/s5e_ops_cs.txt > gpurun_out/s5e_cs.json 2>&1
 grep attention gpurun_out/s5e_ops_cs.txt; tail -1 gpurun_out/s5e_ops_cs.txt
-CCDM_ATT_NK=128 timeout 200 python bench.py --workload cityscapes --steps 2 --warmup 3 --T 30 --no-cpu-baseline --op-table gpurun_out/s5e_ops_cs128.txt > gpurun_out/s5e_cs128.json 2>&1
-grep attention gpurun_out/s5e_ops_cs128.txt; tail -1 gpurun_out/s5e_ops_cs128.txt
+true
+true
 fi
