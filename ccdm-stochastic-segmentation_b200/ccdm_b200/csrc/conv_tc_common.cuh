@@ -235,48 +235,34 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
 #pragma unroll
             for (int i = 0; i < CGW; ++i) s1[i] = 0.f, s2[i] = 0.f;
             int o = o0, c = c0;
-            // software pipeline: the residual of row block mb+1 is fetched while block mb is processed
-            uint4 res_n[CGW / 8];
-            bool valid_n = o < ylim && c < xlim;
-            int off_n = (o * Wo + c) * ups;
-            if (resb != nullptr && valid_n) {
-#pragma unroll
-                for (int h2 = 0; h2 < CGW / 8; ++h2) res_n[h2] = ldg_nc16(resb + (size_t(h2) * hw + off_n) * 8);
-            }
             if (!waited) {
                 mbar_wait(acc_full + buf, aph);
                 tc_fence_after();
                 waited = true;
             }
-            for (int mb = 0; mb < p.MB; ++mb) {
-                const bool valid = valid_n;
-                const int off = off_n;
-                uint4 rr[CGW / 8];
-#pragma unroll
-                for (int h2 = 0; h2 < CGW / 8; ++h2) rr[h2] = res_n[h2];
-                if (mb + 1 < p.MB) {
-                    c += d128c;
-                    o += d128r;
-                    if (c >= P) {
-                        c -= P;
-                        ++o;
-                    }
-                    valid_n = o < ylim && c < xlim;
-                    off_n = (o * Wo + c) * ups;
-                    if (resb != nullptr && valid_n) {
-#pragma unroll
-                        for (int h2 = 0; h2 < CGW / 8; ++h2) res_n[h2] = ldg_nc16(resb + (size_t(h2) * hw + off_n) * 8);
-                    }
+            // accumulator rows stream out of TMEM double-buffered: the load of row block mb+1 is in flight while
+            // block mb is processed (tcgen05.ld is asynchronous until tcgen05.wait::ld)
+            auto process = [&](const uint32_t (&raw)[CGW], int mb) {
+                (void)mb;
+                const bool valid = o < ylim && c < xlim;
+                const int off = (o * Wo + c) * ups;
+                c += d128c;  // next row block: 128 positions further in the flattened window
+                o += d128r;
+                if (c >= P) {
+                    c -= P;
+                    ++o;
                 }
                 float v[CGW];
-                tmem_ld16(tbase + uint32_t((mb * nsub + sub) * NT + cg * CGW), v);
+#pragma unroll
+                for (int i = 0; i < CGW; ++i) v[i] = __uint_as_float(raw[i]);
                 if (valid) {
 #pragma unroll
                     for (int i = 0; i < CGW; ++i) v[i] += add[i];
-                    if (resb != nullptr) {
+                    if (resb != nullptr) {  // identity residual read here (the engine's bf16 path folds it into the MMA instead)
 #pragma unroll
                         for (int h2 = 0; h2 < CGW / 8; ++h2) {
-                            const uint32_t w4[4] = {rr[h2].x, rr[h2].y, rr[h2].z, rr[h2].w};
+                            const uint4 rr = ldg_nc16(resb + (size_t(h2) * hw + off) * 8);
+                            const uint32_t w4[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 float2 f = unpack_bf16(w4[i]);
@@ -306,6 +292,19 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
                         s1[i] += v[i];
                         s2[i] = fmaf(v[i], v[i], s2[i]);
                     }
+                }
+            };
+            const uint32_t tcol = tbase + uint32_t(sub * NT + cg * CGW), tstep = uint32_t(nsub * NT);
+            uint32_t ra[CGW], rb[CGW];
+            tmem_ld16_issue(tcol, ra);
+            for (int mb = 0; mb < p.MB; mb += 2) {
+                tmem_ld_wait16(ra);
+                if (mb + 1 < p.MB) tmem_ld16_issue(tcol + uint32_t(mb + 1) * tstep, rb);
+                process(ra, mb);
+                if (mb + 1 < p.MB) {
+                    tmem_ld_wait16(rb);
+                    if (mb + 2 < p.MB) tmem_ld16_issue(tcol + uint32_t(mb + 2) * tstep, ra);
+                    process(rb, mb + 1);
                 }
             }
             if (want_stats) {
