@@ -71,7 +71,7 @@ __device__ __forceinline__ Item decode_item(const WsP &p, int it) {
 __device__ __forceinline__ void gn_build_affine(const WsP &p, int b, float *sAff, int t, int nthreads) {
     const int cpg = p.Cin / kGnGroups;
     const double inv_n = 1.0 / (double(cpg) * double(p.Hin) * double(p.Win));
-    const float half = p.silu ? 0.5f : 1.0f;
+    const float half = (p.silu == 1 || p.silu == 2) ? 0.5f : 1.0f;  // tanh forms of SiLU work on x/2
     int n_rows[2] = {0, 0};  // partial rows of sample b per source (32-bit: the host checked (B*ips+1)*grid < 2^31)
 #pragma unroll
     for (int i = 0; i < 2; ++i)
@@ -116,6 +116,9 @@ __device__ __forceinline__ void gn_build_affine(const WsP &p, int b, float *sAff
 // optional milestone hook (conv_tma.cu defines CCDM_EPI_TRACE before including this header)
 #ifndef CCDM_EPI_TRACE
 #define CCDM_EPI_TRACE(slot)
+#endif
+#ifndef CCDM_EPI_TL
+#define CCDM_EPI_TL(item, edge)
 #endif
 
 template <int NEW, int NSUB = 1>
@@ -239,6 +242,7 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
                 mbar_wait(acc_full + buf, aph);
                 tc_fence_after();
                 waited = true;
+                if (tid == 0) CCDM_EPI_TL(it - it_begin, 0);
             }
             // accumulator rows stream out of TMEM double-buffered: the load of row block mb+1 is in flight while
             // block mb is processed (tcgen05.ld is asynchronous until tcgen05.wait::ld)
@@ -327,6 +331,7 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty + buf);
         if (tid == 0 && it == it_begin) CCDM_EPI_TRACE(6);
+        if (tid == 0) CCDM_EPI_TL(it - it_begin, 1);
         ++n_pending;
     }
     if (want_stats && n_pending > 0) flush_stats(cur_b, n_pending);

@@ -28,9 +28,11 @@
 namespace ccdm {
 namespace {
 __device__ void conv_tma_trace_hook(int slot);
+__device__ void conv_tma_tl_hook(int item, int edge);
 }
 }  // namespace ccdm
 #define CCDM_EPI_TRACE(slot) conv_tma_trace_hook(slot)
+#define CCDM_EPI_TL(item, edge) conv_tma_tl_hook(item, edge)
 #include "conv_tc_common.cuh"
 
 namespace ccdm {
@@ -72,6 +74,15 @@ __device__ __forceinline__ uint4 xf_row(uint4 raw, const float (&fa)[8], const f
         if (SILU == 1) {
             h0 = fmaf(h0, tanh_approx(h0), h0);
             h1 = fmaf(h1, tanh_approx(h1), h1);
+        }
+        if (SILU == 3) {  // x * sigmoid(x) = x / (1 + 2^(-x log2 e)): two full-rate MUFU ops instead of one tanh
+            float e0, e1, r0, r1;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(h0 * -1.4426950408889634f));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(h1 * -1.4426950408889634f));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(1.0f + e0));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(1.0f + e1));
+            h0 *= r0;
+            h1 *= r1;
         }
         r4[i] = pack_bf16(h0, h1);
         if (SILU == 2) {
@@ -139,6 +150,20 @@ __device__ __forceinline__ void xf_pass(uint32_t addr, int q, int NQ, int r, int
 // Milestone time stamps of CTA 0 (debug aid, read back with ccdm_debug_conv_trace): one store per milestone.
 __device__ unsigned long long g_trace[16];
 enum { kTraceStart = 0, kTraceSetup, kTraceAffine, kTraceRaw0, kTraceXf0, kTraceMma0, kTraceEpi0, kTraceFlush, kTraceEnd };
+// Steady-state timeline of CTA 0 (CCDM_TRACE builds): begin / end stamps of the first 8 items per role
+// {0 TMA issue, 1 transform, 2 MMA warp 0, 3 epilogue warp 0}.
+__device__ unsigned long long g_tl[4][8][2];
+__device__ __forceinline__ void tl(int role, int item, int edge) {
+#ifdef CCDM_TRACE
+    if (blockIdx.x == 0 && item < 8) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_tl[role][item][edge] = t;
+    }
+#else
+    (void)role; (void)item; (void)edge;
+#endif
+}
 __device__ __forceinline__ void trace(int slot) {
 #ifdef CCDM_TRACE
     if (blockIdx.x == 0) {
@@ -152,6 +177,7 @@ __device__ __forceinline__ void trace(int slot) {
 }
 
 __device__ void conv_tma_trace_hook(int slot) { trace(slot); }
+__device__ void conv_tma_tl_hook(int item, int edge) { tl(3, item, edge); }
 
 // PL = planes (8-channel groups) per K chunk: KC = 8*PL channels per pipeline stage.
 // UP: the fused nearest-x2 + conv3x3 variant (16 pre-summed sub-pixel taps, 4 accumulator sets per M block); a separate
@@ -261,6 +287,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
                 const bool need_mask = ymin < 0 || ymin + p.RW > p.H || xmin < 0 || xmin + P > p.W;
                 const int q0 = sub * 32 + lane;
                 const int r0 = int((uint32_t(q0) * p.magicP) >> 20), c0 = q0 - r0 * P;
+                if (pt == 0) tl(1, it - it_begin, 0);
                 for (int kc = 0; kc < n_chunks; ++kc) {
                     // every chunk is acknowledged on xf_full (raw skip-conv chunks without touching them), so
                     // that barrier completes exactly one phase per use of the stage, like the others; waiting
@@ -279,17 +306,19 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
                             }
                         } else {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) fa[i] = p.silu ? 0.5f : 1.0f, fb[i] = 0.f;
+                            for (int i = 0; i < 8; ++i) fa[i] = (p.silu == 1 || p.silu == 2) ? 0.5f : 1.0f, fb[i] = 0.f;
                         }
                         mbar_wait(raw_full + stage, phase);
                         if (pt == 0 && it == it_begin && kc == 0) trace(kTraceRaw0);
                         const uint32_t addr = sA32 + uint32_t(stage) * p.a_stage + (uint32_t(plane) * uint32_t(NQ) + uint32_t(q0)) * 16u;
                         if (need_mask) {
-                            if (p.silu == 2) xf_pass<STEP, true, 2>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
+                            if (p.silu == 3) xf_pass<STEP, true, 3>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
+                            else if (p.silu == 2) xf_pass<STEP, true, 2>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
                             else if (p.silu) xf_pass<STEP, true, 1>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
                             else xf_pass<STEP, true, 0>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
                         } else {
-                            if (p.silu == 2) xf_pass<STEP, false, 2>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
+                            if (p.silu == 3) xf_pass<STEP, false, 3>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
+                            else if (p.silu == 2) xf_pass<STEP, false, 2>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
                             else if (p.silu) xf_pass<STEP, false, 1>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
                             else xf_pass<STEP, false, 0>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
                         }
@@ -303,6 +332,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
                         phase ^= 1u;
                     }
                 }
+                if (pt == 0) tl(1, it - it_begin, 1);
             }
         }
     } else if (warp < WARP_TMA) {
@@ -322,6 +352,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
             const uint32_t aph = p.acc2 ? uint32_t((acc_it >> 1) & 1) : uint32_t(acc_it & 1);
             mbar_wait(acc_empty + buf, aph ^ 1u);
             tc_fence_after();
+            if (mw == 0 && lane == 0) tl(2, it - it_begin, 0);
             const uint32_t d0 = tmem_base + uint32_t(buf * p.MB * NT * (UP ? 4 : 1));
             for (int kc = 0; kc < n_chunks; ++kc) {
                 const bool is_skip = kc >= p.n_main;
@@ -399,6 +430,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
             }
             umma_commit_elect(acc_full + buf);
             if (mw == 0 && lane == 0 && it == it_begin) trace(kTraceMma0);
+            if (mw == 0 && lane == 0) tl(2, it - it_begin, 1);
         }
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -410,7 +442,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
             const uint32_t a_bytes = uint32_t(PL) * uint32_t(NQ) * 16u;
             for (int it = it_begin; it < it_end; ++it) {
                 const Item I = decode_item(p, it);
+                tl(0, it - it_begin, 0);
                 for (int kc = 0; kc < n_chunks; ++kc) {
+                    if (kc == n_chunks - 1) tl(0, it - it_begin, 1);
                     const bool is_skip = kc >= p.n_main;
                     const int cbase = is_skip ? (kc - p.n_main) * KC : kc * KC;
                     const int CA = is_skip ? p.S0 : p.C0;
@@ -622,9 +656,10 @@ int make_map_s2(CUtensorMap *m, const void *base, int B, int C, int H, int W, in
 }  // namespace
 
 int conv_tma_read_trace(unsigned long long *out, int n) {
-    unsigned long long tmp[16];
-    if (cudaMemcpyFromSymbol(tmp, g_trace, sizeof(tmp)) != cudaSuccess) return 0;
-    const int m = n < 16 ? n : 16;
+    unsigned long long tmp[16 + 64];
+    if (cudaMemcpyFromSymbol(tmp, g_trace, 16 * sizeof(unsigned long long)) != cudaSuccess) return 0;
+    if (cudaMemcpyFromSymbol(tmp + 16, g_tl, 64 * sizeof(unsigned long long)) != cudaSuccess) return 0;
+    const int m = n < 80 ? n : 80;  // [0,16): milestones; [16,80): timeline [role][item][begin/end]
     for (int i = 0; i < m; ++i) out[i] = tmp[i];
     return m;
 }
@@ -690,7 +725,7 @@ int launch_conv_tma(const ccdm_op &op, cudaStream_t s) {
     p.C0 = op.C0; p.C1 = op.C1; p.Cin = op.C0 + op.C1; p.Cout = op.Cout; p.CoutP = (op.Cout + 15) / 16 * 16;
     p.NT = c.NT; p.n_cc = c.n_cc;
     static const int env_silu = getenv("CCDM_SILU_MODE") ? atoi(getenv("CCDM_SILU_MODE")) : 1;
-    p.upsample = op.upsample; p.nsub = op.upsample ? 4 : 1; p.gn = op.gn; p.silu = op.silu ? (env_silu == 2 ? 2 : 1) : 0; p.S0 = op.S0; p.S1 = op.S1;
+    p.upsample = op.upsample; p.nsub = op.upsample ? 4 : 1; p.gn = op.gn; p.silu = op.silu ? (env_silu == 2 || env_silu == 3 ? env_silu : 1) : 0; p.S0 = op.S0; p.S1 = op.S1;
     p.emb_off = op.emb_off; p.emb_cols = op.emb_cols; p.emb_bstride = op.emb_bstride;
     p.out_f32 = op.out_dtype == CCDM_DT_F32;
     p.R = c.R; p.Wt = c.Wt; p.P = c.P; p.MB = c.MB; p.WN = c.NQ; p.tiles_x = c.tiles_x; p.tiles = c.tiles;

@@ -23,7 +23,7 @@ prog = eng.program(B, wl["H"], wl["W"])
 names = ["start", "setup", "affine", "raw0", "xf0", "mma0", "epi0", "flush", "end"]
 seen = set()
 sp = _lib.stream_ptr(eng.stream)
-buf = (ctypes.c_uint64 * 16)()
+buf = (ctypes.c_uint64 * 80)()
 with torch.cuda.stream(eng.stream):
     for i in range(prog.n_ops):
         o = prog._op_array[i]
@@ -36,7 +36,15 @@ with torch.cuda.stream(eng.stream):
         for _ in range(3):
             _lib.check(L.ccdm_launch_op(ctypes.byref(o), sp))
         eng.stream.synchronize()
-        L.ccdm_debug_conv_trace(buf, 16)
+        L.ccdm_debug_conv_trace(buf, 80)
         t = [int(v) for v in buf[:9]]
         rel = [(v - t[0]) / 1e3 if v >= t[0] else float("nan") for v in t]
         print(f"{c:44s} " + " ".join(f"{n}={r:6.1f}" for n, r in zip(names[1:], rel[1:])))
+        if "128x128" in c or "64x64" in c:
+            tl = [int(v) for v in buf[16:80]]
+            for role, rn in enumerate(("tma", "xform", "mma", "epi")):
+                row = []
+                for item in range(8):
+                    b, e = tl[(role * 8 + item) * 2], tl[(role * 8 + item) * 2 + 1]
+                    row.append(f"[{(b - t[0]) / 1e3:5.1f},{(e - t[0]) / 1e3:5.1f}]" if b >= t[0] and e >= t[0] else "[  -  ]")
+                print(f"      {rn:6s} " + " ".join(row))
