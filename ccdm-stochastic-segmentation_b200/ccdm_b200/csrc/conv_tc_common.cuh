@@ -13,6 +13,17 @@ constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int MAX_STAGES = 8;
 constexpr int CGW = 16;  // accumulator columns per tcgen05.ld
 
+// Output channels per work item (the N of the MMAs) = the packing unit of the weights, a function of Cout only so
+// that one packed tensor serves every shape.  Up to 128 output channels: the largest divisor <= 64 (narrow items:
+// more CTAs busy on small maps).  Wider layers (the 1x1 q/k/v convs, Cout = 3C): the largest divisor <= 192, so a
+// sample is 2 items instead of 6 and the input is normalised twice instead of six times.
+inline int tc_nt(int Cout) {
+    const int CoutP = (Cout + 15) / 16 * 16;
+    for (int nt = CoutP > 128 ? 192 : 64; nt >= 16; nt -= 16)
+        if (CoutP % nt == 0) return nt;
+    return 16;
+}
+
 struct WsP {
     const __nv_bfloat16 *src0, *src1;
     const double *stat0, *stat1;
@@ -65,10 +76,14 @@ __device__ __forceinline__ Item decode_item(const WsP &p, int it) {
 // quarter split the 16-column groups of the accumulator between them.  Named barrier 2 is private to
 // these NEW*32 threads.
 // GroupNorm scale / shift of every input channel of sample b into sAff[0..Cin) / sAff[Cin..2Cin) (the SiLU's
-// 1/2 folded in), computed by `nthreads` threads (thread index `t`).  The per-channel {sum, sum of squares}
-// of source i are either folded already (double2 [B, C], st_slots[i] == 0) or are the fp32 partial rows its
-// producer's epilogue wrote, one per CTA that touched the sample: folded here in row order, in double.
-__device__ __forceinline__ void gn_build_affine(const WsP &p, int b, float *sAff, int t, int nthreads) {
+// 1/2 folded in), computed by `nthreads` threads (thread index `t`) that share named barrier `bar_id`.  The
+// per-channel {sum, sum of squares} of source i are either folded already (double2 [B, C], st_slots[i] == 0) or
+// are the fp32 partial rows its producer's epilogue wrote, one per CTA that touched the sample: folded here in row
+// order, in double.  This runs at the head of every launch with nothing to overlap it, so it is arranged as ONE
+// round of independent L2 loads per four partial rows: thread c sums the rows of channel c (sSum, [Cin] double2
+// scratch), and after a barrier every thread adds up the cpg channels of its group from shared memory.  (The first
+// version walked cpg x rows elements per thread, one L2 round trip per channel of the group: 3 us at cpg = 4.)
+__device__ __forceinline__ void gn_build_affine(const WsP &p, int b, float *sAff, double2 *sSum, int t, int nthreads, int bar_id) {
     const int cpg = p.Cin / kGnGroups;
     const double inv_n = 1.0 / (double(cpg) * double(p.Hin) * double(p.Win));
     const float half = (p.silu == 1 || p.silu == 2) ? 0.5f : 1.0f;  // tanh forms of SiLU work on x/2
@@ -82,34 +97,53 @@ __device__ __forceinline__ void gn_build_affine(const WsP &p, int b, float *sAff
             n_rows[i] = int(c_last - c_first) + 1;
         }
     for (int c = t; c < p.Cin; c += nthreads) {
+        const int i = c < p.C0 ? 0 : 1;
+        const int cs = i ? c - p.C0 : c;
+        const double *st = i ? p.stat1 : p.stat0;
+        const float g = p.gamma[c], be = p.beta[c];
+        double s = 0.0, q = 0.0;
+        if (p.st_slots[i] == 0) {
+            const double2 e = __ldcg(reinterpret_cast<const double2 *>(st + (size_t(b) * (i ? p.C1 : p.C0) + cs) * 2));
+            s = e.x;
+            q = e.y;
+        } else {
+            const int rows = p.st_rows[i], n = n_rows[i];
+            const float2 *pp = reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(st) + (size_t(b) * p.st_slots[i] * rows + cs) * 2);
+            for (int r0 = 0; r0 < n; r0 += 4) {
+                float2 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = r0 + u < n ? r0 + u : r0;  // clamped: the load is unconditional, the value is masked
+                    v[u] = __ldcg(pp + size_t(r) * rows);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (r0 + u < n) {
+                        s += double(v[u].x);
+                        q += double(v[u].y);
+                    }
+            }
+        }
+        sSum[c] = make_double2(s, q);
+        sAff[c] = g;
+        sAff[p.Cin + c] = be;
+    }
+    named_bar_sync(bar_id, nthreads);
+    for (int c = t; c < p.Cin; c += nthreads) {
         const int g0 = (c / cpg) * cpg;
         double s = 0.0, q = 0.0;
         for (int j = 0; j < cpg; ++j) {
-            const int cc = g0 + j;
-            const int i = cc < p.C0 ? 0 : 1;
-            const int cs = i ? cc - p.C0 : cc;
-            const double *st = i ? p.stat1 : p.stat0;
-            if (p.st_slots[i] == 0) {
-                const double *e = st + (size_t(b) * (i ? p.C1 : p.C0) + cs) * 2;
-                s += e[0];
-                q += e[1];
-            } else {
-                const int rows = p.st_rows[i];
-                const float *pp = reinterpret_cast<const float *>(st) + (size_t(b) * p.st_slots[i] * rows + cs) * 2;
-                for (int r = 0; r < n_rows[i]; ++r) {
-                    const float2 v = __ldcg(reinterpret_cast<const float2 *>(pp + size_t(r) * rows * 2));
-                    s += double(v.x);
-                    q += double(v.y);
-                }
-            }
+            const double2 e = sSum[g0 + j];
+            s += e.x;
+            q += e.y;
         }
         const double mean = s * inv_n;
         double var = q * inv_n - mean * mean;
         var = var < 0.0 ? 0.0 : var;
         const float rstd = rsqrtf(float(var) + kGnEps);
-        const float a = p.gamma[c] * rstd;
+        const float a = sAff[c] * rstd;
         sAff[c] = half * a;
-        sAff[p.Cin + c] = half * (p.beta[c] - float(mean) * a);
+        sAff[p.Cin + c] = half * (sAff[p.Cin + c] - float(mean) * a);
     }
 }
 

@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
     uint64_t *acc_full = bars + 3 * MAX_STAGES, *acc_empty = acc_full + 2, *w_res = acc_empty + 2;
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(w_res + 1);
     int *s_last = reinterpret_cast<int *>(s_tmem + 1);
+    double2 *sSum = reinterpret_cast<double2 *>((reinterpret_cast<uintptr_t>(s_last + 1) + 15) & ~uintptr_t(15));  // [Cin] GroupNorm fold scratch
 
     if (warp == WARP_MMA0) tmem_alloc(s_tmem, uint32_t(p.tmem_cols));
     if (tid == WARP_TMA * 32) {
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
                     // GroupNorm scale/shift of the (concatenated) input of sample b; the SiLU's 0.5 is
                     // folded in: silu(x) = h + h*tanh(h), h = x/2.
                     named_bar_sync(1, XF_THREADS);
-                    gn_build_affine(p, I.b, sAff, pt, XF_THREADS);
+                    gn_build_affine(p, I.b, sAff, sSum, pt, XF_THREADS, 1);
                     named_bar_sync(1, XF_THREADS);
                     if (pt == 0 && it == it_begin) trace(kTraceAffine);
                     cur_b = I.b;
@@ -504,12 +505,7 @@ constexpr size_t kTmSmemBudget = 224 * 1024;  // of the 227 KB a CTA may opt in 
 constexpr size_t kTmResidentMax = 80 * 1024;  // weights kept in smem for the whole launch when they fit
 constexpr int kTmNumSMs = 148;
 
-int tm_nt(int Cout) {
-    const int CoutP = (Cout + 15) / 16 * 16;
-    for (int nt = 64; nt >= 16; nt -= 16)
-        if (CoutP % nt == 0) return nt;
-    return 16;
-}
+int tm_nt(int Cout) { return tc_nt(Cout); }
 
 bool tm_configure(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout, int ksize, int stride, int up, TmCfg &best) {
     const int Cin = C0 + C1, Sk = S0 + S1;
@@ -545,7 +541,7 @@ bool tm_configure(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout,
     c.resident = (c.n_cc == 1 && w_total <= kTmResidentMax) ? 1 : 0;
     c.w_stage = c.resident ? 0u : uint32_t(c.PL * taps * c.NT * 16);
     const size_t slack = (size_t(128 + 2 * pad * c.P + 2 * pad) * 16 + 127) & ~size_t(127);
-    const size_t fixed = sizeof(float) * (2 * size_t(Cin) + c.NT + size_t(TM_EPI_WARPS) * CoutP * 2) + (3 * MAX_STAGES + 5) * 8 + 64 + slack +
+    const size_t fixed = sizeof(float) * (2 * size_t(Cin) + c.NT + size_t(TM_EPI_WARPS) * CoutP * 2) + (3 * MAX_STAGES + 5) * 8 + 64 + 16 * size_t(Cin) + 16 + slack +
                          (c.resident ? w_total : 0) + 1024;
     double best_cost = 1e300;
     bool found = false;

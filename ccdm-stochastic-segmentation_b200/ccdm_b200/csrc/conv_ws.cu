@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
     uint64_t *acc_full = bars + 3 * MAX_STAGES, *acc_empty = acc_full + 2, *w_res = acc_empty + 2;
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(w_res + 1);
     int *s_last = reinterpret_cast<int *>(s_tmem + 1);
+    double2 *sSum = reinterpret_cast<double2 *>((reinterpret_cast<uintptr_t>(s_last + 1) + 15) & ~uintptr_t(15));  // [Cin] GroupNorm fold scratch
 
     if (warp == WARP_MMA) tmem_alloc(s_tmem, uint32_t(p.tmem_cols));
     if (tid == WARP_LOAD * 32) {
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
                 // GroupNorm scale/shift of the (concatenated) input of sample b; the SiLU's 0.5 is
                 // folded in: silu(x) = h + h*tanh(h), h = x/2.
                 named_bar_sync(1, PROD_THREADS);
-                gn_build_affine(p, I.b, sAff, pt, PROD_THREADS);
+                gn_build_affine(p, I.b, sAff, sSum, pt, PROD_THREADS, 1);
                 named_bar_sync(1, PROD_THREADS);
                 cur_b = I.b;
             }
@@ -331,15 +332,10 @@ constexpr size_t kSmemBudget = 222 * 1024;   // of the 227 KB a CTA may opt in t
 constexpr size_t kResidentMax = 80 * 1024;   // weights kept in smem for the whole launch when they fit
 constexpr int kNumSMs = 148;
 
-int ws_nt(int Cout) {
-    const int CoutP = (Cout + 15) / 16 * 16;
-    for (int nt = 64; nt >= 16; nt -= 16)
-        if (CoutP % nt == 0) return nt;
-    return 16;
-}
+int ws_nt(int Cout) { return tc_nt(Cout); }
 
 size_t ws_fixed_smem(int Cin, int NT, int CoutP) {
-    return sizeof(float) * (2 * size_t(Cin) + NT + size_t(EPI_WARPS) * CoutP * 2) + (3 * MAX_STAGES + 5) * 8 + 64;
+    return sizeof(float) * (2 * size_t(Cin) + NT + size_t(EPI_WARPS) * CoutP * 2) + (3 * MAX_STAGES + 5) * 8 + 64 + 16 * size_t(Cin) + 16;
 }
 
 bool ws_configure(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout, int ksize, WsCfg &best) {
