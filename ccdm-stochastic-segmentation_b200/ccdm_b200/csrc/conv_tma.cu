@@ -153,6 +153,19 @@ enum { kTraceStart = 0, kTraceSetup, kTraceAffine, kTraceRaw0, kTraceXf0, kTrace
 // Steady-state timeline of CTA 0 (CCDM_TRACE builds): begin / end stamps of the first 8 items per role
 // {0 TMA issue, 1 transform, 2 MMA warp 0, 3 epilogue warp 0}.
 __device__ unsigned long long g_tl[4][8][2];
+// start / end stamp of every CTA of the last launch (CCDM_TRACE builds): the spread shows load imbalance
+__device__ unsigned long long g_cta[2][160];
+__device__ __forceinline__ void cta_stamp(int edge) {
+#ifdef CCDM_TRACE
+    if (blockIdx.x < 160) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_cta[edge][blockIdx.x] = t;
+    }
+#else
+    (void)edge;
+#endif
+}
 __device__ __forceinline__ void tl(int role, int item, int edge) {
 #ifdef CCDM_TRACE
     if (blockIdx.x == 0 && item < 8) {
@@ -189,7 +202,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
     constexpr int KC = 8 * PL;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NT = p.NT, P = p.P, NS = p.NS, NQ = p.NQ;
-    if (tid == 0) trace(kTraceStart);
+    if (tid == 0) trace(kTraceStart), cta_stamp(0);
 
     // smem carve-up: [NS] activation stages (+ over-read slack) | weights | GN affine | bias | stats | barriers
     uint8_t *sA = smem_raw;
@@ -491,7 +504,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
         tc_fence_after();
         tmem_dealloc(tmem_base, uint32_t(p.tmem_cols));
     }
-    if (tid == 0) trace(kTraceEnd);
+    if (tid == 0) trace(kTraceEnd), cta_stamp(1);
 }
 
 // ---- host-side configuration --------------------------------------------------------------------
@@ -652,10 +665,11 @@ int make_map_s2(CUtensorMap *m, const void *base, int B, int C, int H, int W, in
 }  // namespace
 
 int conv_tma_read_trace(unsigned long long *out, int n) {
-    unsigned long long tmp[16 + 64];
+    unsigned long long tmp[16 + 64 + 320];
     if (cudaMemcpyFromSymbol(tmp, g_trace, 16 * sizeof(unsigned long long)) != cudaSuccess) return 0;
     if (cudaMemcpyFromSymbol(tmp + 16, g_tl, 64 * sizeof(unsigned long long)) != cudaSuccess) return 0;
-    const int m = n < 80 ? n : 80;  // [0,16): milestones; [16,80): timeline [role][item][begin/end]
+    if (cudaMemcpyFromSymbol(tmp + 80, g_cta, 320 * sizeof(unsigned long long)) != cudaSuccess) return 0;
+    const int m = n < 400 ? n : 400;  // [0,16): milestones; [16,80): timeline [role][item][begin/end]; [80,400): CTA [start|end][160]
     for (int i = 0; i < m; ++i) out[i] = tmp[i];
     return m;
 }

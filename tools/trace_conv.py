@@ -23,7 +23,7 @@ prog = eng.program(B, wl["H"], wl["W"])
 names = ["start", "setup", "affine", "raw0", "xf0", "mma0", "epi0", "flush", "end"]
 seen = set()
 sp = _lib.stream_ptr(eng.stream)
-buf = (ctypes.c_uint64 * 80)()
+buf = (ctypes.c_uint64 * 400)()
 with torch.cuda.stream(eng.stream):
     for i in range(prog.n_ops):
         o = prog._op_array[i]
@@ -36,11 +36,19 @@ with torch.cuda.stream(eng.stream):
         for _ in range(3):
             _lib.check(L.ccdm_launch_op(ctypes.byref(o), sp))
         eng.stream.synchronize()
-        L.ccdm_debug_conv_trace(buf, 80)
+        L.ccdm_debug_conv_trace(buf, 400)
         t = [int(v) for v in buf[:9]]
         rel = [(v - t[0]) / 1e3 if v >= t[0] else float("nan") for v in t]
         print(f"{c:44s} " + " ".join(f"{n}={r:6.1f}" for n, r in zip(names[1:], rel[1:])))
-        if "128x128" in c or "64x64" in c:
+        cfg = (ctypes.c_int32 * 16)()
+        L.ccdm_conv_tc_config(ctypes.byref(o), cfg)
+        grid = min(int(cfg[13]), 160)
+        st = sorted(int(v) - t[0] for v in buf[80:80 + grid])
+        en = sorted(int(v) - t[0] for v in buf[240:240 + grid])
+        dur = sorted(int(buf[240 + k]) - int(buf[80 + k]) for k in range(grid))
+        print(f"      CTAs {grid} items {cfg[12]}: start min/med/max {st[0] / 1e3:.1f}/{st[grid // 2] / 1e3:.1f}/{st[-1] / 1e3:.1f}  "
+              f"end {en[0] / 1e3:.1f}/{en[grid // 2] / 1e3:.1f}/{en[-1] / 1e3:.1f}  duration {dur[0] / 1e3:.1f}/{dur[grid // 2] / 1e3:.1f}/{dur[-1] / 1e3:.1f} us")
+        if "128x128" in c or "64x64" in c or "256x512" in c:
             tl = [int(v) for v in buf[16:80]]
             for role, rn in enumerate(("tma", "xform", "mma", "epi")):
                 row = []
