@@ -115,6 +115,18 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
     return c;
 }
 // bits -> Exp(1): u = ((bits >> 9) + 0.5) * 2^-23 is exact in fp32 and in (0,1).
+// approximate base-2 exponential / logarithm (MUFU), for the non-exact engine mode only
+__device__ __forceinline__ float exp2f_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float log2f_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ float bits_to_exponential(uint32_t bits) {
     float u = (static_cast<float>(bits >> 9) + 0.5f) * 1.1920928955078125e-07f;
     return -logf(u);

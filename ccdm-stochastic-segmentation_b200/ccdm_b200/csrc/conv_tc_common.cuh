@@ -309,11 +309,21 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
                             }
                         }
                     }
-                    if (p.out_f32) {  // fp32 logits stay NHWC
+                    if (p.out_f32) {  // fp32 logits stay NHWC: Cout floats per pixel, written with the widest aligned store
                         float *op = outf + size_t(off) * p.Cout;
+                        if ((p.Cout & 3) == 0) {  // K = 20: a pixel's row is 16-byte aligned
 #pragma unroll
-                        for (int i = 0; i < CGW; ++i)
-                            if (cobase + i < p.Cout) op[i] = v[i];
+                            for (int i = 0; i < CGW; i += 4)
+                                if (cobase + i < p.Cout) *reinterpret_cast<float4 *>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        } else if ((p.Cout & 1) == 0) {  // K = 2: one 8-byte store per pixel, contiguous across the warp
+#pragma unroll
+                            for (int i = 0; i < CGW; i += 2)
+                                if (cobase + i < p.Cout) *reinterpret_cast<float2 *>(op + i) = make_float2(v[i], v[i + 1]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < CGW; ++i)
+                                if (cobase + i < p.Cout) op[i] = v[i];
+                        }
                     } else {
 #pragma unroll
                         for (int h2 = 0; h2 < CGW / 8; ++h2) {

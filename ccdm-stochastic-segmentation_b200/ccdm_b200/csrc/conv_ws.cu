@@ -473,6 +473,7 @@ int launch_conv_tc(const ccdm_op &op, cudaStream_t s) {
     p.upsample = op.upsample; p.gn = op.gn; p.silu = op.silu; p.S0 = op.S0; p.S1 = op.S1;
     p.emb_off = op.emb_off; p.emb_cols = op.emb_cols; p.emb_bstride = op.emb_bstride;
     p.out_f32 = op.out_dtype == CCDM_DT_F32;
+    if (p.out_f32 && (reinterpret_cast<uintptr_t>(op.out) & 15)) CCDM_FAIL(-2, "conv: fp32 output must be 16-byte aligned");
     p.R = c.R; p.Wt = c.Wt; p.P = c.P; p.MB = c.MB; p.WN = c.WN; p.tiles_x = c.tiles_x; p.tiles = c.tiles;
     p.taps = op.ksize * op.ksize; p.pad = op.ksize / 2;
     p.n_main = c.n_main; p.n_skip = c.n_skip; p.NS = c.NS; p.resident = c.resident; p.acc2 = c.acc2;

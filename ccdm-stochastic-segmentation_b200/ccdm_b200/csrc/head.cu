@@ -42,7 +42,69 @@ struct HeadP {
     int K;
     int from_logits;
     int noise_mode;
+    int fast;  // ccdm_op::exact == 0: sampling steps may use the fast-math path below
 };
+
+// Sampling step in fast maths (bf16 engine mode, ccdm_op::exact == 0): the same quantities as the exact path --
+// softmax, closed-form posterior, clamp(1e-12), exponential race on the SAME Philox bits -- with approximate
+// exp2 / log2 / reciprocal instead of IEEE divisions (the exact path spends ~4 divisions per class), and without
+// the final normalisation, a positive factor common to all classes that cannot change the argmax.  Labels differ
+// from the exact path only where two race scores agree to ~1e-6 relative, far below what bf16 logits resolve.
+template <int KMAX>
+__device__ __forceinline__ int head_sample_fast(const float (&x)[KMAX], int K, int lab, float alpha, float cum, uint32_t pix, uint32_t smp,
+                                                uint32_t draw, uint64_t seed) {
+    constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+    float m = x[0];
+#pragma unroll
+    for (int c = 1; c < KMAX; ++c)
+        if (c < K) m = fmaxf(m, x[c]);
+    float v[KMAX];
+    float s = 0.f;
+    const float mo = m * kLog2e;
+#pragma unroll
+    for (int c = 0; c < KMAX; ++c)
+        if (c < K) {
+            v[c] = exp2f_approx(fmaf(x[c], kLog2e, -mo));
+            s += v[c];
+        }
+    const float Kf = float(K);
+    const float ua = (1.0f - alpha) / Kf, u = (1.0f - cum) / Kf;
+    const float a_hit = alpha + ua, a_miss = ua;
+    const float inv_s = __fdividef(1.0f, s);
+    const float w_hit = __fdividef(inv_s, fmaf(cum, a_hit, u)), w_miss = __fdividef(inv_s, fmaf(cum, a_miss, u));
+    float S = 0.f;
+#pragma unroll
+    for (int c = 0; c < KMAX; ++c)
+        if (c < K) {
+            v[c] *= (c == lab) ? w_hit : w_miss;  // softmax / z
+            S += v[c];
+        }
+    const float uS = u * S;
+    const uint2 key = make_uint2(uint32_t(seed), uint32_t(seed >> 32));
+    int best = 0;
+    float bestv = -1.0f;
+#pragma unroll
+    for (int cb = 0; cb < (KMAX + 3) / 4; ++cb)
+        if (cb * 4 < K) {
+            const uint4 r = philox4x32_10(make_uint4(pix, smp, draw, uint32_t(cb)), key);
+            const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = cb * 4 + j;
+                if (c < KMAX && c < K) {
+                    const float post = fmaxf(((c == lab) ? a_hit : a_miss) * fmaf(cum, v[c], uS), 1e-12f);
+                    const float uu = (static_cast<float>(w[j] >> 9) + 0.5f) * 1.1920928955078125e-07f;  // as bits_to_exponential
+                    const float e = -kLn2 * log2f_approx(uu);
+                    const float score = __fdividef(post, e);
+                    if (score > bestv) {
+                        bestv = score;
+                        best = c;
+                    }
+                }
+            }
+        }
+    return best;
+}
 
 template <int KMAX>
 __global__ void __launch_bounds__(128) head_kernel(const HeadP p) {
@@ -79,6 +141,11 @@ __global__ void __launch_bounds__(128) head_kernel(const HeadP p) {
                 if (c < K) v[c] = src[c];
         }
 
+        if (p.fast && p.from_logits && mode == CCDM_DRAW_SAMPLE && p.noise_mode != CCDM_NOISE_TENSOR && p.noise_out == nullptr &&
+            p.labels_out != nullptr && p.steps != nullptr) {
+            const uint32_t smp = i / p.n_pix, pix = i - smp * p.n_pix;
+            p.labels_out[i] = uint8_t(head_sample_fast<KMAX>(v, K, int(p.labels_in[i]), alpha, cum, pix, p.sample0 + smp, draw, p.seed));
+        } else {
         if (p.from_logits) {  // unet.py:706
             float m = v[0];
 #pragma unroll
@@ -189,6 +256,7 @@ __global__ void __launch_bounds__(128) head_kernel(const HeadP p) {
                 }
             p.labels_out[i] = uint8_t(best);
         }
+        }  // exact path
     }
     if (p.step_advance != nullptr) {
         // End of a reverse step: the last CTA to finish bumps the device step
@@ -282,6 +350,7 @@ int launch_head(const ccdm_op &op, cudaStream_t s) {
     p.K = op.K;
     p.from_logits = 1;
     p.noise_mode = op.noise_mode;
+    p.fast = op.exact ? 0 : 1;
     p.step_advance = (int *)op.step_ptr;
     p.step_ticket = (unsigned int *)op.ticket;
     if (!p.steps || !p.step_ptr || !p.step_ticket) CCDM_FAIL(-2, "head: needs the step table and a ticket");

@@ -24,16 +24,23 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
-bool pdl_enabled() {
+// CCDM_PDL: 0 = off, 1 = every launch, 2 = only the launches of ops on small maps (<= kPdlSmallPixels pixels per
+// sample: the latency-bound 8x8 .. 32x32 levels), selected per op by launch_any through g_pdl_hint.
+static thread_local int g_pdl_hint = 0;
+constexpr int kPdlSmallPixels = 1024;
+static int pdl_mode() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("CCDM_PDL");
-        v = (e && e[0] == '1') ? 1 : 0;  // opt-in: measured +2.4 % on LIDC B=64 but -10 % on Cityscapes B=8 (profiles/README.md)
+        v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
     }
-    return v == 1;
+    return v;
 }
+bool pdl_enabled() { return pdl_mode() == 1 || (pdl_mode() == 2 && g_pdl_hint); }
 
 static int launch_any(const ccdm_op &op, cudaStream_t s) {
+    g_pdl_hint = (op.kind == CCDM_OP_CONV || op.kind == CCDM_OP_ATTENTION) &&
+                 (op.kind == CCDM_OP_ATTENTION ? op.Hin * op.Win : op.Hout * op.Wout) <= kPdlSmallPixels;
     switch (op.kind) {
         case CCDM_OP_INPUT_CONV:
         case CCDM_OP_CONV: return launch_conv(op, s);

@@ -522,7 +522,8 @@ class Program:
                 if len(sk) > 1:
                     op.S1 = sk[1].C
             use_tc = bool(self.exact == 0 and o["kind"] == _lib.OP_CONV and L.ccdm_conv_uses_tc(ctypes.byref(op)))
-            if not use_tc and o["kind"] != _lib.OP_ATTENTION:  # attention: exact=0 selects the tcgen05 kernel (bf16, head_dim 32)
+            # attention: exact=0 selects the tcgen05 kernel (bf16, head_dim 32); head: exact=0 selects fast maths for sampling steps
+            if not use_tc and o["kind"] not in (_lib.OP_ATTENTION, _lib.OP_HEAD):
                 op.exact = 1
             if "_w" in o:
                 op.weight, op.bias = (W.addr16(o["_w"]) if use_tc else W.addr(o["_w"])), W.addr(o["_b"])

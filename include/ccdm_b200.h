@@ -96,7 +96,8 @@ typedef struct ccdm_op {
     int32_t sample0;    /* global index of local sample 0 (Philox counter; sharding) */
     int32_t out_dtype;  /* CCDM_DT_* of `out` (logits stay fp32 in bf16 mode) */
     int32_t src_kind;   /* 0: src0/src1 NHWC activations; 1: one-hot(labels_in) ++ image (unet.py:760) */
-    int32_t exact;      /* 1: fp32 FFMA kernels (parity mode); 0: tensor-core kernels where available */
+    int32_t exact;      /* 1: fp32 FFMA kernels (parity mode); 0: tensor-core kernels where available; HEAD: 0 lets sampling
+                         * steps use approximate exp2/log2/reciprocal (same Philox bits, no IEEE divisions) */
     int32_t reserved[2];
     /* Layout of stat0 / stat1.  st_slots[i] == 0: double2 [B, C] {sum, sum of squares}, folded by the producer.
      * st_slots[i] > 0 ("deferred fold", tensor-core producers): fp32 per-CTA partial rows [B][st_slots][st_rows][2] exactly

@@ -376,6 +376,38 @@ def test_tc_conv1x1_qkv_proj_and_head(L):
         _tc_check(out, ref_conv([x], w, b, gn=gn, silu=True))
 
 
+@pytest.mark.parametrize("K", [2, 20])
+def test_head_fast_sampling_agrees_with_exact(L, K):
+    """OP_HEAD with exact=0 (bf16 engine mode: approximate exp2/log2/reciprocal, no final normalisation) draws the same
+    labels as the exact path from the same logits and Philox bits, up to near-ties of the race scores."""
+    import ctypes
+    from ccdm_b200 import _lib
+    from gpu_util import StepCtx, sp
+    B, H, W = 3, 64, 96
+    g = torch.Generator().manual_seed(77)
+    logits = (torch.randn(B, H, W, K, generator=g) * 3).cuda().contiguous()
+    lab_in = torch.randint(0, K, (B, H, W), generator=g, dtype=torch.uint8).cuda()
+    outs = []
+    for exact in (1, 0):
+        ctx = StepCtx(t=17.0, alpha=0.97, cum=0.61, mode=_lib.DRAW_SAMPLE, draw=5)
+        lab_out = torch.full((B, H, W), 255, dtype=torch.uint8, device="cuda")
+        ticket = torch.zeros(4, dtype=torch.int32, device="cuda")
+        op = _lib.Op(kind=_lib.OP_HEAD, dtype=_lib.DT_F32, out_dtype=_lib.DT_F32, B=B, Hin=H, Win=W, Hout=H, Wout=W, K=K, exact=exact,
+                     noise_mode=_lib.NOISE_PHILOX, seed=1234, sample0=7)
+        op.src0, op.labels_in, op.labels_out = logits.data_ptr(), lab_in.data_ptr(), lab_out.data_ptr()
+        op.steps, op.step_ptr, op.ticket = ctx.table.data_ptr(), ctx.counter.data_ptr(), ticket.data_ptr()
+        _lib.check(L.ccdm_launch_op(ctypes.byref(op), sp()))
+        torch.cuda.synchronize()
+        assert int(ctx.counter.item()) == 1  # the head advances the device step counter on both paths
+        assert int(lab_out.max()) < K
+        outs.append(lab_out.cpu())
+    mismatch = float((outs[0] != outs[1]).float().mean())
+    print("head fast/exact label mismatch K=%d: %.2e" % (K, mismatch))
+    assert mismatch < 1e-4, mismatch
+    # and the draw is a real draw: not the argmax of the posterior everywhere
+    assert float((outs[1] != logits.argmax(-1).cpu()).float().mean()) > 0.01
+
+
 # ---------------------------------------------------------------------------------------
 # attention (QKVAttentionLegacy) vs torch
 # ---------------------------------------------------------------------------------------
