@@ -19,6 +19,7 @@ with the reference) only.
 """
 import ctypes
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
 
@@ -92,6 +93,11 @@ def pack_conv_weight(w: torch.Tensor, cin_pad: Optional[int] = None) -> torch.Te
     out = torch.zeros(kh * kw, cip, _ceil(co, 32), dtype=torch.float32, device=w.device)
     out[:, :ci, :co] = w.float().permute(2, 3, 1, 0).reshape(kh * kw, ci, co)
     return out
+
+
+# A/B switch: identity residuals of the bf16 mode as an extra 1x1 MMA chunk with identity weights (default) or as a
+# read-and-add in the epilogue (CCDM_IDENT_SKIP=0)
+_IDENT_SKIP = os.environ.get("CCDM_IDENT_SKIP", "1") != "0"
 
 
 def pack_conv_weight_tc(w: torch.Tensor, nt: Optional[int] = None) -> torch.Tensor:
@@ -373,7 +379,7 @@ class Program:
                              _g=p + ":g2", _be=p + ":be2", _w=p + ":w2", _b=p + ":b2")
                     if Ly.skip_conv:
                         f.update(_skip=srcs, _ws=p + ":ws")
-                    elif self.exact == 0:
+                    elif self.exact == 0 and _IDENT_SKIP:
                         f.update(_skip=[srcs[0]], _ws="ident:%d" % Ly.cout)
                     else:
                         f.update(_res=srcs[0])
@@ -387,7 +393,7 @@ class Program:
                                _w=p + ":wqkv", _b=p + ":bqkv")
                     a = emit(_lib.OP_ATTENTION, [qkv], new(p + ":a", C, ch, cw, stat=False), Hin=ch, Win=cw, Hout=ch, Wout=cw,
                              Cout=C, heads=Ly.heads, head_dim=C // Ly.heads, _src=[qkv])
-                    fr = dict(_skip=[x], _ws="ident:%d" % C) if self.exact == 0 else dict(_res=x)
+                    fr = dict(_skip=[x], _ws="ident:%d" % C) if self.exact == 0 and _IDENT_SKIP else dict(_res=x)
                     h = emit(_lib.OP_CONV, [a, x], new(p, C, ch, cw), ksize=1, stride=1, gn=0, silu=0, Hin=ch, Win=cw, Hout=ch,
                              Wout=cw, Cout=C, _src=[a], _w=p + ":wproj", _b=p + ":bproj", **fr)
                     srcs = [h]

@@ -1,8 +1,13 @@
 mkdir -p gpurun_out
-timeout 60 python tools/tiny_chain.py bf16 128 8 > gpurun_out/s9b_tiny.log 2>&1 || { echo "tiny chain FAILED"; tail -5 gpurun_out/s9b_tiny.log; exit 1; }
-timeout 300 python -m pytest tests -m gpu -q -s -k "head_fast" 2>&1 | grep -i "mismatch\|passed\|failed\|error" | head
-timeout 300 python -m pytest tests -m gpu -q > gpurun_out/s9b_pytest.log 2>&1; tail -3 gpurun_out/s9b_pytest.log | cut -c1-300
-timeout 200 python bench.py --steps 2 --warmup 3 --T 40 --no-cpu-baseline --op-table gpurun_out/s9b_ops_lidc.txt > gpurun_out/s9b_lidc.json 2>&1
-grep -n "head\|32->2 " gpurun_out/s9b_ops_lidc.txt | head; tail -1 gpurun_out/s9b_ops_lidc.txt
-timeout 200 python bench.py --workload cityscapes --steps 2 --warmup 3 --T 20 --no-cpu-baseline --op-table gpurun_out/s9b_ops_cs.txt > gpurun_out/s9b_cs.json 2>&1
-grep -n "head\|32->20 " gpurun_out/s9b_ops_cs.txt; tail -1 gpurun_out/s9b_ops_cs.txt
+for M in 1 0 1 0; do
+CCDM_IDENT_SKIP=$M timeout 60 python tools/tiny_chain.py bf16 128 8 > gpurun_out/s9c_tiny.log 2>&1 || { echo "tiny chain FAILED"; tail -5 gpurun_out/s9c_tiny.log; exit 1; }
+CCDM_IDENT_SKIP=$M timeout 100 python bench.py --steps 2 --warmup 3 --T 40 --no-cpu-baseline --no-op-profile > gpurun_out/s9c_lidc_$M.json 2>&1
+CCDM_IDENT_SKIP=$M timeout 100 python bench.py --workload cityscapes --steps 2 --warmup 3 --T 20 --no-cpu-baseline --no-op-profile > gpurun_out/s9c_cs_$M.json 2>&1
+echo "IDENT_SKIP=$M"; python - <<PY
+import json
+for w in ("lidc","cs"):
+    try:
+        d=json.loads(open(f"gpurun_out/s9c_{w}_$M.json").read().strip().splitlines()[-1]); print(w, d["value"], d["ms_per_step"])
+    except Exception as e: print(w, "ERR", e)
+PY
+done
