@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libccdm_b200.so")
+# CCDM_B200_LIB: another build of the same library (A/B timing of two builds on one GPU box)
+LIB_PATH = os.environ.get("CCDM_B200_LIB") or os.path.join(_HERE, "libccdm_b200.so")
 
 # constants of include/ccdm_b200.h
 DT_F32, DT_BF16 = 0, 1

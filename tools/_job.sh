@@ -1,13 +1,15 @@
 mkdir -p gpurun_out
-for M in 1 0 1 0; do
-CCDM_IDENT_SKIP=$M timeout 60 python tools/tiny_chain.py bf16 128 8 > gpurun_out/s9c_tiny.log 2>&1 || { echo "tiny chain FAILED"; tail -5 gpurun_out/s9c_tiny.log; exit 1; }
-CCDM_IDENT_SKIP=$M timeout 100 python bench.py --steps 2 --warmup 3 --T 40 --no-cpu-baseline --no-op-profile > gpurun_out/s9c_lidc_$M.json 2>&1
-CCDM_IDENT_SKIP=$M timeout 100 python bench.py --workload cityscapes --steps 2 --warmup 3 --T 20 --no-cpu-baseline --no-op-profile > gpurun_out/s9c_cs_$M.json 2>&1
-echo "IDENT_SKIP=$M"; python - <<PY
+PREV=$PWD/ccdm-stochastic-segmentation_b200/ccdm_b200/libccdm_b200_prev.so
+timeout 60 python tools/tiny_chain.py bf16 128 8 > gpurun_out/s10c_tiny.log 2>&1 || { echo "tiny chain FAILED"; tail -5 gpurun_out/s10c_tiny.log; exit 1; }
+for V in prev new0 new1 prev new0 new1; do
+case $V in
+prev) export CCDM_B200_LIB=$PREV; export CCDM_STREAM=0;;
+new0) unset CCDM_B200_LIB; export CCDM_STREAM=0;;
+new1) unset CCDM_B200_LIB; export CCDM_STREAM=1;;
+esac
+timeout 100 python bench.py --steps 2 --warmup 3 --T 40 --no-cpu-baseline --no-op-profile > gpurun_out/s10c_lidc_$V.json 2>&1
+python - <<PY
 import json
-for w in ("lidc","cs"):
-    try:
-        d=json.loads(open(f"gpurun_out/s9c_{w}_$M.json").read().strip().splitlines()[-1]); print(w, d["value"], d["ms_per_step"])
-    except Exception as e: print(w, "ERR", e)
+d=json.loads(open("gpurun_out/s10c_lidc_$V.json").read().strip().splitlines()[-1]); print("$V", d["ms_per_step"])
 PY
 done
