@@ -325,15 +325,23 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
                         mbar_wait(raw_full + stage, phase);
                         if (pt == 0 && it == it_begin && kc == 0) trace(kTraceRaw0);
                         const uint32_t addr = sA32 + uint32_t(stage) * p.a_stage + (uint32_t(plane) * uint32_t(NQ) + uint32_t(q0)) * 16u;
+                        // (SiLU modes 2 and 3 are measured-and-rejected experiments: compiled only with -DCCDM_SILU_EXPERIMENTS,
+                        // they double the code of this role)
                         if (need_mask) {
+#ifdef CCDM_SILU_EXPERIMENTS
                             if (p.silu == 3) xf_pass<STEP, true, 3>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
                             else if (p.silu == 2) xf_pass<STEP, true, 2>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
-                            else if (p.silu) xf_pass<STEP, true, 1>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
+                            else
+#endif
+                            if (p.silu) xf_pass<STEP, true, 1>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
                             else xf_pass<STEP, true, 0>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
                         } else {
+#ifdef CCDM_SILU_EXPERIMENTS
                             if (p.silu == 3) xf_pass<STEP, false, 3>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
                             else if (p.silu == 2) xf_pass<STEP, false, 2>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
-                            else if (p.silu) xf_pass<STEP, false, 1>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
+                            else
+#endif
+                            if (p.silu) xf_pass<STEP, false, 1>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
                             else xf_pass<STEP, false, 0>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
                         }
                         fence_proxy_async();
@@ -734,7 +742,11 @@ int launch_conv_tma(const ccdm_op &op, cudaStream_t s) {
     p.H = op.upsample ? op.Hin : op.Hout; p.W = op.upsample ? op.Win : op.Wout;  // tile space (low resolution when upsampling)
     p.C0 = op.C0; p.C1 = op.C1; p.Cin = op.C0 + op.C1; p.Cout = op.Cout; p.CoutP = (op.Cout + 15) / 16 * 16;
     p.NT = c.NT; p.n_cc = c.n_cc;
+#ifdef CCDM_SILU_EXPERIMENTS
     static const int env_silu = getenv("CCDM_SILU_MODE") ? atoi(getenv("CCDM_SILU_MODE")) : 1;
+#else
+    static const int env_silu = 1;
+#endif
     p.upsample = op.upsample; p.nsub = op.upsample ? 4 : 1; p.gn = op.gn; p.silu = op.silu ? (env_silu == 2 || env_silu == 3 ? env_silu : 1) : 0; p.S0 = op.S0; p.S1 = op.S1;
     p.emb_off = op.emb_off; p.emb_cols = op.emb_cols; p.emb_bstride = op.emb_bstride;
     p.out_f32 = op.out_dtype == CCDM_DT_F32;
