@@ -155,7 +155,10 @@ __device__ __forceinline__ void gn_build_affine(const WsP &p, int b, float *sAff
 #define CCDM_EPI_TL(item, edge)
 #endif
 
-template <int NEW, int NSUB = 1>
+// LEAN: bf16 plane-major output without an epilogue residual (every conv of the bf16 chain but the output conv): the fp32
+// NHWC store variants and the residual read are compiled out -- the role's code is half of the kernel, and its size costs
+// (instruction fetch) even where it is not executed.
+template <int NEW, int NSUB = 1, bool LEAN = false>
 __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, float *sRed, int *s_last, uint64_t *acc_full,
                                                    uint64_t *acc_empty, uint32_t tmem_base, int it_begin, int it_end) {
     constexpr int NTHR = NEW * 32;
@@ -296,7 +299,7 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
                 if (valid) {
 #pragma unroll
                     for (int i = 0; i < CGW; ++i) v[i] += add[i];
-                    if (resb != nullptr) {  // identity residual read here (the engine's bf16 path folds it into the MMA instead)
+                    if (!LEAN && resb != nullptr) {  // identity residual read here (the engine's bf16 path folds it into the MMA instead)
 #pragma unroll
                         for (int h2 = 0; h2 < CGW / 8; ++h2) {
                             const uint4 rr = ldg_nc16(resb + (size_t(h2) * hw + off) * 8);
@@ -309,7 +312,7 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
                             }
                         }
                     }
-                    if (p.out_f32) {  // fp32 logits stay NHWC: Cout floats per pixel, written with the widest aligned store
+                    if (!LEAN && p.out_f32) {  // fp32 logits stay NHWC: Cout floats per pixel, written with the widest aligned store
                         float *op = outf + size_t(off) * p.Cout;
                         if ((p.Cout & 3) == 0) {  // K = 20: a pixel's row is 16-byte aligned
 #pragma unroll

@@ -195,7 +195,7 @@ __device__ void conv_tma_tl_hook(int item, int edge) { tl(3, item, edge); }
 // PL = planes (8-channel groups) per K chunk: KC = 8*PL channels per pipeline stage.
 // UP: the fused nearest-x2 + conv3x3 variant (16 pre-summed sub-pixel taps, 4 accumulator sets per M block); a separate
 // instantiation so that the common kernel's code and register allocation are untouched by it.
-template <int PL, bool UP>
+template <int PL, bool UP, bool LEAN>
 __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_constant__ TmP P_) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const WsP &p = P_.w;
@@ -241,10 +241,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
-    if (tid == 0 && (smem_u32(sA) & 127u)) {
-        printf("conv_tma: dynamic shared memory is not 128-byte aligned\n");
-        __trap();
-    }
+    if (tid == 0 && (smem_u32(sA) & 127u)) __trap();  // dynamic shared memory must be 128-byte aligned for the TMA boxes
 
     const int it_begin = int((long long)blockIdx.x * p.n_items / gridDim.x);
     const int it_end = int((long long)(blockIdx.x + 1) * p.n_items / gridDim.x);
@@ -269,7 +266,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
     // per LIDC step -- the roles are limited by shared-memory bandwidth and issue slots, not by warp count.)
     if (warp < TM_EPI_WARPS) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
-        conv_epilogue_role<TM_EPI_WARPS, UP ? 4 : 1>(p, sAdd, sRed, s_last, acc_full, acc_empty, tmem_base, it_begin, it_end);
+        conv_epilogue_role<TM_EPI_WARPS, UP ? 4 : 1, LEAN>(p, sAdd, sRed, s_last, acc_full, acc_empty, tmem_base, it_begin, it_end);
     } else if (warp < WARP_MMA0) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
         // =========================== in-place GroupNorm + SiLU ======================================
@@ -787,14 +784,18 @@ int launch_conv_tma(const ccdm_op &op, cudaStream_t s) {
 
     static bool attr_done = false;
     if (!attr_done) {
-        CCDM_CUDA(cudaFuncSetAttribute(conv_tma_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTmSmemBudget)));
-        CCDM_CUDA(cudaFuncSetAttribute(conv_tma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTmSmemBudget)));
-        CCDM_CUDA(cudaFuncSetAttribute(conv_tma_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTmSmemBudget)));
-        CCDM_CUDA(cudaFuncSetAttribute(conv_tma_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTmSmemBudget)));
+        CCDM_CUDA(cudaFuncSetAttribute(conv_tma_kernel<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTmSmemBudget)));
+        CCDM_CUDA(cudaFuncSetAttribute(conv_tma_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTmSmemBudget)));
+        CCDM_CUDA(cudaFuncSetAttribute(conv_tma_kernel<4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTmSmemBudget)));
+        CCDM_CUDA(cudaFuncSetAttribute(conv_tma_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTmSmemBudget)));
+        CCDM_CUDA(cudaFuncSetAttribute(conv_tma_kernel<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTmSmemBudget)));
+        CCDM_CUDA(cudaFuncSetAttribute(conv_tma_kernel<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTmSmemBudget)));
         attr_done = true;
     }
-    auto kern = op.upsample ? (c.PL == 4 ? conv_tma_kernel<4, true> : conv_tma_kernel<2, true>)
-                            : (c.PL == 4 ? conv_tma_kernel<4, false> : conv_tma_kernel<2, false>);
+    const bool lean = op.out_dtype == CCDM_DT_BF16 && !op.res;  // no fp32 store, no epilogue residual: the lean epilogue
+    auto kern = op.upsample ? (c.PL == 4 ? conv_tma_kernel<4, true, true> : conv_tma_kernel<2, true, true>)
+                : lean      ? (c.PL == 4 ? conv_tma_kernel<4, false, true> : conv_tma_kernel<2, false, true>)
+                            : (c.PL == 4 ? conv_tma_kernel<4, false, false> : conv_tma_kernel<2, false, false>);
     CCDM_CUDA(launch_pdl(kern, dim3(c.grid), dim3(TM_THREADS), c.smem, s, P));
     CCDM_LAUNCH_CHECK("conv_tma_kernel");
     return 0;

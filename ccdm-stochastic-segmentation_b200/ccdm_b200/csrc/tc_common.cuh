@@ -42,10 +42,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         if ((++spins & 63u) == 0u) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000ll) {
-                printf("ccdm: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, addr, parity);
-                __trap();
-            }
+            else if (now - t0 > 4000000000ll) __trap();  // no printf here: its argument block and code would sit in every inlined wait
         }
     }
 }
