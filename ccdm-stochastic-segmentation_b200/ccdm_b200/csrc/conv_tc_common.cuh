@@ -173,6 +173,7 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
     const int CoutP = p.CoutP;
     const bool want_stats = p.part != nullptr;  // with ostat: folded here (ticket); without: deferred to the consumer
     if (want_stats) {
+#pragma unroll 1
         for (int e = lane; e < CoutP * 2; e += 32) sAcc[warp * CoutP * 2 + e] = 0.f;
         __syncwarp();
     }
@@ -180,6 +181,7 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
         named_bar_sync(2, NTHR);
         const int c_first = int((((long long)b * p.ips + 1) * gridDim.x - 1) / p.n_items);
         const int slot = int(blockIdx.x) - c_first;
+#pragma unroll 1
         for (int e = tid; e < CoutP * 2; e += NTHR) {
             float s = 0.f;
 #pragma unroll
@@ -207,9 +209,11 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
             __threadfence();
             const int c_last = int(((long long)(b + 1) * p.ips * gridDim.x - 1) / p.n_items);
             const int n_slots = c_last - c_first + 1;
+#pragma unroll 1
             for (int e = tid; e < p.Cout * 2; e += NTHR) {
                 const float *pp = p.part + size_t(b) * p.slots * CoutP * 2 + e;
                 double s = 0.0;
+#pragma unroll 2
                 for (int t = 0; t < n_slots; ++t) s += double(__ldcg(pp + size_t(t) * CoutP * 2));
                 p.ostat[size_t(b) * p.Cout * 2 + e] = s;
             }
@@ -231,12 +235,17 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
     const int n_cg = NT / CGW;
 
     int acc_it = 0, cur_b = -1, cur_cc = -1, n_pending = 0;
-    for (int it = it_begin; it < it_end; ++it, ++acc_it) {
-        const Item I = decode_item(p, it);
-        if (I.b != cur_b && n_pending > 0) {
+    // (one trip past the end: the last sample's statistics are flushed by the same call site as the others -- the
+    // flush is ~500 instructions, and this role's code size is what every launch pays for at its start)
+    for (int it = it_begin; it <= it_end; ++it, ++acc_it) {
+        const bool past_end = it == it_end;
+        Item I;
+        if (!past_end) I = decode_item(p, it);
+        if ((past_end || I.b != cur_b) && n_pending > 0) {
             if (want_stats) flush_stats(cur_b, n_pending);
             n_pending = 0;
         }
+        if (past_end) break;
         if (I.b != cur_b || I.cc != cur_cc) {
             named_bar_sync(2, NTHR);
             for (int c = tid; c < NT; c += NTHR) {
@@ -381,7 +390,6 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
         if (tid == 0) CCDM_EPI_TL(it - it_begin, 1);
         ++n_pending;
     }
-    if (want_stats && n_pending > 0) flush_stats(cur_b, n_pending);
     if (tid == 0) CCDM_EPI_TRACE(7);
 }
 
