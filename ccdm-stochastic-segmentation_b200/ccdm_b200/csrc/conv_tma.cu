@@ -195,7 +195,9 @@ __device__ void conv_tma_tl_hook(int item, int edge) { tl(3, item, edge); }
 // PL = planes (8-channel groups) per K chunk: KC = 8*PL channels per pipeline stage.
 // UP: the fused nearest-x2 + conv3x3 variant (16 pre-summed sub-pixel taps, 4 accumulator sets per M block); a separate
 // instantiation so that the common kernel's code and register allocation are untouched by it.
-template <int PL, bool UP, bool LEAN>
+// XF: which in-place transform the kernel carries -- 0 none (convs without GroupNorm/SiLU: the role idles), 1 GroupNorm +
+// SiLU, 2 GroupNorm only (q/k/v convs), 3 both (selected at run time).  Separate instantiations keep each kernel small.
+template <int PL, bool UP, bool LEAN, int XF>
 __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_constant__ TmP P_) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const WsP &p = P_.w;
@@ -272,7 +274,8 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
         // =========================== in-place GroupNorm + SiLU ======================================
         // Warp xw owns plane (xw % PL) of every transformed stage, so its 8 scale/shift pairs are warp
         // uniform and live in registers; the XF_WARPS/PL warps of a plane interleave blocks of 32 positions.
-        if (p.xf) {
+        if (XF != 0 && p.xf) {
+            constexpr bool kSilu = XF == 1 || XF == 3, kPlain = XF == 2 || XF == 3;
             const int xw = warp - WARP_XF0, pt = tid - WARP_XF0 * 32;
             const int plane = xw & (PL - 1), sub = xw / PL;
             constexpr int NSUB = XF_WARPS / PL;
@@ -330,16 +333,16 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
                             else if (p.silu == 2) xf_pass<STEP, true, 2>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
                             else
 #endif
-                            if (p.silu) xf_pass<STEP, true, 1>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
-                            else xf_pass<STEP, true, 0>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
+                            if (kSilu && (!kPlain || p.silu)) xf_pass<STEP, true, 1>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
+                            else if (kPlain) xf_pass<STEP, true, 0>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
                         } else {
 #ifdef CCDM_SILU_EXPERIMENTS
                             if (p.silu == 3) xf_pass<STEP, false, 3>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
                             else if (p.silu == 2) xf_pass<STEP, false, 2>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
                             else
 #endif
-                            if (p.silu) xf_pass<STEP, false, 1>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
-                            else xf_pass<STEP, false, 0>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
+                            if (kSilu && (!kPlain || p.silu)) xf_pass<STEP, false, 1>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
+                            else if (kPlain) xf_pass<STEP, false, 0>(addr, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
                         }
                         fence_proxy_async();
                         __syncwarp();
@@ -784,18 +787,23 @@ int launch_conv_tma(const ccdm_op &op, cudaStream_t s) {
 
     static bool attr_done = false;
     if (!attr_done) {
-        CCDM_CUDA(cudaFuncSetAttribute(conv_tma_kernel<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTmSmemBudget)));
-        CCDM_CUDA(cudaFuncSetAttribute(conv_tma_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTmSmemBudget)));
-        CCDM_CUDA(cudaFuncSetAttribute(conv_tma_kernel<4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTmSmemBudget)));
-        CCDM_CUDA(cudaFuncSetAttribute(conv_tma_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTmSmemBudget)));
-        CCDM_CUDA(cudaFuncSetAttribute(conv_tma_kernel<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTmSmemBudget)));
-        CCDM_CUDA(cudaFuncSetAttribute(conv_tma_kernel<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTmSmemBudget)));
+        auto opt_in = [](auto kernel) { return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTmSmemBudget)); };
+        CCDM_CUDA(opt_in(conv_tma_kernel<4, false, true, 0>)); CCDM_CUDA(opt_in(conv_tma_kernel<2, false, true, 0>));
+        CCDM_CUDA(opt_in(conv_tma_kernel<4, false, true, 1>)); CCDM_CUDA(opt_in(conv_tma_kernel<2, false, true, 1>));
+        CCDM_CUDA(opt_in(conv_tma_kernel<4, false, true, 2>)); CCDM_CUDA(opt_in(conv_tma_kernel<2, false, true, 2>));
+        CCDM_CUDA(opt_in(conv_tma_kernel<4, false, false, 3>)); CCDM_CUDA(opt_in(conv_tma_kernel<2, false, false, 3>));
+        CCDM_CUDA(opt_in(conv_tma_kernel<4, true, true, 0>)); CCDM_CUDA(opt_in(conv_tma_kernel<2, true, true, 0>));
         attr_done = true;
     }
     const bool lean = op.out_dtype == CCDM_DT_BF16 && !op.res;  // no fp32 store, no epilogue residual: the lean epilogue
-    auto kern = op.upsample ? (c.PL == 4 ? conv_tma_kernel<4, true, true> : conv_tma_kernel<2, true, true>)
-                : lean      ? (c.PL == 4 ? conv_tma_kernel<4, false, true> : conv_tma_kernel<2, false, true>)
-                            : (c.PL == 4 ? conv_tma_kernel<4, false, false> : conv_tma_kernel<2, false, false>);
+    const int xf_kind = !(op.gn || op.silu) ? 0 : (op.silu ? 1 : 2);
+    const bool pl4 = c.PL == 4;
+    void (*kern)(TmP) = nullptr;
+    if (op.upsample) kern = pl4 ? conv_tma_kernel<4, true, true, 0> : conv_tma_kernel<2, true, true, 0>;
+    else if (!lean) kern = pl4 ? conv_tma_kernel<4, false, false, 3> : conv_tma_kernel<2, false, false, 3>;
+    else if (xf_kind == 0) kern = pl4 ? conv_tma_kernel<4, false, true, 0> : conv_tma_kernel<2, false, true, 0>;
+    else if (xf_kind == 1) kern = pl4 ? conv_tma_kernel<4, false, true, 1> : conv_tma_kernel<2, false, true, 1>;
+    else kern = pl4 ? conv_tma_kernel<4, false, true, 2> : conv_tma_kernel<2, false, true, 2>;
     CCDM_CUDA(launch_pdl(kern, dim3(c.grid), dim3(TM_THREADS), c.smem, s, P));
     CCDM_LAUNCH_CHECK("conv_tma_kernel");
     return 0;
