@@ -60,7 +60,7 @@ struct AtP {
 };
 
 template <int NK>
-__global__ void __launch_bounds__(AT_QT) attention_tc_kernel(const AtP p) {
+__global__ void __launch_bounds__(AT_QT, 3) attention_tc_kernel(const AtP p) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr uint32_t Q_BYTES = AT_PLANES * AT_QT * 16;  // 8 KB
     constexpr uint32_t KV_BYTES = AT_PLANES * NK * 16;    // per tensor per buffer
