@@ -1,13 +1,7 @@
+TAG=r01g
 mkdir -p gpurun_out
-PREV=$PWD/ccdm-stochastic-segmentation_b200/ccdm_b200/libccdm_b200_prev.so
-timeout 60 python tools/tiny_chain.py bf16 128 8 > gpurun_out/s12a_tiny.log 2>&1 || { echo "tiny chain FAILED"; tail -5 gpurun_out/s12a_tiny.log; exit 1; }
-timeout 200 python -m pytest tests -m gpu -q -x -k "attention" > gpurun_out/s12a_pytest.log 2>&1; tail -1 gpurun_out/s12a_pytest.log | cut -c1-200
-for V in prev new; do
-case $V in
-prev) export CCDM_B200_LIB=$PREV;;
-new) unset CCDM_B200_LIB;;
-esac
-timeout 100 python bench.py --steps 2 --warmup 3 --T 40 --no-cpu-baseline --op-table gpurun_out/s12a_ops_lidc_$V.txt > gpurun_out/s12a_lidc_$V.json 2>&1
-timeout 100 python bench.py --workload cityscapes --steps 2 --warmup 3 --T 20 --no-cpu-baseline --op-table gpurun_out/s12a_ops_cs_$V.txt > gpurun_out/s12a_cs_$V.json 2>&1
-echo $V; grep -h "attention" gpurun_out/s12a_ops_lidc_$V.txt gpurun_out/s12a_ops_cs_$V.txt | cut -c1-60; tail -1 gpurun_out/s12a_ops_lidc_$V.txt; tail -1 gpurun_out/s12a_ops_cs_$V.txt
-done
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest.log
+tail -3 gpurun_out/${TAG}_pytest.log
+timeout 600 python bench.py --op-table gpurun_out/${TAG}_ops_lidc.txt > gpurun_out/${TAG}_bench_lidc.json 2> gpurun_out/${TAG}_bench_lidc.err; tail -c 600 gpurun_out/${TAG}_bench_lidc.json; tail -3 gpurun_out/${TAG}_bench_lidc.err
+timeout 900 python bench.py --workload cityscapes --steps 2 --warmup 3 --cpu-budget 10 --op-table gpurun_out/${TAG}_ops_cs.txt > gpurun_out/${TAG}_bench_cs.json 2> gpurun_out/${TAG}_bench_cs.err; tail -c 600 gpurun_out/${TAG}_bench_cs.json; tail -3 gpurun_out/${TAG}_bench_cs.err
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
