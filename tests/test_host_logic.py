@@ -195,6 +195,32 @@ def test_weight_packing_layout():
     assert cols == sum(l.cout for b in m.unet.arch.blocks for l in b.layers if l.kind == "res")
 
 
+def test_tensor_core_weight_packing_and_n_tile_rule():
+    """[cc][Cin/8][tap][NT][8] packing of the tcgen05 kernels: NT is a function of Cout only (one packed tensor serves
+    every shape), <= 64 up to 128 output channels, <= 192 for the wider q/k/v layers; every weight lands where the
+    kernel's B-operand descriptor reads it."""
+    from ccdm_b200 import _lib
+    from ccdm_b200.engine import pack_conv_weight_tc
+    L = _lib.lib()
+    want = {2: 16, 20: 32, 32: 32, 64: 64, 96: 48, 128: 64, 192: 192, 288: 144, 384: 192, 160: 160, 224: 112}
+    for cout, nt in want.items():
+        got = int(L.ccdm_conv_tc_nt(cout))
+        cop = (cout + 15) // 16 * 16
+        assert got == nt and cop % got == 0 and got % 16 == 0 and got <= 192, (cout, got)
+    g = torch.Generator().manual_seed(5)
+    for (co, ci, k) in [(384, 128, 1), (96, 32, 3), (20, 32, 3)]:
+        w = torch.randn(co, ci, k, k, generator=g)
+        pk = pack_conv_weight_tc(w)
+        nt = int(L.ccdm_conv_tc_nt(co))
+        cop = (co + 15) // 16 * 16
+        assert pk.dtype == torch.bfloat16 and pk.shape == (cop // nt, ci // 8, k * k, nt, 8)
+        wb = w.to(torch.bfloat16)
+        for (o, c, t) in [(0, 0, 0), (co - 1, ci - 1, k * k - 1), (co // 2, 9 % ci, (k * k) // 2)]:
+            assert pk[o // nt, c // 8, t, o % nt, c % 8] == wb[o, c, t // k, t % k]
+        if cop > co:  # padded output channels are zero rows of the B operand
+            assert float(pk.float().reshape(cop // nt, ci // 8, k * k, nt, 8)[-1, :, :, co % nt:, :].abs().sum()) == 0.0
+
+
 @pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present (GPU box)")
 def test_live_reference_agrees_with_oracle_on_fresh_seed():
     """Beyond the committed fixtures: a different seed / shape, reference imported live."""
