@@ -143,6 +143,28 @@ class DenoisingModel(nn.Module):
             return self.forward_denoising(x, condition, feature_condition, label_ref_logits=label_ref_logits)
         return self.forward_denoising(x, condition, feature_condition, int(t.item()), label_ref_logits)  # :159
 
+    # Philox draw index of the chain's initial state; the reverse steps use 0, 1, 2, ...
+    X_T_DRAW = 0xFFFFFFFF
+
+    @torch.no_grad()
+    def draw_x_T(self, batch: int, height: int, width: int, device=None) -> Tensor:
+        """x_T drawn ON THE DEVICE: a uniform label per pixel, uint8 ``[batch, height, width]``, accepted as ``x`` by
+        ``forward``.  The reference builds it on the host as
+        ``OneHotCategoricalBCHW(logits=zeros(B, K, H, W)).sample()`` -- an exponential race over equal probabilities
+        (evaluate_lidc_uncertainty.py:100, eval_cdm.py:162-163) -- and copies B*K*H*W floats to the GPU.  Here the same
+        race runs in one kernel on Philox noise keyed by (``seed``, ``sample_offset`` + b, ``X_T_DRAW``, pixel): one
+        byte per pixel, no host copy, and independent of how the batch is sharded over ranks."""
+        L = _lib.lib()
+        dev = torch.device(device) if device is not None else next(self.unet.parameters()).device
+        if dev.type != "cuda":
+            raise _lib.CcdmError("draw_x_T needs the model on a CUDA device")
+        K = self.diffusion.num_classes
+        labels = torch.empty((batch, height, width), dtype=torch.uint8, device=dev)
+        sp = _lib.stream_ptr(torch.cuda.current_stream(dev))
+        _lib.check(L.ccdm_uniform_labels(int(self.seed), self.X_T_DRAW, int(self.sample_offset), batch, height * width, K,
+                                         labels.data_ptr(), sp), "uniform_labels")
+        return labels
+
     def forward_step(self, x: Tensor, condition: Tensor, feature_condition: Tensor, t: Tensor) -> dict:
         """One denoiser evaluation (:161-162).  Inference only: no autograd graph is built."""
         self.unet.precision = self.precision

@@ -249,6 +249,34 @@ def test_sub_batch_lanes_do_not_change_the_result(cuda_device):
             assert agree >= 0.995, agree
 
 
+def test_x_T_drawn_on_device_and_label_input(cuda_device):
+    """DenoisingModel.draw_x_T: uniform uint8 labels from the device-side race, keyed by the global sample
+    index; forward() takes them as they are and gives the result of the one-hot float input the reference passes."""
+    tag = "lidc64"
+    T, _, C_img, H, W, K, fce, mult, t_probe, steps = GOLDEN_CASES[tag]
+    from ccdm_b200.synthetic import synthetic_inputs
+    image, _, _ = synthetic_inputs(4, C_img, H, W, K)
+    m = build_ours(T, C_img, H, W, K, "majority").cuda()
+    m.noise, m.seed = "philox", 11
+    xt = m.draw_x_T(4, H, W)
+    assert xt.dtype == torch.uint8 and tuple(xt.shape) == (4, H, W) and int(xt.max()) < K
+    frac = float((xt == 1).float().mean())
+    assert 0.47 < frac < 0.53, frac                      # K = 2: a fair coin per pixel
+    assert not torch.equal(xt[0], xt[1])                 # samples differ
+    m.sample_offset = 2                                  # rank 1 of 2 draws ITS samples of the same batch
+    assert torch.equal(m.draw_x_T(2, H, W), xt[2:4])
+    m.sample_offset = 0
+    m.seed = 12
+    assert not torch.equal(m.draw_x_T(4, H, W), xt)      # and the seed matters
+    m.seed = 11
+    tt = torch.as_tensor(10000 + 3)
+    a = m(xt, image.cuda(), None, t=tt)["diffusion_out"]
+    b = m(_onehot(xt.cpu(), K).cuda(), image.cuda(), None, t=tt)["diffusion_out"]
+    assert a.dtype == torch.int64 and torch.equal(a, b)
+    with pytest.raises(Exception):
+        build_ours(T, C_img, H, W, K, "majority").draw_x_T(1, H, W)  # model on the CPU: loud
+
+
 def test_graph_replay_equals_eager_launches(cuda_device):
     tag = "lidc64"
     T, B, C_img, H, W, K, fce, mult, t_probe, steps = GOLDEN_CASES[tag]
