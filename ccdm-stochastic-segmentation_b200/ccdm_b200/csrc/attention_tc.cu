@@ -19,7 +19,13 @@
 //
 // (Measured and rejected: software-pipelining S(t+1) under softmax(t) with a double-buffered S accumulator --
 // T=256 22.9 vs 15.0 us, T=2048 75.9 vs 66 us.  The kernel is not waiting for the tensor core; with 128 threads per
-// CTA and two CTAs per SM it is short of warps for the softmax arithmetic.  Next: two threads per query row.)
+// CTA and two CTAs per SM it is short of warps for the softmax arithmetic.
+// Also measured and rejected: two threads per query row (256 threads; the warps w and w+4 of a TMEM lane quarter split the
+// key columns and the output channels, one extra CTA barrier per key tile to agree on the running maximum) -- correct,
+// but T=2048 55.7 vs 54.4 us, T=512 14.6 vs 15.7, T=256 19.7 vs 14.7: the barrier costs what the halved per-thread work
+// saves.  What bounds a CTA is the chain of round trips per key tile (MMA commit -> mbarrier -> tcgen05.ld -> barrier ->
+// MMA commit -> ...), so the next step is more independent work per SM: split the key range over two CTAs when
+// B x heads x query tiles < 2 x 148 (Cityscapes B=8), or a second query tile per CTA.)
 #include <stdlib.h>
 
 #include "tc_common.cuh"
