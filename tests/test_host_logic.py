@@ -93,6 +93,9 @@ def test_forward_dispatch_errors_without_gpu():
         from ccdm_b200 import _lib
         with pytest.raises(_lib.CcdmError):  # no CPU fallback
             m(x, torch.zeros(1, 1, 64, 64), None)
+    from ccdm_b200 import _lib
+    with pytest.raises(_lib.CcdmError):  # the device-side x_T draw needs the model on a GPU, too
+        m.draw_x_T(1, 64, 64)
 
 
 def test_onehot_categorical_matches_torch_distributions():
