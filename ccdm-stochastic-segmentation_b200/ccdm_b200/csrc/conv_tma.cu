@@ -546,6 +546,10 @@ bool tm_configure(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout,
     // a 32-channel input would be ONE K chunk per item at PL = 4: two chunks of 16 let the TMA, the transform and
     // the MMAs of one item overlap (measured 73.7 -> 63.5 us on 32->32 @128x128, B = 64)
     if (env_pl == 0 && Cin == 32 && W >= 64) c.PL = 2;
+    // wider inputs on the mid-size levels (B*H*W <= 512k pixels, e.g. 64x64 at B = 64 or 128x256 at B = 8) also prefer
+    // chunks of 16 channels: smaller stages allow taller tiles (less halo) -- measured 33.0 -> 27.6 us (64->32 @128x256, B = 8),
+    // 43.4 -> 39.7 us (96->32 @64x64, B = 64); on the full-resolution level it is 1-5 % slower, so not there
+    if (env_pl == 0 && W >= 64 && (long long)B * H * W <= 524288) c.PL = 2;
     const int KC = 8 * c.PL;
     c.n_main = Cin / KC;
     c.n_skip = Sk / KC;
