@@ -224,6 +224,33 @@ def test_tensor_core_weight_packing_and_n_tile_rule():
             assert float(pk.float().reshape(cop // nt, ci // 8, k * k, nt, 8)[-1, :, :, co % nt:, :].abs().sum()) == 0.0
 
 
+def test_tensor_core_conv_configuration_rules():
+    """Host-side tile / pipeline choices of the TMA-fed tcgen05 conv kernel (no GPU needed): K chunks of 16 channels on
+    32-channel inputs and on the mid-size levels, 32 elsewhere; persistent grid of at most one CTA per SM; the whole
+    configuration fits the 227 KB of shared memory and the 512 TMEM columns."""
+    import ctypes
+    from ccdm_b200 import _lib
+    L = _lib.lib()
+
+    def cfg(B, H, W, C0, C1, Cout, k=3, S0=0, S1=0):
+        op = _lib.Op(kind=_lib.OP_CONV, dtype=_lib.DT_BF16, out_dtype=_lib.DT_BF16, B=B, Hin=H, Win=W, Hout=H, Wout=W, C0=C0, C1=C1,
+                     Cout=Cout, ksize=k, stride=1, S0=S0, S1=S1, gn=1, silu=1)
+        out = (ctypes.c_int32 * 16)()
+        assert L.ccdm_conv_tc_config(ctypes.byref(op), out) == 0 and L.ccdm_conv_uses_tma(ctypes.byref(op)) == 1
+        names = ["PL", "R", "Wt", "MB", "NQ", "NT", "n_cc", "NS", "resident", "acc2", "tmem", "tiles", "items", "grid", "smem", "chunks"]
+        return dict(zip(names, out))
+
+    full = cfg(64, 128, 128, 32, 32, 32)          # LIDC out12-14: concat 64 -> 32 at full resolution
+    assert full["PL"] == 4 and full["chunks"] == 2
+    assert cfg(64, 128, 128, 32, 0, 32)["PL"] == 2  # 32-channel input: two chunks of 16 so the roles of one item overlap
+    mid = cfg(8, 128, 256, 32, 32, 32)              # Cityscapes 128x256 at B = 8: mid-size level -> chunks of 16
+    assert mid["PL"] == 2 and mid["chunks"] == 4 and mid["R"] > cfg(8, 256, 512, 32, 32, 32)["R"]
+    for c in (full, mid, cfg(64, 8, 8, 128, 0, 128, S0=128), cfg(64, 8, 8, 128, 0, 384, k=1), cfg(8, 32, 64, 64, 384, 64)):
+        assert 1 <= c["grid"] <= 148 and c["items"] >= c["grid"]
+        assert c["smem"] <= 227 * 1024 and c["tmem"] in (32, 64, 128, 256, 512)
+        assert c["MB"] * c["NT"] * (2 if c["acc2"] else 1) <= 512 and c["NS"] >= 2
+
+
 @pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present (GPU box)")
 def test_live_reference_agrees_with_oracle_on_fresh_seed():
     """Beyond the committed fixtures: a different seed / shape, reference imported live."""
