@@ -130,3 +130,33 @@ def test_chain_restatement_matches_reference(tag):
     _, probs = chain_ref.reverse_chain(sd, labels.numpy(), image, feat, al, ca, T, 10000 + steps, "confidence",
                                        feature_condition_idx=10 if fce else None, K=K)
     np.testing.assert_allclose(probs, g["chain_confidence_probs"], rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("K", [2, 20])
+def test_fast_sampling_algebra_agrees_with_exact_path(K):
+    """The algebra of the bf16 engine mode's sampling step (head.cu: head_sample_fast) restated in numpy fp32 -- softmax and
+    1/z folded into two weights, clamp(1e-12) at the true scale, NO final normalisation, race score post / E -- draws the
+    labels of the exact path (oracle softmax -> posterior_closed -> draw) on the same Philox noise, up to near-ties."""
+    rng = np.random.default_rng(7 + K)
+    n = 40000
+    logits = (rng.standard_normal((n, K)) * 3).astype(np.float32)
+    lab = rng.integers(0, K, n).astype(np.uint8)
+    alpha, cum = np.float32(0.97), np.float32(0.61)
+    e = cdm.bits_to_exponential(cdm.philox_bits(1234, 5, 0, 1, n, K)).reshape(n, K)
+    want, _ = cdm.draw(cdm.posterior_closed(lab, cdm.softmax(logits), alpha, cum), e, 0)
+    # fast path
+    f = np.float32
+    m = logits.max(-1, keepdims=True)
+    v = np.exp2((logits - m) * f(1.4426950408889634)).astype(f)
+    s = v.sum(-1, keepdims=True, dtype=f)
+    ua, u = (f(1) - alpha) / f(K), (f(1) - cum) / f(K)
+    a_hit, a_miss = alpha + ua, ua
+    hit = np.arange(K)[None, :] == lab[:, None]
+    w = np.where(hit, f(1) / (cum * a_hit + u), f(1) / (cum * a_miss + u)).astype(f) / s
+    r = (v * w).astype(f)
+    S = r.sum(-1, keepdims=True, dtype=f)
+    post = np.maximum(np.where(hit, a_hit, a_miss).astype(f) * (cum * r + u * S), f(1e-12))
+    got = (post / e).argmax(-1).astype(np.uint8)
+    mismatch = float((got != want.reshape(-1)).mean())
+    assert mismatch < 1e-4, mismatch
+    assert float((got != logits.argmax(-1)).mean()) > 0.01  # a real draw, not the mode
