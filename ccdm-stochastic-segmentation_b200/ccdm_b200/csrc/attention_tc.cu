@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(AT_QT, 3) attention_tc_kernel(const AtP p) {
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 4);
     constexpr uint32_t TMEM_COLS = NK + 32 <= 64 ? 64 : (NK + 32 <= 128 ? 128 : 256);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const int qt = blockIdx.x % p.q_tiles, bh = blockIdx.x / p.q_tiles;
     const int h = bh % p.heads, b = bh / p.heads;
     const int T = p.T, q0 = qt * AT_QT;
