@@ -172,7 +172,7 @@ def op_bytes(o, esize):
     if o.kind == _lib.OP_INPUT_CONV:
         return B * (o.Hin * o.Win * (1 + 4 * o.C_img) + o.Hout * o.Wout * o.Cout * esize)
     if o.kind == _lib.OP_CONV:
-        n = o.Hin * o.Win * (o.C0 + o.C1) * esize + o.Hout * o.Wout * o.Cout * (4 if o.out_dtype == _lib.DT_F32 else 2)
+        n = o.Hin * o.Win * (o.C0 + o.C1) * esize + o.Hout * o.Wout * o.Cout * (4 if o.out_dtype == _lib.DT_F32 else esize)
         n += o.Hout * o.Wout * (o.S0 + o.S1) * esize
         if o.res:
             n += o.Hout * o.Wout * o.Cout * esize
@@ -372,7 +372,7 @@ def run_gpu_arm(args, wl):
         line = {
             "metric": "seg samples/sec (full T-step chain)", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "vs_baseline": None, "dtype": {"fp32": "f32", "exact": "f16x2 (fp16 hi+lo operands, fp32 accumulate)", "bf16": "bf16"}[args.precision], "data": "synthetic",
             "config": {"workload": wl["name"], "batch_per_gpu": B, "T": T, "precision": args.precision,
                        "noise": "philox (in-kernel)", "parallelism": f"sample-sharded x{world}, 1 NCCL all-gather of labels",
                        "l2_policy": "per-step activation traffic exceeds L2 (126 MB): inputs larger than L2, no flush",
@@ -402,7 +402,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="lidc", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default=os.environ.get("CCDM_PRECISION", "bf16"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("CCDM_PRECISION", "bf16"), choices=["fp32", "exact", "bf16"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (parity/debug runs)")
     ap.add_argument("--T", type=int, default=0, help="override the chain length (debug runs; invalid as a bench number)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)

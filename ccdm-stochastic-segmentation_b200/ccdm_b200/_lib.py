@@ -11,11 +11,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CCDM_B200_LIB") or os.path.join(_HERE, "libccdm_b200.so")
 
 # constants of include/ccdm_b200.h
-DT_F32, DT_BF16 = 0, 1
+DT_F32, DT_BF16, DT_F16X2 = 0, 1, 2
+F16X2_SCALE_LOG2 = 4
 DRAW_SAMPLE, DRAW_MAJORITY, DRAW_CONFIDENCE, DRAW_X0, DRAW_POSTERIOR = 0, 1, 2, 3, 4
 NOISE_TENSOR, NOISE_PHILOX = 0, 1
 OP_INPUT_CONV, OP_CONV, OP_ATTENTION, OP_HEAD, OP_ENCODE_INPUT = 1, 2, 3, 4, 5
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class StepEntry(ctypes.Structure):
@@ -26,7 +27,7 @@ class StepEntry(ctypes.Structure):
 
 _I32 = ["kind", "dtype", "B", "Hin", "Win", "Hout", "Wout", "C0", "C1", "Cout", "ksize", "stride", "upsample", "gn", "silu",
         "S0", "S1", "heads", "head_dim", "K", "C_img", "emb_off", "emb_cols", "emb_bstride", "noise_mode", "sample0",
-        "out_dtype", "src_kind", "exact", "reserved0", "reserved1", "st_slots0", "st_slots1", "st_ips0", "st_ips1", "st_items0", "st_items1",
+        "out_dtype", "src_kind", "exact", "acc_shift", "reserved", "st_slots0", "st_slots1", "st_ips0", "st_ips1", "st_items0", "st_items1",
         "st_grid0", "st_grid1", "st_rows0", "st_rows1", "pad_align"]
 _U64 = ["seed", "src0", "src1", "stat0", "stat1", "gamma", "beta", "weight", "bias", "emb", "skip0", "skip1", "skip_w", "res",
         "out", "ostat", "part", "ticket", "labels_in", "labels_out", "image", "noise", "probs_out", "noise_out", "steps",
@@ -91,7 +92,7 @@ def lib():
     L.ccdm_conv_uses_tc.argtypes = [ctypes.POINTER(Op)]
     L.ccdm_conv_uses_tma.argtypes = [ctypes.POINTER(Op)]
     L.ccdm_conv_stat_layout.argtypes = [ctypes.POINTER(Op), ctypes.POINTER(ctypes.c_int32)]
-    L.ccdm_conv_tc_nt.argtypes = [ctypes.c_int]
+    L.ccdm_conv_tc_nt.argtypes = [ctypes.c_int, ctypes.c_int]
     L.ccdm_conv_tc_config.argtypes = [ctypes.POINTER(Op), ctypes.POINTER(ctypes.c_int32)]
     L.ccdm_conv_part_floats.restype = ctypes.c_size_t
     L.ccdm_conv_part_floats.argtypes = [ctypes.c_int] * 4

@@ -65,12 +65,16 @@ struct AtP {
     uint32_t idesc_s, idesc_pv;
 };
 
-template <int NK>
+// X3: fp16x2 operands (CCDM_DT_F16X2; the "exact" tensor-core mode).  Every plane of q, k, v and P exists twice (hi, lo,
+// adjacent), both products are three fp16 MMAs (hi*lo + lo*hi + hi*hi), the softmax is the same fp32 arithmetic, and P
+// is split into hi + lo before the P V product -- fp32-grade attention on the tensor cores.
+template <int NK, bool X3>
 __global__ void __launch_bounds__(AT_QT, 3) attention_tc_kernel(const AtP p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    constexpr uint32_t Q_BYTES = AT_PLANES * AT_QT * 16;  // 8 KB
-    constexpr uint32_t KV_BYTES = AT_PLANES * NK * 16;    // per tensor per buffer
-    constexpr uint32_t P_BYTES = (NK / 8) * AT_QT * 16;
+    constexpr int X = X3 ? 2 : 1;
+    constexpr uint32_t Q_BYTES = X * AT_PLANES * AT_QT * 16;  // 8 KB
+    constexpr uint32_t KV_BYTES = X * AT_PLANES * NK * 16;    // per tensor per buffer
+    constexpr uint32_t P_BYTES = X * (NK / 8) * AT_QT * 16;
     uint8_t *sQ = smem;
     uint8_t *sK = sQ + Q_BYTES;        // [2][KV_BYTES]
     uint8_t *sV = sK + 2 * KV_BYTES;   // [2][KV_BYTES]
@@ -88,7 +92,8 @@ __global__ void __launch_bounds__(AT_QT, 3) attention_tc_kernel(const AtP p) {
     const int n_tiles = (T + NK - 1) / NK;
     const int planes3 = p.heads * 3 * AT_PLANES;  // planes of the qkv tensor
     // plane g of (which = 0 q | 1 k | 2 v) of this head: channel h*96 + which*32 + 8g
-    auto plane_ptr = [&](int which, int g) { return p.qkv + ((size_t(b) * planes3 + h * 3 * AT_PLANES + which * AT_PLANES + g) * T) * 8; };
+    // (fp16x2: tensor plane 2*that + part, part = 0 hi | 1 lo; g then counts (group, part) pairs)
+    auto plane_ptr = [&](int which, int g) { return p.qkv + ((size_t(b) * planes3 * X + (h * 3 * AT_PLANES + which * AT_PLANES) * X + g) * T) * 8; };
 
     if (warp == 0) tmem_alloc(s_tmem, TMEM_COLS);
     if (tid == 0) {
@@ -111,23 +116,33 @@ __global__ void __launch_bounds__(AT_QT, 3) attention_tc_kernel(const AtP p) {
 
     auto load_kv = [&](int t, int buf, uint32_t extra_bytes) {  // thread 0
         const int k0 = t * NK, nk = min(NK, T - k0);
-        mbar_expect_tx(kv_full + buf, uint32_t(2 * AT_PLANES * nk * 16) + extra_bytes);
+        mbar_expect_tx(kv_full + buf, uint32_t(2 * X * AT_PLANES * nk * 16) + extra_bytes);
 #pragma unroll
-        for (int g = 0; g < AT_PLANES; ++g) {
+        for (int g = 0; g < X * AT_PLANES; ++g) {
             bulk_g2s(sK + buf * KV_BYTES + g * NK * 16, plane_ptr(1, g) + size_t(k0) * 8, uint32_t(nk * 16), kv_full + buf);
             bulk_g2s(sV + buf * KV_BYTES + g * NK * 16, plane_ptr(2, g) + size_t(k0) * 8, uint32_t(nk * 16), kv_full + buf);
         }
     };
     if (tid == 0) {
-        load_kv(0, 0, uint32_t(AT_PLANES * nq * 16));
+        load_kv(0, 0, uint32_t(X * AT_PLANES * nq * 16));
 #pragma unroll
-        for (int g = 0; g < AT_PLANES; ++g) bulk_g2s(sQ + g * AT_QT * 16, plane_ptr(0, g) + size_t(q0) * 8, uint32_t(nq * 16), kv_full + 0);
+        for (int g = 0; g < X * AT_PLANES; ++g) bulk_g2s(sQ + g * AT_QT * 16, plane_ptr(0, g) + size_t(q0) * 8, uint32_t(nq * 16), kv_full + 0);
     }
 
     const uint32_t desc_hi = 8u | (1u << 14);                                   // SBO 128 B, version 1
-    const uint32_t q_lo = (smem_u32(sQ) >> 4) | (uint32_t(AT_QT) << 16);        // LBO = plane stride (128 rows)
-    const uint32_t p_lo = (smem_u32(sP) >> 4) | (uint32_t(AT_QT) << 16);
-    const uint32_t v_hi = uint32_t(NK) | (1u << 14);                            // MN-major: SBO = plane stride (NK rows)
+    const uint32_t q_lo = (smem_u32(sQ) >> 4) | (uint32_t(X * AT_QT) << 16);    // LBO = stride between 8-channel groups (X planes of 128 rows)
+    const uint32_t p_lo = (smem_u32(sP) >> 4) | (uint32_t(X * AT_QT) << 16);
+    const uint32_t v_hi = uint32_t(X * NK) | (1u << 14);                        // MN-major: SBO = stride between 8-channel groups (X planes of NK rows)
+    // one product = one bf16 MMA, or hi*lo + lo*hi + hi*hi on the split operands; (a_lo, b_lo) = row offsets of the lo planes
+    auto mma = [&](uint32_t d, uint32_t a, uint32_t a_hi, uint32_t a_lo, uint32_t b, uint32_t b_hi, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+        if constexpr (X3) {
+            umma_bf16(d, (uint64_t(a_hi) << 32) | a, (uint64_t(b_hi) << 32) | (b + b_lo), idesc, acc);
+            umma_bf16(d, (uint64_t(a_hi) << 32) | (a + a_lo), (uint64_t(b_hi) << 32) | b, idesc, 1u);
+            umma_bf16(d, (uint64_t(a_hi) << 32) | a, (uint64_t(b_hi) << 32) | b, idesc, 1u);
+        } else {
+            umma_bf16(d, (uint64_t(a_hi) << 32) | a, (uint64_t(b_hi) << 32) | b, idesc, acc);
+        }
+    };
 
     float o[AT_D];
 #pragma unroll
@@ -142,11 +157,11 @@ __global__ void __launch_bounds__(AT_QT, 3) attention_tc_kernel(const AtP p) {
             if (t + 1 < n_tiles) load_kv(t + 1, buf ^ 1, 0u);  // that buffer's last reader (P V of tile t-1) has completed
             mbar_wait(kv_full + buf, uint32_t(t >> 1) & 1u);
             tc_fence_after();
-            const uint32_t k_lo = (smem_u32(sK + buf * KV_BYTES) >> 4) | (uint32_t(NK) << 16);
+            const uint32_t k_lo = (smem_u32(sK + buf * KV_BYTES) >> 4) | (uint32_t(X * NK) << 16);
 #pragma unroll
             for (int j = 0; j < AT_D / 16; ++j)
-                umma_bf16(tmem_s, (uint64_t(desc_hi) << 32) | (q_lo + uint32_t(j * 2 * AT_QT)), (uint64_t(desc_hi) << 32) | (k_lo + uint32_t(j * 2 * NK)),
-                          p.idesc_s, j > 0 ? 1u : 0u);
+                mma(tmem_s, q_lo + uint32_t(j * 2 * X * AT_QT), desc_hi, uint32_t(AT_QT), k_lo + uint32_t(j * 2 * X * NK), desc_hi, uint32_t(NK), p.idesc_s,
+                    j > 0 ? 1u : 0u);
             umma_commit(s_done);
         }
         mbar_wait(s_done, uint32_t(t) & 1u);
@@ -170,10 +185,10 @@ __global__ void __launch_bounds__(AT_QT, 3) attention_tc_kernel(const AtP p) {
         const float corr = ex2_approx((m - m_new) * c);  // m = -inf on the first tile -> 0
         const float mc = m_new * c;
         float rs[4] = {0.f, 0.f, 0.f, 0.f};
-        // pass 2: P = exp2(S*c - m*c) as bf16, K-major rows for the P V product
+        // pass 2: P = exp2(S*c - m*c) as bf16 (fp16x2: hi + lo), K-major rows for the P V product
 #pragma unroll
         for (int c0 = 0; c0 < NK; c0 += 32) {
-            uint32_t pk[16];
+            uint32_t pk[16], pl[16];
             if (c0 < nk) {
                 float s[32];
                 tmem_ld32(tmem_s + trow + uint32_t(c0), s);
@@ -181,17 +196,25 @@ __global__ void __launch_bounds__(AT_QT, 3) attention_tc_kernel(const AtP p) {
                 for (int i = 0; i < 32; i += 2) {
                     float p0 = (c0 + i < nk) ? ex2_approx(fmaf(s[i], c, -mc)) : 0.f;
                     float p1 = (c0 + i + 1 < nk) ? ex2_approx(fmaf(s[i + 1], c, -mc)) : 0.f;
-                    pk[i / 2] = pack_bf16(p0, p1);
-                    const float2 f = unpack_bf16(pk[i / 2]);  // the sum of what the MMA will actually see
-                    rs[(i >> 1) & 3] += f.x + f.y;
+                    if (X3) {
+                        split_f16x2(p0, p1, pk[i / 2], pl[i / 2]);  // hi + lo reproduces p to 2^-23: the sum the MMA sees is the fp32 sum
+                        rs[(i >> 1) & 3] += p0 + p1;
+                    } else {
+                        pk[i / 2] = pack_bf16(p0, p1);
+                        const float2 f = unpack_bf16(pk[i / 2]);  // the sum of what the MMA will actually see
+                        rs[(i >> 1) & 3] += f.x + f.y;
+                    }
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) pk[i] = 0u;
+                for (int i = 0; i < 16; ++i) pk[i] = 0u, pl[i] = 0u;
             }
 #pragma unroll
-            for (int g = 0; g < 4; ++g)  // key planes c0/8 .. c0/8+3, this thread's row
-                *reinterpret_cast<uint4 *>(sP + (size_t(c0 / 8 + g) * AT_QT + tid) * 16) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+            for (int g = 0; g < 4; ++g) {  // key planes c0/8 .. c0/8+3, this thread's row
+                *reinterpret_cast<uint4 *>(sP + (size_t((c0 / 8 + g) * X) * AT_QT + tid) * 16) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+                if (X3)
+                    *reinterpret_cast<uint4 *>(sP + (size_t((c0 / 8 + g) * X + 1) * AT_QT + tid) * 16) = make_uint4(pl[4 * g], pl[4 * g + 1], pl[4 * g + 2], pl[4 * g + 3]);
+            }
         }
         l = l * corr + ((rs[0] + rs[1]) + (rs[2] + rs[3]));
         m = m_new;
@@ -203,8 +226,7 @@ __global__ void __launch_bounds__(AT_QT, 3) attention_tc_kernel(const AtP p) {
             const uint32_t v_lo = (smem_u32(sV + buf * KV_BYTES) >> 4) | (8u << 16);  // LBO = 128 B between groups of 8 keys
 #pragma unroll
             for (int j = 0; j < NK / 16; ++j)
-                umma_bf16(tmem_o, (uint64_t(desc_hi) << 32) | (p_lo + uint32_t(j * 2 * AT_QT)), (uint64_t(v_hi) << 32) | (v_lo + uint32_t(j * 16)),
-                          p.idesc_pv, j > 0 ? 1u : 0u);
+                mma(tmem_o, p_lo + uint32_t(j * 2 * X * AT_QT), desc_hi, uint32_t(AT_QT), v_lo + uint32_t(j * 16), v_hi, uint32_t(NK), p.idesc_pv, j > 0 ? 1u : 0u);
             umma_commit(o_done);
         }
         mbar_wait(o_done, uint32_t(t) & 1u);
@@ -222,15 +244,20 @@ __global__ void __launch_bounds__(AT_QT, 3) attention_tc_kernel(const AtP p) {
     }
 
     if (tid < nq) {
-        const float inv = 1.0f / l;
+        // fp16x2: o = sum (16 p)(16 v): the stored 16 x value is o / (16 l)
+        const float inv = X3 ? 1.0f / (16.0f * l) : 1.0f / l;
         const int planes = p.heads * AT_PLANES;
 #pragma unroll
         for (int g = 0; g < AT_PLANES; ++g) {
-            uint32_t pk[4];
+            uint32_t pk[4], pl[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) pk[i] = pack_bf16(o[8 * g + 2 * i] * inv, o[8 * g + 2 * i + 1] * inv);
-            __nv_bfloat16 *dst = p.out + ((size_t(b) * planes + h * AT_PLANES + g) * T + q0 + tid) * 8;
+            for (int i = 0; i < 4; ++i) {
+                if (X3) split_f16x2_raw(o[8 * g + 2 * i] * inv, o[8 * g + 2 * i + 1] * inv, pk[i], pl[i]);
+                else pk[i] = pack_bf16(o[8 * g + 2 * i] * inv, o[8 * g + 2 * i + 1] * inv);
+            }
+            __nv_bfloat16 *dst = p.out + ((size_t(b) * planes + h * AT_PLANES + g) * X * T + q0 + tid) * 8;
             *reinterpret_cast<uint4 *>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            if (X3) *reinterpret_cast<uint4 *>(dst + size_t(T) * 8) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
         }
     }
     tc_fence_before();
@@ -241,22 +268,24 @@ __global__ void __launch_bounds__(AT_QT, 3) attention_tc_kernel(const AtP p) {
     }
 }
 
-template <int NK>
+template <int NK, bool X3>
 int launch_nk(const AtP &p, int grid, cudaStream_t s) {
-    constexpr size_t smem = AT_PLANES * AT_QT * 16 + 4 * AT_PLANES * NK * 16 + (NK / 8) * AT_QT * 16 + 64;
+    constexpr size_t smem = (X3 ? 2 : 1) * (AT_PLANES * AT_QT * 16 + 4 * AT_PLANES * NK * 16 + (NK / 8) * AT_QT * 16) + 64;
     static bool attr_done = false;
     if (!attr_done) {
-        CCDM_CUDA(cudaFuncSetAttribute(attention_tc_kernel<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        CCDM_CUDA(cudaFuncSetAttribute(attention_tc_kernel<NK, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         attr_done = true;
     }
-    CCDM_CUDA(launch_pdl(attention_tc_kernel<NK>, dim3(grid), dim3(AT_QT), smem, s, p));
+    CCDM_CUDA(launch_pdl(attention_tc_kernel<NK, X3>, dim3(grid), dim3(AT_QT), smem, s, p));
     CCDM_LAUNCH_CHECK("attention_tc_kernel");
     return 0;
 }
 
 }  // namespace
 
-bool attention_tc_supported(const ccdm_op &op) { return op.dtype == CCDM_DT_BF16 && op.head_dim == AT_D && !op.exact && op.heads > 0; }
+bool attention_tc_supported(const ccdm_op &op) {
+    return (op.dtype == CCDM_DT_BF16 || op.dtype == CCDM_DT_F16X2) && op.head_dim == AT_D && !op.exact && op.heads > 0;
+}
 
 int launch_attention_tc(const ccdm_op &op, cudaStream_t s) {
     const int T = op.Hin * op.Win;
@@ -267,16 +296,19 @@ int launch_attention_tc(const ccdm_op &op, cudaStream_t s) {
     p.T = T;
     p.heads = op.heads;
     p.q_tiles = (T + AT_QT - 1) / AT_QT;
-    p.scale_log2 = float(1.4426950408889634 / sqrt(double(AT_D)));  // unet.py:354: q and k are each scaled by 32^-1/4
+    const bool x3 = op.dtype == CCDM_DT_F16X2;
+    // unet.py:354: q and k are each scaled by 32^-1/4; fp16x2 operands are stored as 16 x value: S comes out 256 x too large
+    p.scale_log2 = float(1.4426950408889634 / sqrt(double(AT_D))) * (x3 ? 1.0f / 256.0f : 1.0f);
     static const int env_nk = getenv("CCDM_ATT_NK") ? atoi(getenv("CCDM_ATT_NK")) : 0;  // tuning override
-    const int NK = env_nk == 64 || env_nk == 128 ? env_nk : (T <= 256 ? 64 : 128);  // measured: T=256 16.8 vs 20.9 us, T=2048 76 vs 66 us
+    const int NK = x3 ? 64 : env_nk == 64 || env_nk == 128 ? env_nk : (T <= 256 ? 64 : 128);  // measured: T=256 16.8 vs 20.9 us, T=2048 76 vs 66 us
     // cute::UMMA::InstrDescriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), b_major = MN (bit 16), N>>3 at 17, M>>4 at 24
-    const uint32_t base = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(128 >> 4) << 24);
+    const uint32_t base = (1u << 4) | (x3 ? 0u : ((1u << 7) | (1u << 10))) | (uint32_t(128 >> 4) << 24);  // formats: 0 = f16, 1 = bf16
     p.idesc_s = base | (uint32_t(NK >> 3) << 17);
     p.idesc_pv = base | (uint32_t(AT_D >> 3) << 17) | (1u << 16);
     const int grid = op.B * op.heads * p.q_tiles;
     if (!p.qkv || !p.out || T <= 0 || grid <= 0) CCDM_FAIL(-2, "attention_tc: missing tensors");
-    return NK == 64 ? launch_nk<64>(p, grid, s) : launch_nk<128>(p, grid, s);
+    if (x3) return launch_nk<64, true>(p, grid, s);  // 80 KB of shared memory per CTA at NK = 64: two CTAs per SM
+    return NK == 64 ? launch_nk<64, false>(p, grid, s) : launch_nk<128, false>(p, grid, s);
 }
 
 }  // namespace ccdm

@@ -374,37 +374,27 @@ size_t conv_part_floats(int B, int Hout, int Wout, int Cout) {
     return size_t(B) * tiles * CoutP * 2;
 }
 
-bool conv_tc_supported(const ccdm_op &op);
-size_t conv_tc_part_floats(const ccdm_op &op);
-int launch_conv_tc(const ccdm_op &op, cudaStream_t s);
-
 bool conv_tma_supported(const ccdm_op &op);
 size_t conv_tma_part_floats(const ccdm_op &op);
 int launch_conv_tma(const ccdm_op &op, cudaStream_t s);
 
-// CCDM_CONV_TMA=0 routes every tensor-core conv to the LDG-fed kernel (A/B measurements)
-static bool tma_enabled() {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("CCDM_CONV_TMA");
-        v = (e && e[0] == '0') ? 0 : 1;
-    }
-    return v == 1;
-}
-// (upsampling convs always take the TMA kernel: their packed weights are the 16 pre-summed sub-pixel tap matrices)
-bool conv_uses_tma(const ccdm_op &op) { return !op.exact && op.kind == CCDM_OP_CONV && (tma_enabled() || op.upsample) && conv_tma_supported(op); }
-bool conv_uses_tc(const ccdm_op &op) { return !op.exact && op.kind == CCDM_OP_CONV && (conv_uses_tma(op) || conv_tc_supported(op)); }
+// The tensor-core modes (bf16 / fp16x2 storage, op.exact == 0) have exactly one conv kernel, conv_tma.cu.  An op it
+// cannot take falls to the FFMA kernel below, which reads the same plane-major bf16 tensors with fp32 [tap][Cin][Cout]
+// weights and FOLDED double2 statistics; the engine binds it accordingly and says so (engine.Program.bind).
+bool conv_uses_tma(const ccdm_op &op) { return !op.exact && op.kind == CCDM_OP_CONV && conv_tma_supported(op); }
+bool conv_uses_tc(const ccdm_op &op) { return conv_uses_tma(op); }
 
 size_t op_part_floats(const ccdm_op &op) {
     if (op.kind != CCDM_OP_CONV && op.kind != CCDM_OP_INPUT_CONV) return 0;
     if (conv_uses_tma(op)) return conv_tma_part_floats(op);
-    if (conv_uses_tc(op)) return conv_tc_part_floats(op);
     return conv_part_floats(op.B, op.Hout, op.Wout, op.Cout);
 }
 
 int launch_conv(const ccdm_op &op, cudaStream_t s) {
     if (conv_uses_tma(op)) return launch_conv_tma(op, s);
-    if (conv_uses_tc(op)) return launch_conv_tc(op, s);
+    if (op.dtype == CCDM_DT_F16X2) CCDM_FAIL(-3, "conv: this shape does not fit the tensor-core kernel and the fp16x2 (exact tensor-core) mode has no other");
+    if (op.st_slots[0] > 0 || op.st_slots[1] > 0)
+        CCDM_FAIL(-2, "conv_ffma: deferred-fold statistics rows (st_slots > 0) are a tensor-core consumer's layout; this kernel reads folded double2 [B,C]");
     ConvP p{};
     p.src0 = (const void *)op.src0; p.src1 = (const void *)op.src1;
     p.stat0 = (const double *)op.stat0; p.stat1 = (const double *)op.stat1;

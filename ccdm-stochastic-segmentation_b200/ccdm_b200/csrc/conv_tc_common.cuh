@@ -1,6 +1,6 @@
-// Pieces shared by the two tcgen05 conv kernels (conv_tma.cu: TMA-fed, conv_ws.cu: LDG-fed): the launch
-// parameter block, the work-item decoding and the epilogue role (TMEM -> registers -> +bias +embedding
-// +residual -> plane-major bf16 / NHWC fp32 store + GroupNorm statistics of the output).
+// Pieces of the tcgen05 conv kernel (conv_tma.cu) that do not depend on how its operands are staged: the launch
+// parameter block, the work-item decoding, the GroupNorm fold and the epilogue role (TMEM -> registers -> +bias
+// +embedding +residual -> plane-major bf16 / fp16x2 / NHWC fp32 store + GroupNorm statistics of the output).
 #pragma once
 
 #include "tc_common.cuh"
@@ -13,13 +13,14 @@ constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int MAX_STAGES = 8;
 constexpr int CGW = 16;  // accumulator columns per tcgen05.ld
 
-// Output channels per work item (the N of the MMAs) = the packing unit of the weights, a function of Cout only so
-// that one packed tensor serves every shape.  Up to 128 output channels: the largest divisor <= 64 (narrow items:
-// more CTAs busy on small maps).  Wider layers (the 1x1 q/k/v convs, Cout = 3C): the largest divisor <= 192, so a
-// sample is 2 items instead of 6 and the input is normalised twice instead of six times.
-inline int tc_nt(int Cout) {
+// Output channels per work item (the N of the MMAs) = the packing unit of the weights, a function of (Cout, taps) only so
+// that one packed tensor serves every shape.  Up to 128 output channels, and every 3x3 conv: the largest divisor <= 64
+// (narrow items: more CTAs busy on small maps, and a weight stage of 9 or 16 taps stays small).  Wider 1x1 layers (the
+// q/k/v convs, Cout = 3C): the largest divisor <= 192, so a sample is 2 items instead of 6 and the input is normalised
+// twice instead of six times.
+inline int tc_nt(int Cout, int taps) {
     const int CoutP = (Cout + 15) / 16 * 16;
-    for (int nt = CoutP > 128 ? 192 : 64; nt >= 16; nt -= 16)
+    for (int nt = (CoutP > 128 && taps == 1) ? 192 : 64; nt >= 16; nt -= 16)
         if (CoutP % nt == 0) return nt;
     return 16;
 }
@@ -52,6 +53,8 @@ struct WsP {
     int RW, NQ, xf;  // conv_tma: window rows, window positions (= plane stride in 16-byte rows), 1 if chunks are transformed in smem
     uint32_t a_stage, w_stage, w_main_bytes, w_skip_bytes, magicP;
     uint32_t idesc;
+    int x3;          // fp16x2 storage (CCDM_DT_F16X2): operands are (hi, lo) plane pairs, three MMAs per product
+    float descale;   // x3: 2^-acc_shift, applied to the accumulator in the epilogue
 };
 
 struct Item {
@@ -140,6 +143,14 @@ __device__ __forceinline__ void gn_build_affine(const WsP &p, int b, float *sAff
         const double mean = s * inv_n;
         double var = q * inv_n - mean * mean;
         var = var < 0.0 ? 0.0 : var;
+        if (p.x3) {
+            // exact mode: fp32-grade 1/sqrt; the stored operand is 2^4 x, so only the scale carries the 2^-4
+            const float rstd = float(1.0 / sqrt(var + double(kGnEps)));
+            const float a = sAff[c] * rstd;
+            sAff[c] = a * (1.0f / float(1 << CCDM_F16X2_SCALE_LOG2));
+            sAff[p.Cin + c] = sAff[p.Cin + c] - float(mean) * a;
+            continue;
+        }
         const float rstd = rsqrtf(float(var) + kGnEps);
         const float a = sAff[c] * rstd;
         sAff[c] = half * a;
@@ -158,7 +169,7 @@ __device__ __forceinline__ void gn_build_affine(const WsP &p, int b, float *sAff
 // LEAN: bf16 plane-major output without an epilogue residual (every conv of the bf16 chain but the output conv): the fp32
 // NHWC store variants and the residual read are compiled out -- the role's code is half of the kernel, and its size costs
 // (instruction fetch) even where it is not executed.
-template <int NEW, int NSUB = 1, bool LEAN = false>
+template <int NEW, int NSUB = 1, bool LEAN = false, bool X3 = false>
 __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, float *sRed, int *s_last, uint64_t *acc_full,
                                                    uint64_t *acc_empty, uint32_t tmem_base, int it_begin, int it_end) {
     constexpr int NTHR = NEW * 32;
@@ -276,7 +287,8 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
                 add[i] = t.x; add[i + 1] = t.y; add[i + 2] = t.z; add[i + 3] = t.w;
             }
             // plane-major bases of this thread's two 8-channel planes (bf16 in/out) or the NHWC fp32 row
-            const size_t plane0 = (size_t(I.b) * (p.Cout >> 3) + (cobase >> 3)) * hw + pix0;
+            // (fp16x2: twice the planes -- the hi and lo plane of an 8-channel group are adjacent)
+            const size_t plane0 = (size_t(I.b) * (p.Cout >> 3) + (cobase >> 3)) * (X3 ? 2 : 1) * hw + pix0;
             const __nv_bfloat16 *resb = p.res != nullptr ? p.res + plane0 * 8 : nullptr;
             __nv_bfloat16 *outb = reinterpret_cast<__nv_bfloat16 *>(p.out) + plane0 * 8;
             float *outf = reinterpret_cast<float *>(p.out) + (size_t(I.b) * hw + pix0) * p.Cout + cobase;
@@ -307,8 +319,8 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
                 for (int i = 0; i < CGW; ++i) v[i] = __uint_as_float(raw[i]);
                 if (valid) {
 #pragma unroll
-                    for (int i = 0; i < CGW; ++i) v[i] += add[i];
-                    if (!LEAN && resb != nullptr) {  // identity residual read here (the engine's bf16 path folds it into the MMA instead)
+                    for (int i = 0; i < CGW; ++i) v[i] = X3 ? fmaf(v[i], p.descale, add[i]) : v[i] + add[i];
+                    if (!X3 && !LEAN && resb != nullptr) {  // identity residual read here (the engine's bf16 path folds it into the MMA instead)
 #pragma unroll
                         for (int h2 = 0; h2 < CGW / 8; ++h2) {
                             const uint4 rr = ldg_nc16(resb + (size_t(h2) * hw + off) * 8);
@@ -335,6 +347,15 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
 #pragma unroll
                             for (int i = 0; i < CGW; ++i)
                                 if (cobase + i < p.Cout) op[i] = v[i];
+                        }
+                    } else if (X3) {
+#pragma unroll
+                        for (int h2 = 0; h2 < CGW / 8; ++h2) {
+                            uint32_t ph[4], pl[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) split_f16x2(v[h2 * 8 + 2 * i], v[h2 * 8 + 2 * i + 1], ph[i], pl[i]);
+                            *reinterpret_cast<uint4 *>(outb + (size_t(2 * h2) * hw + off) * 8) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                            *reinterpret_cast<uint4 *>(outb + (size_t(2 * h2 + 1) * hw + off) * 8) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
                         }
                     } else {
 #pragma unroll

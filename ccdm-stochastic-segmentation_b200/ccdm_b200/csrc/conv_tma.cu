@@ -1,7 +1,8 @@
 // Fused GroupNorm + SiLU + conv (3x3 / 1x1, stride 1) on the 5th-generation tensor cores, fed by TMA.
 //
-// Same arithmetic and same "flattened padded tile" implicit GEMM as conv_ws.cu (see there), but the data
-// path is the one the hardware is built for:
+// Implicit GEMM over a "flattened padded tile": the M rows of an MMA are consecutive positions of the (haloed) window
+// of a tile, so the 3x3 taps are pure shifts of the A descriptor's start address.  The data path is the one the
+// hardware is built for:
 //
 //   * bf16 activations live in HBM PLANE-MAJOR, [B][C/8][H][W][8]: 16 bytes per (8-channel plane, pixel),
 //     i.e. exactly one row of a tcgen05 "K-major, no swizzle" core matrix.  A 4-D TMA box
@@ -147,6 +148,76 @@ __device__ __forceinline__ void xf_pass(uint32_t addr, int q, int NQ, int r, int
     }
 }
 
+// ---- fp16x2 ("exact" tensor-core mode) transform --------------------------------------------------------------
+// One position of one 8-channel group = a hi row and a lo row (NQ rows apart): x = (hi + lo) * 2^-4 exactly in fp32,
+// GroupNorm affine (the 2^-4 is folded into fa) and SiLU as h / (1 + exp(-h)) with full-rate MUFU ex2 / rcp (a few ulp;
+// tanh.approx of the bf16 path is good to 2^-11 only), then split again.
+template <bool SILU>
+__device__ __forceinline__ void xf_row_x3(uint4 &hi, uint4 &lo, const float (&fa)[8], const float (&fb)[8]) {
+    uint32_t h4[4] = {hi.x, hi.y, hi.z, hi.w}, l4[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 xh = unpack_f16x2(h4[i]), xl = unpack_f16x2(l4[i]);
+        float h0 = fmaf(xh.x, fa[2 * i], fmaf(xl.x, fa[2 * i], fb[2 * i]));
+        float h1 = fmaf(xh.y, fa[2 * i + 1], fmaf(xl.y, fa[2 * i + 1], fb[2 * i + 1]));
+        if (SILU) {
+            h0 = __fdividef(h0, 1.0f + __expf(-h0));
+            h1 = __fdividef(h1, 1.0f + __expf(-h1));
+        }
+        split_f16x2(h0, h1, h4[i], l4[i]);
+    }
+    hi = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+    lo = make_uint4(l4[0], l4[1], l4[2], l4[3]);
+}
+
+// In-place pass over positions q0, q0 + STEP, ... < NQ of one (hi, lo) plane pair; `addr` = the hi row of q0, the lo row
+// is lo_off bytes further.  Two positions per iteration (32 live registers of data); halo positions stay zero (see xf_pass).
+template <int STEP, bool MASK, bool SILU>
+__device__ __forceinline__ void xf_pass_x3(uint32_t addr, uint32_t lo_off, int q, int NQ, int r, int c, int dr, int dc, int P, int ymin,
+                                           int xmin, int H, int W, const float (&fa)[8], const float (&fb)[8]) {
+    auto advance = [&]() {
+        if (MASK) {
+            c += dc;
+            r += dr;
+            if (c >= P) {
+                c -= P;
+                ++r;
+            }
+        }
+    };
+    auto ok = [&]() -> bool { return !MASK || (unsigned(ymin + r) < unsigned(H) && unsigned(xmin + c) < unsigned(W)); };
+    for (; q + STEP < NQ; q += 2 * STEP, addr += 2u * STEP * 16u) {
+        uint4 hi[2], lo[2];
+        bool keep[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            hi[u] = lds128(addr + uint32_t(u) * STEP * 16u);
+            lo[u] = lds128(addr + uint32_t(u) * STEP * 16u + lo_off);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            keep[u] = ok();
+            advance();
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) xf_row_x3<SILU>(hi[u], lo[u], fa, fb);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (MASK && !keep[u]) hi[u] = lo[u] = make_uint4(0u, 0u, 0u, 0u);
+            sts128(addr + uint32_t(u) * STEP * 16u, hi[u]);
+            sts128(addr + uint32_t(u) * STEP * 16u + lo_off, lo[u]);
+        }
+    }
+    for (; q < NQ; q += STEP, addr += uint32_t(STEP) * 16u) {
+        uint4 hi = lds128(addr), lo = lds128(addr + lo_off);
+        xf_row_x3<SILU>(hi, lo, fa, fb);
+        if (MASK && !ok()) hi = lo = make_uint4(0u, 0u, 0u, 0u);
+        sts128(addr, hi);
+        sts128(addr + lo_off, lo);
+        advance();
+    }
+}
+
 // Milestone time stamps of CTA 0 (debug aid, read back with ccdm_debug_conv_trace): one store per milestone.
 __device__ unsigned long long g_trace[16];
 enum { kTraceStart = 0, kTraceSetup, kTraceAffine, kTraceRaw0, kTraceXf0, kTraceMma0, kTraceEpi0, kTraceFlush, kTraceEnd };
@@ -197,11 +268,15 @@ __device__ void conv_tma_tl_hook(int item, int edge) { tl(3, item, edge); }
 // instantiation so that the common kernel's code and register allocation are untouched by it.
 // XF: which in-place transform the kernel carries -- 0 none (convs without GroupNorm/SiLU: the role idles), 1 GroupNorm +
 // SiLU, 2 GroupNorm only (q/k/v convs), 3 both (selected at run time).  Separate instantiations keep each kernel small.
-template <int PL, bool UP, bool LEAN, int XF>
+// X3: fp16x2 operands (CCDM_DT_F16X2).  A stage holds 2*PL planes -- (hi, lo) of PL 8-channel groups -- the weights carry
+// NT hi rows + NT lo rows per (plane, tap), and every product is three MMAs into the same accumulator:
+// A_hi B_hi + A_hi B_lo + A_lo B_hi (the dropped lo*lo term is 2^-22 of the product).
+template <int PL, bool UP, bool LEAN, int XF, bool X3 = false>
 __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_constant__ TmP P_) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const WsP &p = P_.w;
     constexpr int KC = 8 * PL;
+    constexpr int X = X3 ? 2 : 1;  // smem planes per 8-channel group; B rows per (plane, tap) in units of NT
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NT = p.NT, P = p.P, NS = p.NS, NQ = p.NQ;
     if (tid == 0) trace(kTraceStart), cta_stamp(0);
@@ -268,7 +343,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
     // per LIDC step -- the roles are limited by shared-memory bandwidth and issue slots, not by warp count.)
     if (warp < TM_EPI_WARPS) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
-        conv_epilogue_role<TM_EPI_WARPS, UP ? 4 : 1, LEAN>(p, sAdd, sRed, s_last, acc_full, acc_empty, tmem_base, it_begin, it_end);
+        conv_epilogue_role<TM_EPI_WARPS, UP ? 4 : 1, LEAN, X3>(p, sAdd, sRed, s_last, acc_full, acc_empty, tmem_base, it_begin, it_end);
     } else if (warp < WARP_MMA0) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
         // =========================== in-place GroupNorm + SiLU ======================================
@@ -320,11 +395,21 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
                             }
                         } else {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) fa[i] = (p.silu == 1 || p.silu == 2) ? 0.5f : 1.0f, fb[i] = 0.f;
+                            for (int i = 0; i < 8; ++i) fa[i] = X3 ? 0.0625f : ((p.silu == 1 || p.silu == 2) ? 0.5f : 1.0f), fb[i] = 0.f;
                         }
                         mbar_wait(raw_full + stage, phase);
                         if (pt == 0 && it == it_begin && kc == 0) trace(kTraceRaw0);
-                        const uint32_t addr = sA32 + uint32_t(stage) * p.a_stage + (uint32_t(plane) * uint32_t(NQ) + uint32_t(q0)) * 16u;
+                        const uint32_t addr = sA32 + uint32_t(stage) * p.a_stage + (uint32_t(X * plane) * uint32_t(NQ) + uint32_t(q0)) * 16u;
+                        if constexpr (X3) {
+                            const uint32_t lo_off = uint32_t(NQ) * 16u;
+                            if (need_mask) {
+                                if (kSilu && (!kPlain || p.silu)) xf_pass_x3<STEP, true, true>(addr, lo_off, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
+                                else if (kPlain) xf_pass_x3<STEP, true, false>(addr, lo_off, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
+                            } else {
+                                if (kSilu && (!kPlain || p.silu)) xf_pass_x3<STEP, false, true>(addr, lo_off, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
+                                else if (kPlain) xf_pass_x3<STEP, false, false>(addr, lo_off, q0, NQ, r0, c0, dr, dc, P, ymin, xmin, p.H, p.W, fa, fb);
+                            }
+                        } else
                         // (SiLU modes 2 and 3 are measured-and-rejected experiments: compiled only with -DCCDM_SILU_EXPERIMENTS,
                         // they double the code of this role)
                         if (need_mask) {
@@ -365,10 +450,22 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
         uint32_t phase = 0;
         if (p.resident) mbar_wait(w_res, 0);
         const uint32_t desc_hi = 8u | (1u << 14);  // SBO = 128 B, descriptor version 1
-        const uint32_t a0 = (smem_u32(sA) >> 4) | (uint32_t(NQ) << 16);  // LBO of A: plane stride = NQ rows
+        const uint32_t a0 = (smem_u32(sA) >> 4) | (uint32_t(X * NQ) << 16);  // LBO of A: stride between 8-channel groups = X planes of NQ rows
         const uint32_t w0 = smem_u32(sW) >> 4;
         const uint32_t a_stage16 = p.a_stage >> 4, w_stage16 = p.w_stage >> 4;
-        const uint32_t kA = 2u * uint32_t(NQ);
+        const uint32_t kA = 2u * uint32_t(X * NQ);
+        // one product: a single bf16 MMA, or the three fp16 MMAs of the split operands (lo plane of A: NQ rows after the
+        // hi plane; lo rows of B: NT rows after the hi rows)
+        const uint32_t a_lo = uint32_t(NQ), b_lo = uint32_t(NT);
+        auto mma = [&](uint32_t d, uint32_t a, uint32_t b, uint32_t acc) {
+            if constexpr (X3) {
+                umma_bf16_split(d, a, desc_hi, b + b_lo, desc_hi, p.idesc, acc);
+                umma_bf16_split(d, a + a_lo, desc_hi, b, desc_hi, p.idesc, 1u);
+                umma_bf16_split(d, a, desc_hi, b, desc_hi, p.idesc, 1u);
+            } else {
+                umma_bf16_split(d, a, desc_hi, b, desc_hi, p.idesc, acc);
+            }
+        };
         for (int it = it_begin; it < it_end; ++it, ++acc_it) {
             const int buf = p.acc2 ? (acc_it & 1) : 0;
             const uint32_t aph = p.acc2 ? uint32_t((acc_it >> 1) & 1) : uint32_t(acc_it & 1);
@@ -384,11 +481,11 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
                 const uint32_t aaddr = a0 + uint32_t(stage) * a_stage16;
                 uint32_t waddr;
                 if (p.resident)
-                    waddr = is_skip ? w0 + (p.w_main_bytes >> 4) + uint32_t((kc - p.n_main) * PL * NT) : w0 + uint32_t(kc * PL * ntap * NT);
+                    waddr = is_skip ? w0 + (p.w_main_bytes >> 4) + uint32_t((kc - p.n_main) * PL * NT * X) : w0 + uint32_t(kc * PL * ntap * NT * X);
                 else
                     waddr = w0 + uint32_t(stage) * w_stage16;
-                waddr |= uint32_t(ntap * NT) << 16;  // LBO of B: one 8-channel plane = ntap * NT rows of 16 bytes
-                const uint32_t kB = 2u * uint32_t(ntap * NT);
+                waddr |= uint32_t(ntap * NT * X) << 16;  // LBO of B: one 8-channel plane = ntap * (X * NT) rows of 16 bytes
+                const uint32_t kB = 2u * uint32_t(ntap * NT * X);
                 if (UP && ntap == 16) {
                     // nearest x2 + conv3x3 as four 2x2 convs on the LOW-resolution window, one per output parity
                     // (py, px): output (2y+py, 2x+px) reads low-res rows y-1+py+ry, columns x-1+px+rx, (ry, rx) in
@@ -403,10 +500,10 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
 #pragma unroll
                             for (int t = 0; t < 4; ++t) {
                                 const uint32_t at = arow + uint32_t(((par >> 1) + (t >> 1)) * P + (par & 1) + (t & 1));
-                                const uint32_t bt = waddr + uint32_t((par * 4 + t) * NT);
+                                const uint32_t bt = waddr + uint32_t((par * 4 + t) * NT * X);
 #pragma unroll
                                 for (int k16 = 0; k16 < PL / 2; ++k16) {
-                                    umma_bf16_split(d, at + k16 * kA, desc_hi, bt + k16 * kB, desc_hi, p.idesc, acc);
+                                    mma(d, at + k16 * kA, bt + k16 * kB, acc);
                                     acc = 1u;
                                 }
                             }
@@ -425,10 +522,10 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
                             const uint32_t at = arow + (p.stride2 ? uint32_t(((((tap / 3) + 1) & 1) * 2 + (((tap % 3) + 1) & 1)) * p.blk16 +
                                                                              ((tap / 3) > 0 ? P : 0) + ((tap % 3) > 0 ? 1 : 0))
                                                                   : uint32_t((tap / 3) * P + (tap % 3)));
-                            const uint32_t bt = waddr + uint32_t(tap * NT);
+                            const uint32_t bt = waddr + uint32_t(tap * NT * X);
 #pragma unroll
                             for (int k16 = 0; k16 < PL / 2; ++k16) {
-                                umma_bf16_split(d, at + k16 * kA, desc_hi, bt + k16 * kB, desc_hi, p.idesc, acc);
+                                mma(d, at + k16 * kA, bt + k16 * kB, acc);
                                 acc = 1u;
                             }
                         }
@@ -441,7 +538,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
                         const uint32_t at = aaddr + uint32_t(mb * 128) + shift;
 #pragma unroll
                         for (int k16 = 0; k16 < PL / 2; ++k16)
-                            umma_bf16_split(d, at + k16 * kA, desc_hi, waddr + k16 * kB, desc_hi, p.idesc, (kc > 0 || k16 > 0) ? 1u : 0u);
+                            mma(d, at + k16 * kA, waddr + k16 * kB, (kc > 0 || k16 > 0) ? 1u : 0u);
                     }
                 }
                 umma_commit_elect(empty + stage);
@@ -461,7 +558,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
             int stage = 0;
             uint32_t phase = 0;
             const int planes_main = p.Cin / 8, planes_skip = (p.S0 + p.S1) / 8;
-            const uint32_t a_bytes = uint32_t(PL) * uint32_t(NQ) * 16u;
+            const uint32_t a_bytes = uint32_t(X * PL) * uint32_t(NQ) * 16u;
             for (int it = it_begin; it < it_end; ++it) {
                 const Item I = decode_item(p, it);
                 tl(0, it - it_begin, 0);
@@ -472,14 +569,14 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
                     const int CA = is_skip ? p.S0 : p.C0;
                     const bool first = cbase < CA;
                     const CUtensorMap *map = &P_.map[(is_skip ? 2 : 0) + (first ? 0 : 1)];
-                    const int g0 = (first ? cbase : cbase - CA) >> 3;
+                    const int g0 = ((first ? cbase : cbase - CA) >> 3) * X;  // first plane of the chunk in the tensor
                     uint32_t bytes = a_bytes;
                     const __nv_bfloat16 *wsrc = nullptr;
                     uint32_t wbytes = 0;
                     if (!p.resident) {
-                        wbytes = uint32_t(PL * (is_skip ? 1 : p.taps) * NT) * 16;
-                        wsrc = is_skip ? p.skip_w + (size_t(I.cc) * planes_skip + size_t(kc - p.n_main) * PL) * NT * 8
-                                       : p.weight + (size_t(I.cc) * planes_main + size_t(kc) * PL) * p.taps * NT * 8;
+                        wbytes = uint32_t(PL * (is_skip ? 1 : p.taps) * NT * X) * 16;
+                        wsrc = is_skip ? p.skip_w + (size_t(I.cc) * planes_skip + size_t(kc - p.n_main) * PL) * NT * 8 * X
+                                       : p.weight + (size_t(I.cc) * planes_main + size_t(kc) * PL) * p.taps * NT * 8 * X;
                         bytes += wbytes;
                     }
                     mbar_wait(empty + stage, phase ^ 1u);
@@ -524,18 +621,40 @@ struct TmCfg {
 
 constexpr size_t kTmSmemBudget = 224 * 1024;  // of the 227 KB a CTA may opt in to
 constexpr size_t kTmResidentMax = 80 * 1024;  // weights kept in smem for the whole launch when they fit
-constexpr int kTmNumSMs = 148;
+// one CTA per SM: the persistent grid and the statistics-slot layout follow the device the library runs on (148 on a
+// B200; the no-GPU planning paths -- dry-run engines, host tests -- assume that)
+int tm_num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
+        else n = 148;
+        (void)cudaGetLastError();
+    }
+    return n;
+}
 
-int tm_nt(int Cout) { return tc_nt(Cout); }
+int tm_nt(int Cout, int taps) { return tc_nt(Cout, taps); }
 
-bool tm_configure(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout, int ksize, int stride, int up, TmCfg &best) {
+// x3: fp16x2 operands -- a stage holds 2*PL planes and the weights are twice as many rows (conv_tma_kernel<..., X3>)
+bool tm_configure_pl(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout, int ksize, int stride, int up, int x3, int force_pl, TmCfg &best);
+
+bool tm_configure(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout, int ksize, int stride, int up, int x3, TmCfg &best) {
+    if (tm_configure_pl(B, H, W, C0, C1, S0, S1, Cout, ksize, stride, up, x3, 0, best)) return true;
+    // the preferred K-chunk width does not fit (wide layers whose weight stage alone is > 100 KB): halve it
+    return !x3 && tm_configure_pl(B, H, W, C0, C1, S0, S1, Cout, ksize, stride, up, x3, 2, best);
+}
+
+bool tm_configure_pl(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout, int ksize, int stride, int up, int x3, int force_pl, TmCfg &best) {
+    const int X = x3 ? 2 : 1;
+    const int kTmNumSMs = tm_num_sms();
     const int Cin = C0 + C1, Sk = S0 + S1;
     if (Cin <= 0 || (C0 % 16) || (C1 % 16) || (S0 % 16) || (S1 % 16)) return false;
     const int pad = ksize / 2, taps = up ? 16 : ksize * ksize;  // up: H, W are the LOW-resolution (tile space) size
     const int nsub = up ? 4 : 1;                                 // accumulator sets per M block (output parities)
     const int CoutP = (Cout + 15) / 16 * 16;
     TmCfg c{};
-    c.NT = tm_nt(Cout);
+    c.NT = tm_nt(Cout, taps);
     c.n_cc = CoutP / c.NT;
     const bool all32 = !(C0 % 32) && !(C1 % 32) && !(S0 % 32) && !(S1 % 32);
     c.PL = all32 ? 4 : 2;
@@ -550,6 +669,8 @@ bool tm_configure(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout,
     // chunks of 16 channels: smaller stages allow taller tiles (less halo) -- measured 33.0 -> 27.6 us (64->32 @128x256, B = 8),
     // 43.4 -> 39.7 us (96->32 @64x64, B = 64); on the full-resolution level it is 1-5 % slower, so not there
     if (env_pl == 0 && W >= 64 && (long long)B * H * W <= 524288) c.PL = 2;
+    if (x3) c.PL = 2;  // fp16x2: 16 channels = 4 planes per stage, the only instantiation
+    if (force_pl) c.PL = force_pl;
     const int KC = 8 * c.PL;
     c.n_main = Cin / KC;
     c.n_skip = Sk / KC;
@@ -560,11 +681,11 @@ bool tm_configure(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout,
     if (2 * c.P > 256) return false;  // TMA box limit (8-byte elements)
     c.magicP = uint32_t(((1u << 20) + c.P - 1) / c.P);
     c.tiles_x = (W + c.Wt - 1) / c.Wt;
-    c.w_main_bytes = uint32_t(size_t(Cin) * taps * c.NT * 2);
-    c.w_skip_bytes = uint32_t(size_t(Sk) * c.NT * 2);
+    c.w_main_bytes = uint32_t(size_t(Cin) * taps * c.NT * 2 * X);
+    c.w_skip_bytes = uint32_t(size_t(Sk) * c.NT * 2 * X);
     const size_t w_total = size_t(c.w_main_bytes) + c.w_skip_bytes;
     c.resident = (c.n_cc == 1 && w_total <= kTmResidentMax) ? 1 : 0;
-    c.w_stage = c.resident ? 0u : uint32_t(c.PL * taps * c.NT * 16);
+    c.w_stage = c.resident ? 0u : uint32_t(c.PL * taps * c.NT * 16 * X);
     const size_t slack = (size_t(128 + 2 * pad * c.P + 2 * pad) * 16 + 127) & ~size_t(127);
     const size_t fixed = sizeof(float) * (2 * size_t(Cin) + c.NT + size_t(TM_EPI_WARPS) * CoutP * 2) + (3 * MAX_STAGES + 5) * 8 + 64 + 16 * size_t(Cin) + 16 + slack +
                          (c.resident ? w_total : 0) + 1024;
@@ -578,7 +699,7 @@ bool tm_configure(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout,
         for (int q = 0; q < NQ + 256; ++q)
             if (int((uint32_t(q) * c.magicP) >> 20) != q / c.P) magic_ok = false;
         if (!magic_ok) continue;
-        const size_t blk = (size_t(c.PL) * NQ * 16 + 127) & ~size_t(127);  // one TMA box (128-byte aligned destination)
+        const size_t blk = (size_t(X * c.PL) * NQ * 16 + 127) & ~size_t(127);  // one TMA box (128-byte aligned destination)
         const size_t a_stage = (s2 ? 4 : 1) * blk;
         if (fixed + 2 * (a_stage + c.w_stage) > kTmSmemBudget) break;
         int NS = int((kTmSmemBudget - fixed) / (a_stage + c.w_stage));
@@ -591,7 +712,7 @@ bool tm_configure(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout,
         const long long per_cta = (items + grid - 1) / grid;
         // transform work per item (window positions x channels, skip chunks are only copied) + M-block padding
         // + a fixed per-item hand-off cost
-        const double item_cost = double(NQ) * (Cin + 0.25 * Sk) + double(MB * 128) * (0.15 * (Cin + Sk)) + 3000.0;
+        const double item_cost = double(NQ) * (Cin + 0.25 * Sk) + double(MB * 128) * (0.15 * X * (Cin + Sk)) + 3000.0;
         double cost = double(per_cta) * item_cost;
         if (NS < 3) cost *= 1.5;
         else if (NS < 4) cost *= 1.1;
@@ -624,8 +745,9 @@ bool tm_configure(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout,
 }
 
 bool tm_configure_op(const ccdm_op &op, TmCfg &c) {
-    if (op.upsample) return tm_configure(op.B, op.Hin, op.Win, op.C0, op.C1, op.S0, op.S1, op.Cout, op.ksize, op.stride, 1, c);
-    return tm_configure(op.B, op.Hout, op.Wout, op.C0, op.C1, op.S0, op.S1, op.Cout, op.ksize, op.stride, 0, c);
+    const int x3 = op.dtype == CCDM_DT_F16X2;
+    if (op.upsample) return tm_configure(op.B, op.Hin, op.Win, op.C0, op.C1, op.S0, op.S1, op.Cout, op.ksize, op.stride, 1, x3, c);
+    return tm_configure(op.B, op.Hout, op.Wout, op.C0, op.C1, op.S0, op.S1, op.Cout, op.ksize, op.stride, 0, x3, c);
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
@@ -646,6 +768,7 @@ EncodeTiledFn encode_fn() {
 
 // Tensor map of a plane-major bf16 activation [B][C/8][H][W][8], viewed as 8-byte elements so that a
 // window row is ONE contiguous run of the innermost dimension: dims {2W, H, C/8, B}, box {2P, RW, PL, 1}.
+// (fp16x2 tensors have two planes per 8-channel group: the callers pass C = 2 x channels and PL = 2 x groups per chunk)
 int make_map(CUtensorMap *m, const void *base, int B, int C, int H, int W, int P, int RW, int PL) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) CCDM_FAIL(-5, "conv_tma: cuTensorMapEncodeTiled is not available from this driver");
@@ -686,17 +809,22 @@ int conv_tma_read_trace(unsigned long long *out, int n) {
     return m;
 }
 
+int conv_tc_nt(int Cout, int taps) { return tm_nt(Cout, taps); }
+
 bool conv_tma_supported(const ccdm_op &op) {
-    if (op.dtype != CCDM_DT_BF16 || op.src_kind != 0) return false;
+    if ((op.dtype != CCDM_DT_BF16 && op.dtype != CCDM_DT_F16X2) || op.src_kind != 0) return false;
+    const bool x3 = op.dtype == CCDM_DT_F16X2;
+    if (x3 && (op.res || (op.out_dtype != CCDM_DT_F16X2 && op.out_dtype != CCDM_DT_F32))) return false;
+    if (!x3 && op.out_dtype == CCDM_DT_F16X2) return false;
     if (op.ksize != 1 && op.ksize != 3) return false;
     if (op.upsample) {  // Upsample (unet.py:106-116): nearest x2 + 3x3, no norm, no skip, single source
         if (op.ksize != 3 || op.stride != 1 || op.gn || op.silu || op.S0 || op.C1 || op.res) return false;
-        if (op.Hout != 2 * op.Hin || op.Wout != 2 * op.Win || (op.Cout % 16) || op.out_dtype != CCDM_DT_BF16) return false;
+        if (op.Hout != 2 * op.Hin || op.Wout != 2 * op.Win || (op.Cout % 16) || op.out_dtype != op.dtype) return false;
         TmCfg cu;
         return tm_configure_op(op, cu);
     }
     if ((op.C0 % 16) || (op.C1 % 16) || (op.S0 % 16) || (op.S1 % 16)) return false;
-    if (op.out_dtype == CCDM_DT_BF16 && (op.Cout % 16)) return false;
+    if (op.out_dtype != CCDM_DT_F32 && (op.Cout % 16)) return false;
     if (op.stride == 2) {  // Downsample (unet.py:136-139): 3x3, no norm, no skip, single source
         if (op.ksize != 3 || op.gn || op.silu || op.S0 || op.C1) return false;
         if (op.Hout != (op.Hin + 1) / 2 || op.Wout != (op.Win + 1) / 2) return false;
@@ -729,6 +857,10 @@ size_t conv_tma_part_floats(const ccdm_op &op) {
     return size_t(op.B) * c.slots * ((op.Cout + 15) / 16 * 16) * 2;
 }
 
+// fp16x2 instruction descriptor / bf16: cute::UMMA::InstrDescriptor -- D = f32 (bit 4), A and B formats at bits 7 and 10
+// (0 = f16, 1 = bf16), K-major both, N >> 3 at bit 17, M >> 4 at bit 24
+static uint32_t tm_idesc(int NT, bool f16) { return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | (uint32_t(NT >> 3) << 17) | (uint32_t(128 >> 4) << 24); }
+
 int launch_conv_tma(const ccdm_op &op, cudaStream_t s) {
     TmCfg c;
     if (!conv_tma_supported(op) || !tm_configure_op(op, c)) CCDM_FAIL(-3, "conv_tma: unsupported configuration");
@@ -739,7 +871,7 @@ int launch_conv_tma(const ccdm_op &op, cudaStream_t s) {
     p.gamma = (const float *)op.gamma; p.beta = (const float *)op.beta;
     p.weight = (const __nv_bfloat16 *)op.weight; p.bias = (const float *)op.bias; p.emb = (const float *)op.emb;
     p.skip0 = (const __nv_bfloat16 *)op.skip0; p.skip1 = (const __nv_bfloat16 *)op.skip1;
-    p.skip_w = (const __nv_bfloat16 *)op.skip_w; p.res = (const __nv_bfloat16 *)op.res;
+    p.skip_w = (const __nv_bfloat16 *)op.skip_w; p.res = (const __nv_bfloat16 *)op.res;  // (fp16 data in fp16x2 mode: the kernel only moves 16-byte rows)
     p.out = (void *)op.out; p.ostat = (double *)op.ostat; p.part = (float *)op.part; p.ticket = (unsigned int *)op.ticket;
     p.steps = (const ccdm_step_entry *)op.steps; p.step_ptr = (const int *)op.step_ptr;
     p.B = op.B; p.Hin = op.Hin; p.Win = op.Win;
@@ -764,11 +896,15 @@ int launch_conv_tma(const ccdm_op &op, cudaStream_t s) {
         p.st_slots[i] = op.st_slots[i]; p.st_ips[i] = op.st_ips[i]; p.st_items[i] = op.st_items[i];
         p.st_grid[i] = op.st_grid[i]; p.st_rows[i] = op.st_rows[i];
     }
-    p.blk16 = uint32_t(((size_t(c.PL) * c.NQ * 16 + 127) & ~size_t(127)) >> 4);
+    p.blk16 = uint32_t(((size_t((op.dtype == CCDM_DT_F16X2 ? 2 : 1) * c.PL) * c.NQ * 16 + 127) & ~size_t(127)) >> 4);
     p.a_stage = c.a_stage; p.w_stage = c.w_stage; p.w_main_bytes = c.w_main_bytes; p.w_skip_bytes = c.w_skip_bytes;
     p.magicP = c.magicP;
-    // cute::UMMA::InstrDescriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major both, N>>3 at 17, M>>4 at 24
-    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(c.NT >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+    const bool x3 = op.dtype == CCDM_DT_F16X2;
+    const int X = x3 ? 2 : 1;
+    p.idesc = tm_idesc(c.NT, x3);
+    p.x3 = x3 ? 1 : 0;
+    p.descale = x3 ? float(ldexp(1.0, -op.acc_shift)) : 1.0f;
+    if (x3 && (op.acc_shift < CCDM_F16X2_SCALE_LOG2 || op.acc_shift > 40)) CCDM_FAIL(-2, "conv_tma: fp16x2 op without a valid acc_shift (%d)", op.acc_shift);
 
     if (op.gn && (!op.stat0 || (op.C1 && !op.stat1) || !op.gamma || !op.beta)) CCDM_FAIL(-2, "conv_tma: gn without stats/affine");
     if (op.gn && (p.Cin % kGnGroups)) CCDM_FAIL(-2, "conv_tma: GroupNorm needs Cin %% 32 == 0");
@@ -782,11 +918,11 @@ int launch_conv_tma(const ccdm_op &op, cudaStream_t s) {
     if (!op.src0 || (op.C1 && !op.src1) || (op.S1 && !op.skip1)) CCDM_FAIL(-2, "conv_tma: missing source tensor");
 
     const int mapH = op.upsample ? op.Hin : op.Hout, mapW = op.upsample ? op.Win : op.Wout;
-    int rc = op.stride == 2 ? make_map_s2(&P.map[0], (const void *)op.src0, op.B, op.C0, op.Hin, op.Win, c.P, c.RW, c.PL)
-                            : make_map(&P.map[0], (const void *)op.src0, op.B, op.C0, mapH, mapW, c.P, c.RW, c.PL);
-    if (rc == 0 && op.C1) rc = make_map(&P.map[1], (const void *)op.src1, op.B, op.C1, op.Hout, op.Wout, c.P, c.RW, c.PL);
-    if (rc == 0 && op.S0) rc = make_map(&P.map[2], (const void *)op.skip0, op.B, op.S0, op.Hout, op.Wout, c.P, c.RW, c.PL);
-    if (rc == 0 && op.S1) rc = make_map(&P.map[3], (const void *)op.skip1, op.B, op.S1, op.Hout, op.Wout, c.P, c.RW, c.PL);
+    int rc = op.stride == 2 ? make_map_s2(&P.map[0], (const void *)op.src0, op.B, X * op.C0, op.Hin, op.Win, c.P, c.RW, X * c.PL)
+                            : make_map(&P.map[0], (const void *)op.src0, op.B, X * op.C0, mapH, mapW, c.P, c.RW, X * c.PL);
+    if (rc == 0 && op.C1) rc = make_map(&P.map[1], (const void *)op.src1, op.B, X * op.C1, op.Hout, op.Wout, c.P, c.RW, X * c.PL);
+    if (rc == 0 && op.S0) rc = make_map(&P.map[2], (const void *)op.skip0, op.B, X * op.S0, op.Hout, op.Wout, c.P, c.RW, X * c.PL);
+    if (rc == 0 && op.S1) rc = make_map(&P.map[3], (const void *)op.skip1, op.B, X * op.S1, op.Hout, op.Wout, c.P, c.RW, X * c.PL);
     if (rc != 0) return rc;
 
     static bool attr_done = false;
@@ -797,13 +933,23 @@ int launch_conv_tma(const ccdm_op &op, cudaStream_t s) {
         CCDM_CUDA(opt_in(conv_tma_kernel<4, false, true, 2>)); CCDM_CUDA(opt_in(conv_tma_kernel<2, false, true, 2>));
         CCDM_CUDA(opt_in(conv_tma_kernel<4, false, false, 3>)); CCDM_CUDA(opt_in(conv_tma_kernel<2, false, false, 3>));
         CCDM_CUDA(opt_in(conv_tma_kernel<4, true, true, 0>)); CCDM_CUDA(opt_in(conv_tma_kernel<2, true, true, 0>));
+        CCDM_CUDA(opt_in(conv_tma_kernel<2, false, true, 0, true>)); CCDM_CUDA(opt_in(conv_tma_kernel<2, false, true, 1, true>));
+        CCDM_CUDA(opt_in(conv_tma_kernel<2, false, true, 2, true>)); CCDM_CUDA(opt_in(conv_tma_kernel<2, false, false, 3, true>));
+        CCDM_CUDA(opt_in(conv_tma_kernel<2, true, true, 0, true>));
         attr_done = true;
     }
-    const bool lean = op.out_dtype == CCDM_DT_BF16 && !op.res;  // no fp32 store, no epilogue residual: the lean epilogue
+    const bool lean = op.out_dtype != CCDM_DT_F32 && !op.res;  // no fp32 store, no epilogue residual: the lean epilogue
     const int xf_kind = !(op.gn || op.silu) ? 0 : (op.silu ? 1 : 2);
     const bool pl4 = c.PL == 4;
     void (*kern)(TmP) = nullptr;
-    if (op.upsample) kern = pl4 ? conv_tma_kernel<4, true, true, 0> : conv_tma_kernel<2, true, true, 0>;
+    if (x3) {
+        if (c.PL != 2) CCDM_FAIL(-3, "conv_tma: fp16x2 kernels are instantiated for 16-channel K chunks only");
+        if (op.upsample) kern = conv_tma_kernel<2, true, true, 0, true>;
+        else if (!lean) kern = conv_tma_kernel<2, false, false, 3, true>;
+        else if (xf_kind == 0) kern = conv_tma_kernel<2, false, true, 0, true>;
+        else if (xf_kind == 1) kern = conv_tma_kernel<2, false, true, 1, true>;
+        else kern = conv_tma_kernel<2, false, true, 2, true>;
+    } else if (op.upsample) kern = pl4 ? conv_tma_kernel<4, true, true, 0> : conv_tma_kernel<2, true, true, 0>;
     else if (!lean) kern = pl4 ? conv_tma_kernel<4, false, false, 3> : conv_tma_kernel<2, false, false, 3>;
     else if (xf_kind == 0) kern = pl4 ? conv_tma_kernel<4, false, true, 0> : conv_tma_kernel<2, false, true, 0>;
     else if (xf_kind == 1) kern = pl4 ? conv_tma_kernel<4, false, true, 1> : conv_tma_kernel<2, false, true, 1>;

@@ -1,6 +1,6 @@
 // Small kernels around the reverse step: the timestep-embedding table, layout
 // converters at the chain boundary, label <-> one-hot conversion.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace ccdm {
 namespace {
@@ -89,7 +89,7 @@ __global__ void labels_to_onehot_i64_kernel(const uint8_t *__restrict__ labels, 
 // chain on the feature condition, so its cost and (tiny) order non-determinism in
 // the 17th digit of a double do not matter; the sums are rounded through the same
 // double -> float path every step.
-template <typename T>
+template <typename T, bool X3 = false>
 __global__ void __launch_bounds__(256) nchw_to_nhwc_stats_kernel(const float *__restrict__ src, int C, int HW, T *__restrict__ dst,
                                                                  double *__restrict__ stat) {
     __shared__ float tile[32][33];
@@ -105,7 +105,15 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_stats_kernel(const float *__
         int p = p0 + j, c = c0 + tx;
         if (p < HW && c < C) {
             float v = tile[tx][j];
-            if (sizeof(T) == 2) {
+            if (X3) {
+                // fp16x2 [B][C/8][2][HW][8]: hi plane then lo plane of every 8-channel group; the statistics describe
+                // the fp32 value (hi + lo reproduces it to 2^-23)
+                uint32_t hi, lo;
+                split_f16x2(v, 0.f, hi, lo);
+                __half *d = reinterpret_cast<__half *>(dst) + ((size_t(b) * (C >> 3) + (c >> 3)) * 2 * HW + p) * 8 + (c & 7);
+                d[0] = __ushort_as_half(static_cast<unsigned short>(hi & 0xFFFFu));
+                d[size_t(HW) * 8] = __ushort_as_half(static_cast<unsigned short>(lo & 0xFFFFu));
+            } else if (sizeof(T) == 2) {
                 __nv_bfloat16 h = __float2bfloat16_rn(v);
                 // bf16 activations are plane-major [B][C/8][HW][8]
                 reinterpret_cast<__nv_bfloat16 *>(dst)[((size_t(b) * (C >> 3) + (c >> 3)) * HW + p) * 8 + (c & 7)] = h;
@@ -134,6 +142,8 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_stats_kernel(const float *__
 
 // one-hot(labels) ++ image -> plane-major bf16 [B][CP/8][HW][8], CP = ceil16(K + C_img), zero padded.
 // One thread per (pixel, plane): consecutive threads write consecutive 16-byte rows.
+// X3: fp16x2 [B][CP/8][2][HW][8] -- one thread writes the hi row and the lo row of its (pixel, group).
+template <bool X3>
 __global__ void __launch_bounds__(256) encode_input_kernel(const uint8_t *__restrict__ labels, const float *__restrict__ image, int K,
                                                            int C_img, int planes, size_t HW, size_t total, __nv_bfloat16 *__restrict__ out) {
     const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -145,7 +155,7 @@ __global__ void __launch_bounds__(256) encode_input_kernel(const uint8_t *__rest
     const int g = int(bg % planes);
     const size_t b = bg / planes;
     const int lab = labels[b * HW + pix];
-    uint32_t pk[4];
+    uint32_t pk[4], pl[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         float v[2];
@@ -154,22 +164,33 @@ __global__ void __launch_bounds__(256) encode_input_kernel(const uint8_t *__rest
             const int c = g * 8 + 2 * j + e;
             v[e] = c < K ? (c == lab ? 1.f : 0.f) : (c < K + C_img ? image[(b * C_img + (c - K)) * HW + pix] : 0.f);
         }
-        __nv_bfloat162 h = __floats2bfloat162_rn(v[0], v[1]);
-        pk[j] = *reinterpret_cast<uint32_t *>(&h);
+        if (X3) {
+            split_f16x2(v[0], v[1], pk[j], pl[j]);
+        } else {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[0], v[1]);
+            pk[j] = *reinterpret_cast<uint32_t *>(&h);
+        }
     }
-    *reinterpret_cast<uint4 *>(out + i * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    if (X3) {
+        __nv_bfloat16 *o = out + ((b * planes + g) * 2 * HW + pix) * 8;
+        *reinterpret_cast<uint4 *>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4 *>(o + HW * 8) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    } else {
+        *reinterpret_cast<uint4 *>(out + i * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
 }
 
 }  // namespace
 
 int launch_encode_input(const ccdm_op &op, cudaStream_t s) {
     const int CP = op.Cout;
-    if (op.dtype != CCDM_DT_BF16 || (CP % 16) || CP < op.K + op.C_img || op.K < 1) CCDM_FAIL(-2, "encode_input: bad channel counts");
+    const bool x3 = op.dtype == CCDM_DT_F16X2;
+    if ((op.dtype != CCDM_DT_BF16 && !x3) || (CP % 16) || CP < op.K + op.C_img || op.K < 1) CCDM_FAIL(-2, "encode_input: bad channel counts");
     if (!op.labels_in || !op.image || !op.out) CCDM_FAIL(-2, "encode_input: missing tensors");
     const size_t HW = size_t(op.Hin) * op.Win, total = size_t(op.B) * (CP / 8) * HW;
     if (total == 0) return 0;
-    CCDM_CUDA(launch_pdl(encode_input_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), 0, s, (const uint8_t *)op.labels_in,
-                         (const float *)op.image, op.K, op.C_img, CP / 8, HW, total, (__nv_bfloat16 *)op.out));
+    CCDM_CUDA(launch_pdl(x3 ? encode_input_kernel<true> : encode_input_kernel<false>, dim3(unsigned((total + 255) / 256)), dim3(256), 0, s,
+                         (const uint8_t *)op.labels_in, (const float *)op.image, op.K, op.C_img, CP / 8, HW, total, (__nv_bfloat16 *)op.out));
     CCDM_LAUNCH_CHECK("encode_input_kernel");
     return 0;
 }
@@ -214,7 +235,9 @@ extern "C" int ccdm_nchw_to_nhwc_stats(const float *src, int B, int C, int H, in
     CCDM_CUDA(cudaMemsetAsync(stat, 0, sizeof(double) * 2 * size_t(B) * C, s));
     const int HW = H * W;
     dim3 grid((HW + 31) / 32, (C + 31) / 32, B);
-    if (dtype == CCDM_DT_BF16)
+    if (dtype == CCDM_DT_F16X2)
+        nchw_to_nhwc_stats_kernel<__nv_bfloat16, true><<<grid, 256, 0, s>>>(src, C, HW, (__nv_bfloat16 *)dst, stat);
+    else if (dtype == CCDM_DT_BF16)
         nchw_to_nhwc_stats_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(src, C, HW, (__nv_bfloat16 *)dst, stat);
     else
         nchw_to_nhwc_stats_kernel<float><<<grid, 256, 0, s>>>(src, C, HW, (float *)dst, stat);

@@ -70,19 +70,19 @@ extern "C" size_t ccdm_sizeof_step_entry(void) { return sizeof(ccdm_step_entry);
 namespace ccdm { size_t conv_part_floats(int B, int Hout, int Wout, int Cout); }
 extern "C" size_t ccdm_conv_part_floats(int B, int Hout, int Wout, int Cout) { return ccdm::conv_part_floats(B, Hout, Wout, Cout); }
 
-namespace ccdm { bool conv_uses_tc(const ccdm_op &op); size_t op_part_floats(const ccdm_op &op); int conv_tc_nt(int Cout); }
+namespace ccdm { bool conv_uses_tc(const ccdm_op &op); size_t op_part_floats(const ccdm_op &op); int conv_tc_nt(int Cout, int taps); }
 extern "C" int ccdm_conv_uses_tc(const ccdm_op *op) { return op && ccdm::conv_uses_tc(*op) ? 1 : 0; }
-extern "C" int ccdm_conv_tc_nt(int Cout) { return ccdm::conv_tc_nt(Cout); }
-namespace ccdm { int conv_tc_config(const ccdm_op &op, int32_t *out); int conv_tma_config(const ccdm_op &op, int32_t *out); bool conv_uses_tma(const ccdm_op &op); }
+extern "C" int ccdm_conv_tc_nt(int Cout, int taps) { return ccdm::conv_tc_nt(Cout, taps); }
+namespace ccdm { int conv_tma_config(const ccdm_op &op, int32_t *out); bool conv_uses_tma(const ccdm_op &op); }
 extern "C" int ccdm_conv_tc_config(const ccdm_op *op, int32_t *out16) {
-    if (!op || !out16) return -1;
-    return ccdm::conv_uses_tma(*op) ? ccdm::conv_tma_config(*op, out16) : ccdm::conv_tc_config(*op, out16);
+    if (!op || !out16 || !ccdm::conv_uses_tma(*op)) return -1;
+    return ccdm::conv_tma_config(*op, out16);
 }
 extern "C" int ccdm_conv_uses_tma(const ccdm_op *op) { return op && ccdm::conv_uses_tma(*op) ? 1 : 0; }
-namespace ccdm { int conv_tma_stat_layout(const ccdm_op &op, int32_t *out5); int conv_tc_stat_layout(const ccdm_op &op, int32_t *out5); }
+namespace ccdm { int conv_tma_stat_layout(const ccdm_op &op, int32_t *out5); }
 extern "C" int ccdm_conv_stat_layout(const ccdm_op *op, int32_t *out5) {
     if (!op || !out5 || !ccdm::conv_uses_tc(*op)) return -1;
-    return ccdm::conv_uses_tma(*op) ? ccdm::conv_tma_stat_layout(*op, out5) : ccdm::conv_tc_stat_layout(*op, out5);
+    return ccdm::conv_tma_stat_layout(*op, out5);
 }
 extern "C" size_t ccdm_op_part_floats(const ccdm_op *op) { return op ? ccdm::op_part_floats(*op) : 0; }
 

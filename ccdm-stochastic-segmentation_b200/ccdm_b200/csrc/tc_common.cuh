@@ -1,6 +1,8 @@
 // PTX wrappers shared by the tcgen05 kernels (sm_100a): mbarrier, TMA (bulk and tensor), TMEM, UMMA.
 #pragma once
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace ccdm {
@@ -175,6 +177,28 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
     return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xFFFF0000u));
 }
+
+// ---- fp16x2 ("exact" tensor-core mode, CCDM_DT_F16X2): v is carried as hi = fp16(16 v), lo = fp16(16 v - hi) ------
+// Two values -> packed hi pair and packed lo pair (element 0 in the low half).  satfinite: |16 v| > 65504 clamps
+// instead of producing inf (inf - inf in the lo term would poison an MMA).
+__device__ __forceinline__ uint32_t cvt_f16x2_sat(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t u) {
+    return __half22float2(*reinterpret_cast<const __half2 *>(&u));
+}
+__device__ __forceinline__ void split_f16x2_raw(float a, float b, uint32_t &hi, uint32_t &lo) {  // values already scaled
+    hi = cvt_f16x2_sat(a, b);
+    const float2 h = unpack_f16x2(hi);
+    lo = cvt_f16x2_sat(a - h.x, b - h.y);
+}
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t &hi, uint32_t &lo) {
+    const float s = float(1 << CCDM_F16X2_SCALE_LOG2);
+    split_f16x2_raw(a * s, b * s, hi, lo);
+}
+// same MMA for fp16 operands is umma_bf16_split with an fp16 instruction descriptor (kind::f16 covers both)
 
 // Transpose-reduce: on entry every lane holds 16 per-channel partial sums; on exit lane l holds
 // the warp total of channel ((l>>4)&1)*8 + ((l>>3)&1)*4 + ((l>>2)&1)*2 + ((l>>1)&1) (both lanes

@@ -18,8 +18,10 @@ torch is used for device memory, streams and the global generator (noise parity
 with the reference) only.
 """
 import ctypes
+import logging
 import math
 import os
+from collections import OrderedDict
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
 
@@ -29,6 +31,14 @@ from . import _lib
 from ._lib import Op, StepEntry
 
 ALIGN = 256
+LOGGER = logging.getLogger(__name__)
+
+# precision modes of the engine -> (activation storage CCDM_DT_*, bytes per stored element, tensor-core kernels?)
+#   fp32  : NHWC fp32, FFMA kernels                      (the in-library reference every other mode is tested against)
+#   exact : fp16x2 (hi + lo planes), tcgen05 3-MMA split  (fp32-grade products at tensor-core speed; the default)
+#   bf16  : bf16 planes, tcgen05                           (fast mode)
+PRECISIONS = {"fp32": (_lib.DT_F32, 4, False), "exact": (_lib.DT_F16X2, 4, True), "bf16": (_lib.DT_BF16, 2, True)}
+PROGRAM_CACHE = 4  # programs (workspaces of ~1 GB at the benchmark shapes) kept per engine, least recently used first out
 
 
 def _ceil(a, b):
@@ -46,6 +56,7 @@ class Ten:
     W: int
     esize: int            # bytes per element
     want_stat: bool
+    fmt: int = 0          # CCDM_DT_* storage format
     nbytes: int = 0
     off: int = -1         # byte offset in the activation arena
     stat_off: int = -1    # byte offset in the stat arena
@@ -109,7 +120,7 @@ def pack_conv_weight_tc(w: torch.Tensor, nt: Optional[int] = None) -> torch.Tens
     co, ci, kh, kw = w.shape
     assert ci % 8 == 0
     if nt is None:
-        nt = int(_lib.lib().ccdm_conv_tc_nt(co))
+        nt = int(_lib.lib().ccdm_conv_tc_nt(co, kh * kw))
     cop = _ceil(co, 16)
     assert cop % nt == 0
     taps = kh * kw
@@ -117,6 +128,49 @@ def pack_conv_weight_tc(w: torch.Tensor, nt: Optional[int] = None) -> torch.Tens
     full[:co] = w.float().reshape(co, ci, taps)
     out = full.reshape(cop // nt, nt, ci // 8, 8, taps).permute(0, 2, 4, 1, 3).contiguous()
     return out.to(torch.bfloat16)
+
+
+def split_f16x2(x: torch.Tensor, scale_log2: int = _lib.F16X2_SCALE_LOG2):
+    """fp32 -> (hi, lo) fp16 with hi + lo == 2^scale_log2 * x to 2^-23 relative (CCDM_DT_F16X2), saturating like the kernels."""
+    y = (x.float() * float(2 ** scale_log2)).clamp(-65504.0, 65504.0)
+    hi = y.to(torch.float16)
+    lo = (y - hi.float()).to(torch.float16)
+    return hi, lo
+
+
+def pack_conv_weight_x3(w: torch.Tensor, shift: int, nt: Optional[int] = None) -> torch.Tensor:
+    """OIHW (or OI1) -> the fp16x2 tensor-core layout [cc][Cin/8][tap][2][NT][8] fp16 of 2^shift * w: per (chunk, 8-channel
+    plane, tap) the NT hi rows, then the NT lo rows."""
+    if w.dim() == 3:
+        w = w[:, :, :, None]
+    co, ci, kh, kw = w.shape
+    assert ci % 8 == 0
+    if nt is None:
+        nt = int(_lib.lib().ccdm_conv_tc_nt(co, kh * kw))
+    cop = _ceil(co, 16)
+    assert cop % nt == 0
+    taps = kh * kw
+    full = torch.zeros(cop, ci, taps, dtype=torch.float32, device=w.device)
+    full[:co] = w.float().reshape(co, ci, taps)
+    hi, lo = split_f16x2(full, shift)
+    both = torch.stack([hi, lo], 0)  # [2, cop, ci, taps]
+    return both.reshape(2, cop // nt, nt, ci // 8, 8, taps).permute(1, 3, 5, 0, 2, 4).contiguous()
+
+
+def to_pm_x3(x_nhwc: torch.Tensor) -> torch.Tensor:
+    """NHWC fp32 [B,H,W,C] -> fp16x2 plane-major [B, C/8, 2, H, W, 8] (contiguous)."""
+    B, H, W, C = x_nhwc.shape
+    assert C % 8 == 0
+    hi, lo = split_f16x2(x_nhwc)
+    both = torch.stack([hi, lo], -1).reshape(B, H, W, C // 8, 8, 2)
+    return both.permute(0, 3, 5, 1, 2, 4).contiguous()
+
+
+def from_pm_x3(x: torch.Tensor) -> torch.Tensor:
+    """fp16x2 plane-major [B, C/8, 2, H, W, 8] -> NHWC fp32 [B,H,W,C] = (hi + lo) / 16."""
+    B, G, _, H, W, _ = x.shape
+    v = (x[:, :, 0].float() + x[:, :, 1].float()) * (1.0 / float(2 ** _lib.F16X2_SCALE_LOG2))
+    return v.permute(0, 2, 3, 1, 4).reshape(B, H, W, G * 8).contiguous()
 
 
 def to_pm(x_nhwc: torch.Tensor) -> torch.Tensor:
@@ -163,13 +217,15 @@ def pack_bias(b: torch.Tensor) -> torch.Tensor:
 class PackedWeights:
     """All kernel-layout parameters in one flat fp32 device buffer with stable addresses."""
 
-    def __init__(self, unet, device, with_tc: bool = False):
+    def __init__(self, unet, device, with_tc: bool = False, x3: bool = False):
         self.unet = unet
         self.device = device
         self.slots: Dict[str, tuple] = {}  # name -> (offset_floats, numel)
         self.total = 0
         self.buf: Optional[torch.Tensor] = None
-        self.with_tc = with_tc            # also keep bf16 tensor-core layouts of every stride-1 conv
+        self.with_tc = with_tc            # also keep tensor-core layouts of every conv (bf16, or fp16 hi + lo rows when x3)
+        self.x3 = x3
+        self.shift = 0                    # x3: the packed weights are 2^shift * w (one power of two for the whole model)
         self.slots16: Dict[str, tuple] = {}
         self.total16 = 0
         self.buf16: Optional[torch.Tensor] = None
@@ -181,7 +237,7 @@ class PackedWeights:
         self.total += _ceil(numel, ALIGN // 4)
         if tc_shape is not None and self.with_tc:
             taps, ci, co = tc_shape
-            n16 = taps * ci * _ceil(co, 16)
+            n16 = taps * ci * _ceil(co, 16) * (2 if self.x3 else 1)
             self.slots16[name] = (self.total16, n16)
             self.total16 += _ceil(n16, ALIGN // 2)
 
@@ -243,8 +299,17 @@ class PackedWeights:
             return False
         if self.buf is None:
             self.buf = torch.zeros(self.total, dtype=torch.float32, device=self.device)
-            self.buf16 = torch.zeros(max(self.total16, 8), dtype=torch.bfloat16, device=self.device)
+            self.buf16 = torch.zeros(max(self.total16, 8), dtype=torch.float16 if self.x3 else torch.bfloat16, device=self.device)
         sd = {k: v.detach().to(device=self.device, dtype=torch.float32) for k, v in self.unet.state_dict().items()}
+        if self.x3:
+            # one power-of-two scale for every packed weight, as large as fp16 allows (|2^shift w| <= 2^15; the sub-pixel
+            # sums of the upsampling convs add up to four taps): the lo parts stay normal numbers, the identity matrices of
+            # the residual chunks are 2^shift exactly, and the epilogue's 2^-acc_shift is exact
+            wmax = 1e-30
+            for k, v in sd.items():
+                if v.dim() >= 3:
+                    wmax = max(wmax, float(v.abs().max()) * (4.0 if k.endswith(".conv.weight") else 1.0))
+            self.shift = int(max(0, min(13, math.floor(math.log2(32768.0 / wmax)))))
 
         def put(name, t, raw=None):
             v = self.view(name)
@@ -252,7 +317,7 @@ class PackedWeights:
             v[:t.numel()].copy_(t.reshape(-1))
             if raw is not None and name in self.slots16:
                 off, n = self.slots16[name]
-                tc = pack_conv_weight_tc(raw).reshape(-1)
+                tc = (pack_conv_weight_x3(raw, self.shift) if self.x3 else pack_conv_weight_tc(raw)).reshape(-1)
                 assert tc.numel() == n, (name, tc.numel(), n)
                 self.buf16[off:off + n].copy_(tc)
 
@@ -311,9 +376,9 @@ class Program:
         self.B, self.H, self.W = B, H, W
         self.K = unet.out_channels
         self.C_img = unet.in_channels - self.K
-        self.esize = 4 if engine.precision == "fp32" else 2
-        self.dt = _lib.DT_F32 if engine.precision == "fp32" else _lib.DT_BF16
-        self.exact = 1 if engine.precision == "fp32" else 0
+        self.dt, self.esize, tc_mode = PRECISIONS[engine.precision]
+        self.exact = 0 if tc_mode else 1     # ccdm_op::exact of the convs / attention: 1 = FFMA kernels
+        self.x3 = engine.precision == "exact"
         dev = engine.device
         L = _lib.lib()
 
@@ -321,7 +386,7 @@ class Program:
         tens: List[Ten] = []
 
         def new(name, C, h, w, stat=True, esize=None):
-            t = Ten(name, C, h, w, esize or self.esize, stat)
+            t = Ten(name, C, h, w, esize or self.esize, stat, fmt=_lib.DT_F32 if esize == 4 else self.dt)
             t.nbytes = _ceil(B * h * w * C * t.esize, ALIGN)
             tens.append(t)
             return t
@@ -341,7 +406,7 @@ class Program:
         self.feat: Optional[Ten] = None
         fc = unet.feat_channels
         if fc:
-            self.feat = Ten("feature_condition", fc, H // 8, W // 8, self.esize, True, external=True)
+            self.feat = Ten("feature_condition", fc, H // 8, W // 8, self.esize, True, fmt=self.dt, external=True)
 
         hs: List[Ten] = []
         h: Optional[Ten] = None
@@ -379,7 +444,7 @@ class Program:
                              _g=p + ":g2", _be=p + ":be2", _w=p + ":w2", _b=p + ":b2")
                     if Ly.skip_conv:
                         f.update(_skip=srcs, _ws=p + ":ws")
-                    elif self.exact == 0 and _IDENT_SKIP:
+                    elif self.exact == 0 and (_IDENT_SKIP or self.x3):
                         f.update(_skip=[srcs[0]], _ws="ident:%d" % Ly.cout)
                     else:
                         f.update(_res=srcs[0])
@@ -393,7 +458,7 @@ class Program:
                                _w=p + ":wqkv", _b=p + ":bqkv")
                     a = emit(_lib.OP_ATTENTION, [qkv], new(p + ":a", C, ch, cw, stat=False), Hin=ch, Win=cw, Hout=ch, Wout=cw,
                              Cout=C, heads=Ly.heads, head_dim=C // Ly.heads, _src=[qkv])
-                    fr = dict(_skip=[x], _ws="ident:%d" % C) if self.exact == 0 and _IDENT_SKIP else dict(_res=x)
+                    fr = dict(_skip=[x], _ws="ident:%d" % C) if self.exact == 0 and (_IDENT_SKIP or self.x3) else dict(_res=x)
                     h = emit(_lib.OP_CONV, [a, x], new(p, C, ch, cw), ksize=1, stride=1, gn=0, silu=0, Hin=ch, Win=cw, Hout=ch,
                              Wout=cw, Cout=C, _src=[a], _w=p + ":wproj", _b=p + ":bproj", **fr)
                     srcs = [h]
@@ -499,22 +564,61 @@ class Program:
         self._stat_bufs = []
         for t in self.tens.values():
             t.part_addr, t.stat_layout = 0, None
-        arr = (Op * self.n_ops)()
-        for i, o in enumerate(self._op_dicts):
+
+        def base_op(o) -> Op:
+            """Shape / variant fields of an op: everything the kernel dispatch depends on (no statistics, no weights)."""
             f = {k: v for k, v in o.items() if not k.startswith("_")}
             fields = dict(dtype=self.dt, B=self.B, exact=self.exact, out_dtype=self.dt)
             fields.update(f)
             op = Op(**fields)
             src = o.get("_src", [])
-            if o["kind"] in (_lib.OP_INPUT_CONV, _lib.OP_ENCODE_INPUT):
-                op.labels_in = self.addr["labels"]
-                op.image = self.addr["image"]
             if o["kind"] in (_lib.OP_CONV, _lib.OP_ATTENTION):
                 op.src0, op.C0 = src[0].addr, src[0].C
                 if len(src) > 1:
                     op.src1, op.C1 = src[1].addr, src[1].C
+            if "_skip" in o:
+                sk = o["_skip"]
+                op.skip0, op.S0 = sk[0].addr, sk[0].C
+                if len(sk) > 1:
+                    op.skip1, op.S1 = sk[1].addr, sk[1].C
+            if "_res" in o:
+                op.res = o["_res"].addr
+            return op
+
+        # pass 1: which convs land on the tensor-core kernel.  Everything downstream -- weight layout, statistics layout of
+        # the INPUT tensors -- follows from this, so it is decided before anything is bound.
+        use_tc = [bool(self.exact == 0 and o["kind"] == _lib.OP_CONV and L.ccdm_conv_uses_tc(ctypes.byref(base_op(o))))
+                  for o in self._op_dicts]
+        off_tc = [i for i, o in enumerate(self._op_dicts) if self.exact == 0 and o["kind"] == _lib.OP_CONV and not use_tc[i]]
+        if off_tc:
+            what = ", ".join("op %d (%s -> %d ch @%dx%d)" % (i, "+".join(str(t.C) for t in self._op_dicts[i]["_src"]),
+                                                              self._op_dicts[i]["Cout"], self._op_dicts[i]["Hout"], self._op_dicts[i]["Wout"])
+                             for i in off_tc)
+            if self.x3:
+                raise _lib.CcdmError("precision='exact': the tensor-core conv kernel cannot take " + what +
+                                     "; this mode has no other conv kernel (use precision='fp32')")
+            LOGGER.warning("precision='bf16': %d conv(s) do not fit the tensor-core kernel and run on the fp32 FFMA kernel: %s",
+                           len(off_tc), what)
+        self.off_tc = off_tc
+        # a tensor's statistics are left as per-CTA partial rows (deferred fold) only if its producer is a tensor-core conv
+        # AND every GroupNorm consumer is one too: the FFMA kernel reads folded double2 sums
+        gn_readers: Dict[int, List[int]] = {}
+        for i, o in enumerate(self._op_dicts):
+            if o["kind"] == _lib.OP_CONV and o.get("gn"):
+                for sten in o.get("_src", [])[:2]:
+                    gn_readers.setdefault(id(sten), []).append(i)
+
+        arr = (Op * self.n_ops)()
+        for i, o in enumerate(self._op_dicts):
+            op = base_op(o)
+            src = o.get("_src", [])
+            if o["kind"] in (_lib.OP_INPUT_CONV, _lib.OP_ENCODE_INPUT):
+                op.labels_in = self.addr["labels"]
+                op.image = self.addr["image"]
+            if o["kind"] == _lib.OP_CONV and o.get("gn"):
                 for si, sten in enumerate(src[:2]):
                     if sten.stat_layout is not None:  # the producer left per-CTA partial rows: this op folds them
+                        assert use_tc[i]
                         setattr(op, "stat%d" % si, sten.part_addr)
                         for name, v in zip(("st_slots", "st_ips", "st_items", "st_grid", "st_rows"), sten.stat_layout):
                             setattr(op, "%s%d" % (name, si), int(v))
@@ -522,33 +626,32 @@ class Program:
                         setattr(op, "stat%d" % si, sten.stat_addr)
             if "_g" in o:
                 op.gamma, op.beta = W.addr(o["_g"]), W.addr(o["_be"])
-            if "_skip" in o:
-                sk = o["_skip"]
-                op.S0 = sk[0].C
-                if len(sk) > 1:
-                    op.S1 = sk[1].C
-            use_tc = bool(self.exact == 0 and o["kind"] == _lib.OP_CONV and L.ccdm_conv_uses_tc(ctypes.byref(op)))
-            # attention: exact=0 selects the tcgen05 kernel (bf16, head_dim 32); head: exact=0 selects fast maths for sampling steps
-            if not use_tc and o["kind"] not in (_lib.OP_ATTENTION, _lib.OP_HEAD):
+            # attention: exact=0 selects the tcgen05 kernel (head_dim 32); head: exact=0 selects fast maths for sampling steps
+            if o["kind"] == _lib.OP_CONV and not use_tc[i]:
                 op.exact = 1
+            if o["kind"] == _lib.OP_HEAD and self.x3:
+                op.exact = 1  # the exact tensor-core mode draws with the bit-exact posterior arithmetic
+            if use_tc[i] and self.x3:
+                op.acc_shift = W.shift + _lib.F16X2_SCALE_LOG2
             if "_w" in o:
-                op.weight, op.bias = (W.addr16(o["_w"]) if use_tc else W.addr(o["_w"])), W.addr(o["_b"])
+                op.weight, op.bias = (W.addr16(o["_w"]) if use_tc[i] else W.addr(o["_w"])), W.addr(o["_b"])
             if o.get("_emb"):
                 op.emb = self.emb_buf.data_ptr()
                 op.emb_cols = emb_cols
                 op.emb_bstride = self.rows_per_sample
             if "_skip" in o:
-                sk = o["_skip"]
-                op.skip0, op.S0 = sk[0].addr, sk[0].C
-                if len(sk) > 1:
-                    op.skip1, op.S1 = sk[1].addr, sk[1].C
-                op.skip_w = W.addr16(o["_ws"]) if use_tc else W.addr(o["_ws"])
-            if "_res" in o:
-                op.res = o["_res"].addr
+                if not use_tc[i] and o["_ws"].startswith("ident:"):
+                    # identity residual folded into the MMA exists as packed tensor-core weights only: on the FFMA kernel
+                    # the residual is read in the epilogue instead
+                    op.skip0 = op.skip1 = op.S0 = op.S1 = 0
+                    op.res = o["_skip"][0].addr
+                else:
+                    op.skip_w = W.addr16(o["_ws"]) if use_tc[i] else W.addr(o["_ws"])
             out = o["_out"]
             if out is not None:
                 op.out = out.addr
-                if out.want_stat and use_tc:
+                deferred = use_tc[i] and all(use_tc[j] for j in gn_readers.get(id(out), []))
+                if out.want_stat and deferred:
                     # deferred fold: the epilogue only writes its per-CTA partial rows into a buffer owned by the
                     # tensor; the consumers' GroupNorm prologue folds them (no ticket, fence or atomic in the producer)
                     lay = (ctypes.c_int32 * 5)()
@@ -578,7 +681,7 @@ class Program:
         self.part_buf = torch.zeros(part_floats, dtype=torch.float32, device=dev)
         for i in shared:
             arr[i].part = self.part_buf.data_ptr()
-        self.n_tc = sum(1 for i in range(self.n_ops) if arr[i].kind == _lib.OP_CONV and not arr[i].exact)
+        self.n_tc = sum(use_tc)
         self._op_array = arr
         self.plan = L.ccdm_plan_create(arr, self.n_ops)
         if not self.plan:
@@ -612,8 +715,8 @@ class UNetEngine:
     def __init__(self, unet, precision: str = "fp32", dry_run: bool = False):
         """``dry_run``: plan programs with host buffers and never launch (host-logic tests
         on machines without a GPU); any attempt to run raises."""
-        if precision not in ("fp32", "bf16"):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+        if precision not in PRECISIONS:
+            raise ValueError("precision must be one of %s" % sorted(PRECISIONS))
         p0 = next(unet.parameters())
         self.dry_run = dry_run
         if not dry_run:
@@ -623,8 +726,8 @@ class UNetEngine:
         self.unet = unet
         self.precision = precision
         self.device = p0.device
-        self.weights = PackedWeights(unet, self.device, with_tc=(precision == "bf16"))
-        self.programs: Dict[tuple, Program] = {}
+        self.weights = PackedWeights(unet, self.device, with_tc=PRECISIONS[precision][2], x3=(precision == "exact"))
+        self.programs: "OrderedDict[tuple, Program]" = OrderedDict()
         self.stream = None if dry_run else torch.cuda.Stream(device=self.device)
         self.use_graph = True
         # Lanes (experimental, default 1): the batch of a chain is split into `lanes` contiguous sub-batches that run as
@@ -642,7 +745,12 @@ class UNetEngine:
         key = (B, H, W, rows_per_sample)
         prog = self.programs.get(key)
         if prog is None:
+            # bounded cache: a ragged last batch or a change of batch size must not pile up ~1 GB workspaces
+            while len(self.programs) >= PROGRAM_CACHE:
+                self.programs.popitem(last=False)
             prog = self.programs[key] = Program(self, B, H, W, rows_per_sample)
+        else:
+            self.programs.move_to_end(key)
         return prog
 
     def _sp(self):
@@ -731,7 +839,7 @@ class UNetEngine:
         while len(self._children) < n:
             c = UNetEngine.__new__(UNetEngine)
             c.dry_run, c.unet, c.precision, c.device, c.weights = False, self.unet, self.precision, self.device, self.weights
-            c.programs, c.stream, c.use_graph, c.lanes, c._children = {}, torch.cuda.Stream(device=self.device), self.use_graph, 1, []
+            c.programs, c.stream, c.use_graph, c.lanes, c._children = OrderedDict(), torch.cuda.Stream(device=self.device), self.use_graph, 1, []
             self._children.append(c)
         for c in self._children:
             c.use_graph = self.use_graph
@@ -867,11 +975,12 @@ class UNetEngine:
         return out
 
     def tensor_view(self, prog: Program, t: Ten) -> torch.Tensor:
-        """NHWC view (fp32 tensors) or NHWC copy (bf16 tensors, stored plane-major) of a workspace tensor."""
-        dtype = torch.float32 if t.esize == 4 else torch.bfloat16
+        """NHWC view (fp32 tensors) or NHWC copy (bf16 / fp16x2 tensors, stored plane-major) of a workspace tensor."""
         off = t.addr - prog.workspace.data_ptr()
         n = prog.B * t.H * t.W * t.C * t.esize
-        flat = prog.workspace[off:off + n].view(dtype)
-        if t.esize == 4:
-            return flat.view(prog.B, t.H, t.W, t.C)
-        return from_pm(flat.view(prog.B, t.C // 8, t.H, t.W, 8))
+        raw = prog.workspace[off:off + n]
+        if t.fmt == _lib.DT_F32:
+            return raw.view(torch.float32).view(prog.B, t.H, t.W, t.C)
+        if t.fmt == _lib.DT_F16X2:
+            return from_pm_x3(raw.view(torch.float16).view(prog.B, t.C // 8, 2, t.H, t.W, 8))
+        return from_pm(raw.view(torch.bfloat16).view(prog.B, t.C // 8, t.H, t.W, 8))

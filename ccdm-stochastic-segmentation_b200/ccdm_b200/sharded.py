@@ -74,6 +74,14 @@ def sample_sharded(model, x: torch.Tensor, condition: torch.Tensor, feature_cond
     n = x.shape[0]
     b, e = shard_range(n, rank, world)
     old_offset = getattr(model, "sample_offset", 0)
+    # Sharded draws must come from the counter RNG keyed by the GLOBAL sample index.  The reference's noise source
+    # (noise='torch': each device's global generator) would make the result depend on the number of ranks and, with the
+    # usual identical seeding of every rank, hand all shards the SAME noise -- correlated samples, biased GED/diversity.
+    old_noise = getattr(model, "noise", "philox")
+    if isinstance(old_noise, str) and old_noise != "philox":
+        model.noise = "philox"
+    elif not isinstance(old_noise, str):
+        raise ValueError("sample_sharded: explicit noise tensors cannot be sharded; use noise='philox'")
     model.sample_offset = old_offset + b
     try:
         if e > b:
@@ -84,6 +92,7 @@ def sample_sharded(model, x: torch.Tensor, condition: torch.Tensor, feature_cond
             out = torch.zeros((0, K) + tuple(x.shape[-2:]), dtype=torch.float32 if conf else torch.int64, device=condition.device)
     finally:
         model.sample_offset = old_offset
+        model.noise = old_noise
     if out.dtype == torch.int64:  # majority: ship 1 byte per pixel, rebuild the one-hot view after the gather
         K = out.shape[1]
         labels = gather_shards(out.argmax(dim=1).to(torch.uint8), n, group)

@@ -14,7 +14,7 @@
  *  - no allocation of caller-visible memory, no host synchronisation, every
  *    launch goes to the `stream` argument (a cudaStream_t passed as void*).
  *  - return 0 on success, negative on error; ccdm_last_error() describes it.
- *  - fp32 activations (`CCDM_DT_F32`, the exact kernels) are NHWC ("pixel-major,
+ *  - fp32 activations (`CCDM_DT_F32`, the FFMA kernels) are NHWC ("pixel-major,
  *    channel-minor"); bf16 activations (`CCDM_DT_BF16`, the tensor-core kernels)
  *    are PLANE-MAJOR [B][C/8][H][W][8]: one 16-byte row of a tcgen05 "K-major,
  *    no swizzle" core matrix per (8-channel plane, pixel), so a TMA box of a
@@ -36,11 +36,17 @@
 extern "C" {
 #endif
 
-#define CCDM_ABI_VERSION 2
+#define CCDM_ABI_VERSION 3
 
 /* storage types of activations / packed conv weights */
 #define CCDM_DT_F32 0
 #define CCDM_DT_BF16 1
+/* "fp16x2": every value v is stored as TWO fp16 numbers hi = fp16(16 v), lo = fp16(16 v - hi) (22 significand bits,
+ * error <= max(2^-23 |v|, 2^-29)), plane-major like bf16 with the hi and lo planes of an 8-channel group adjacent:
+ * [B][C/8][2][H][W][8].  The tensor-core kernels multiply such operands with three fp16 MMAs (hi*hi + hi*lo + lo*hi,
+ * fp32 accumulation in TMEM): fp32-grade products at tensor-core speed -- the "exact" tensor-core mode. */
+#define CCDM_DT_F16X2 2
+#define CCDM_F16X2_SCALE_LOG2 4 /* stored = 2^4 * value */
 
 /* last-step / draw modes of the categorical head (diffusion_denoising.py:206-212) */
 #define CCDM_DRAW_SAMPLE 0     /* t > 1: x_{t-1} ~ Cat(p)  == argmax p/E            */
@@ -98,7 +104,9 @@ typedef struct ccdm_op {
     int32_t src_kind;   /* 0: src0/src1 NHWC activations; 1: one-hot(labels_in) ++ image (unet.py:760) */
     int32_t exact;      /* 1: fp32 FFMA kernels (parity mode); 0: tensor-core kernels where available; HEAD: 0 lets sampling
                          * steps use approximate exp2/log2/reciprocal (same Philox bits, no IEEE divisions) */
-    int32_t reserved[2];
+    int32_t acc_shift;  /* fp16x2 convs: packed weights are scaled by 2^(acc_shift - CCDM_F16X2_SCALE_LOG2); the epilogue
+                         * multiplies the accumulator by 2^-acc_shift (powers of two: exact) */
+    int32_t reserved;
     /* Layout of stat0 / stat1.  st_slots[i] == 0: double2 [B, C] {sum, sum of squares}, folded by the producer.
      * st_slots[i] > 0 ("deferred fold", tensor-core producers): fp32 per-CTA partial rows [B][st_slots][st_rows][2] exactly
      * as the producer's epilogue wrote them (ccdm_conv_stat_layout); the consumer folds rows
@@ -140,15 +148,16 @@ size_t ccdm_sizeof_step_entry(void);
 size_t ccdm_conv_part_floats(int B, int Hout, int Wout, int Cout);
 /* the same, for the kernel `op` will actually be dispatched to */
 size_t ccdm_op_part_floats(const ccdm_op *op);
-/* 1 if `op` (exact == 0, bf16, stride 1) runs on the tcgen05 kernel; its `weight` / `skip_w`
- * must then be bf16 packed [cc][Cin/8][tap][NT][8] (cc = chunk of NT = ccdm_conv_tc_nt(Cout) output
+/* 1 if `op` (exact == 0, dtype bf16 or fp16x2) runs on the tcgen05 kernel (conv_tma.cu); its `weight` / `skip_w`
+ * must then be packed [cc][Cin/8][tap][NT][8] bf16 (cc = chunk of NT = ccdm_conv_tc_nt(Cout, taps) output
  * channels of ceil16(Cout)) instead of fp32 [tap][CinP][CoutP]: every (chunk, 8-channel plane, tap)
  * is NT rows of 16 bytes, the UMMA K-major no-swizzle canonical form, and a K chunk of planes is one
- * contiguous block (one cp.async.bulk). */
+ * contiguous block (one cp.async.bulk).  fp16x2: [cc][Cin/8][tap][2][NT][8] fp16 -- the NT hi rows of a
+ * (plane, tap), then its NT lo rows -- of the weights scaled by 2^(acc_shift - 4). */
 int ccdm_conv_uses_tc(const ccdm_op *op);
-/* 1 if that tensor-core conv is the TMA-fed kernel (conv_tma.cu: stride 1, no upsample), 0 if the LDG-fed one. */
+/* same (kept for tools; there is one tensor-core conv kernel) */
 int ccdm_conv_uses_tma(const ccdm_op *op);
-int ccdm_conv_tc_nt(int Cout);
+int ccdm_conv_tc_nt(int Cout, int taps); /* taps = 1 (1x1), 9 (3x3) or 16 (sub-pixel taps of an upsampling conv) */
 /* Tile / pipeline configuration the tcgen05 kernel would use for `op` (introspection for DESIGN.md, the
  * bench and tests): out16 = {PL, R, Wt, MB, WN, NT, n_cc, NS, resident, acc2, tmem_cols, tiles, n_items,
  * grid, smem bytes, K chunks per item}.  Returns -1 if `op` does not run on that kernel. */

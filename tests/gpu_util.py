@@ -6,7 +6,17 @@ import torch
 import torch.nn.functional as F
 
 from ccdm_b200 import _lib
-from ccdm_b200.engine import from_pm, pack_bias, pack_conv_weight, pack_conv_weight_tc, subpixel_weights, to_pm
+from ccdm_b200.engine import (from_pm, from_pm_x3, pack_bias, pack_conv_weight, pack_conv_weight_tc, pack_conv_weight_x3,
+                              subpixel_weights, to_pm, to_pm_x3)
+
+X3 = "x3"  # run_conv(dtype=X3): fp16x2 storage (CCDM_DT_F16X2), the exact tensor-core mode
+
+
+def x3_shift(*ws):
+    """Power-of-two weight scale the engine would pick (PackedWeights.refresh) for these weight tensors."""
+    import math
+    wmax = max(float(w.abs().max()) for w in ws if w is not None)
+    return int(max(0, min(13, math.floor(math.log2(32768.0 / max(wmax, 1e-30))))))
 
 
 def sp():
@@ -43,9 +53,16 @@ def run_conv(srcs, weight, bias, *, gn=None, silu=False, ksize=3, stride=1, upsa
     dev = "cuda"
     one_hot_in = labels is not None
     # bf16 activations live in the kernels' plane-major layout; this helper keeps NHWC at its surface
-    pm = dtype == torch.bfloat16
+    x3 = isinstance(dtype, str) and dtype == X3
+    pm = x3 or dtype == torch.bfloat16
     shapes = [tuple(s.shape) for s in srcs]
-    if pm:
+    skip_ch = [int(t.shape[3]) for t in skip] if skip is not None else []
+    if x3:
+        assert tc and res is None
+        nh = list(srcs)
+        srcs = [to_pm_x3(s.float()) for s in srcs]
+        skip = [to_pm_x3(t.float()) for t in skip] if skip is not None else None
+    elif pm:
         nh = list(srcs)
         srcs = [to_pm(s) for s in srcs]
         skip = [to_pm(s) for s in skip] if skip is not None else None
@@ -61,7 +78,12 @@ def run_conv(srcs, weight, bias, *, gn=None, silu=False, ksize=3, stride=1, upsa
     Hout = Hin * 2 if upsample else ((Hin + 1) // 2 if stride == 2 else Hin)
     Wout = Win * 2 if upsample else ((Win + 1) // 2 if stride == 2 else Win)
     keep = []
-    if tc:
+    shift = 0
+    if x3:
+        wraw = subpixel_weights(weight.to(dev)) if upsample else weight.to(dev)
+        shift = x3_shift(wraw, skip_w)
+        wp = pack_conv_weight_x3(wraw, shift).contiguous()
+    elif tc:
         wp = pack_conv_weight_tc(subpixel_weights(weight.to(dev)) if upsample else weight.to(dev)).contiguous()
     else:
         wp = pack_conv_weight(weight.to(dev), (cin + 7) // 8 * 8 if one_hot_in else None).contiguous()
@@ -69,10 +91,11 @@ def run_conv(srcs, weight, bias, *, gn=None, silu=False, ksize=3, stride=1, upsa
     if skip is not None:
         assert skip_w is not None
     bp = pack_bias(b)
-    out_dtype = torch.float32 if (out_f32 or dtype == torch.float32) else torch.bfloat16
-    out = torch.full((B, Hout, Wout, Cout), float("nan"), dtype=out_dtype, device=dev)
-    op = _lib.Op(kind=_lib.OP_CONV, dtype=_lib.DT_F32 if dtype == torch.float32 else _lib.DT_BF16,
-                 out_dtype=_lib.DT_F32 if out_dtype == torch.float32 else _lib.DT_BF16, B=B, Hin=Hin, Win=Win, Hout=Hout,
+    out_dtype = torch.float32 if (out_f32 or (not x3 and dtype == torch.float32)) else (torch.float16 if x3 else torch.bfloat16)
+    out = torch.full((B, Hout, Wout, Cout * (2 if out_dtype == torch.float16 else 1)), float("nan"), dtype=out_dtype, device=dev)
+    dt_code = _lib.DT_F16X2 if x3 else (_lib.DT_F32 if dtype == torch.float32 else _lib.DT_BF16)
+    op = _lib.Op(kind=_lib.OP_CONV, dtype=dt_code, acc_shift=shift + _lib.F16X2_SCALE_LOG2 if x3 else 0,
+                 out_dtype=_lib.DT_F32 if out_dtype == torch.float32 else dt_code, B=B, Hin=Hin, Win=Win, Hout=Hout,
                  Wout=Wout, Cout=Cout, ksize=ksize, stride=stride, upsample=int(upsample), gn=int(gn is not None),
                  silu=int(silu), exact=0 if tc else 1)
     op.weight, op.bias, op.out = wp.data_ptr(), bp.data_ptr(), out.data_ptr()
@@ -97,11 +120,12 @@ def run_conv(srcs, weight, bias, *, gn=None, silu=False, ksize=3, stride=1, upsa
             keep += [g, be]
             op.gamma, op.beta = g.data_ptr(), be.data_ptr()
     if skip is not None:
-        sw = pack_conv_weight_tc(skip_w.to(dev)).contiguous() if tc else skip_w.to(dev).float()[:, :, 0, 0].t().contiguous()
+        sw = (pack_conv_weight_x3(skip_w.to(dev), shift).contiguous() if x3 else
+              pack_conv_weight_tc(skip_w.to(dev)).contiguous() if tc else skip_w.to(dev).float()[:, :, 0, 0].t().contiguous())
         keep.append(sw)
-        op.skip0, op.S0 = skip[0].data_ptr(), (skip[0].shape[1] * 8 if pm else skip[0].shape[3])
+        op.skip0, op.S0 = skip[0].data_ptr(), skip_ch[0]
         if len(skip) > 1:
-            op.skip1, op.S1 = skip[1].data_ptr(), (skip[1].shape[1] * 8 if pm else skip[1].shape[3])
+            op.skip1, op.S1 = skip[1].data_ptr(), skip_ch[1]
         op.skip_w = sw.data_ptr()
     if res is not None:
         op.res = res.data_ptr()
@@ -127,14 +151,23 @@ def run_conv(srcs, weight, bias, *, gn=None, silu=False, ksize=3, stride=1, upsa
     torch.cuda.synchronize()
     if want_stat:
         assert int(ticket.abs().sum()) == 0, "ticket counters must self-reset"
-    if pm and out_dtype == torch.bfloat16:
+    if out_dtype == torch.float16:
+        out = from_pm_x3(out.view(B, Cout // 8, 2, Hout, Wout, 8))
+    elif pm and out_dtype == torch.bfloat16:
         out = from_pm(out.view(B, Cout // 8, Hout, Wout, 8))
     return out, ostat
 
 
 def ref_conv(srcs_nchw, weight, bias, *, gn=None, silu=False, stride=1, upsample=False, skip=None, skip_w=None,
-             skip_b=None, res=None, emb=None):
-    """fp32 CPU torch reference of the same fused op (NCHW)."""
+             skip_b=None, res=None, emb=None, dtype=torch.float32):
+    """CPU torch reference of the same fused op (NCHW), fp32 by default (dtype=torch.float64: the yardstick both the
+    kernel and the fp32 reference are measured against)."""
+    cast = (lambda t: t.to(dtype).cpu()) if dtype != torch.float32 else None
+    if cast is not None:
+        f = lambda t: None if t is None else cast(t)  # noqa: E731
+        return _ref_conv64([f(t) for t in srcs_nchw], f(weight), f(bias), gn=None if gn is None else (f(gn[0]), f(gn[1])), silu=silu,
+                           stride=stride, upsample=upsample, skip=None if skip is None else [f(t) for t in skip], skip_w=f(skip_w),
+                           skip_b=f(skip_b), res=f(res), emb=f(emb))
     x = torch.cat([s.float().cpu() for s in srcs_nchw], dim=1)
     h = x
     if gn is not None:
@@ -150,6 +183,24 @@ def ref_conv(srcs_nchw, weight, bias, *, gn=None, silu=False, stride=1, upsample
         h = h + F.conv2d(torch.cat([s.float().cpu() for s in skip], dim=1), skip_w.float().cpu(), skip_b)
     if res is not None:
         h = h + res.float().cpu()
+    return h
+
+
+def _ref_conv64(srcs, weight, bias, *, gn, silu, stride, upsample, skip, skip_w, skip_b, res, emb):
+    h = torch.cat(srcs, dim=1)
+    if gn is not None:
+        h = F.group_norm(h, 32, gn[0], gn[1], eps=1e-5)
+    if silu:
+        h = F.silu(h)
+    if upsample:
+        h = F.interpolate(h, scale_factor=2, mode="nearest")
+    h = F.conv2d(h, weight, bias, stride=stride, padding=weight.shape[-1] // 2)
+    if emb is not None:
+        h = h + emb[:, :, None, None]
+    if skip is not None:
+        h = h + F.conv2d(torch.cat(skip, dim=1), skip_w, skip_b)
+    if res is not None:
+        h = h + res
     return h
 
 

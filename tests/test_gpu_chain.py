@@ -2,7 +2,8 @@
 reference-shaped Python surface (ccdm_b200.models), against (a) the fixtures generated from
 the unmodified reference and (b) the CPU oracle on seeded inputs.
 
-Tolerances (fp32 "exact" precision mode; stated per SURVEY.md section 7 item 1):
+Two parity-grade precision modes are held to the SAME tolerances: 'fp32' (FFMA kernels) and 'exact' (tensor cores on
+fp16 hi + lo operands, three MMAs per product -- the default of DenoisingModel).  Tolerances:
   * x0 prediction (softmax probabilities):   max |dp| <= 2e-4
   * posterior log-probabilities:              max |d log p| <= 1e-3 on entries with p >= 1e-6
   * sampled labels, teacher-forced per step:  identical wherever the top-2 race margin
@@ -22,6 +23,7 @@ pytestmark = pytest.mark.gpu
 X0_TOL = 2e-4
 RACE_MARGIN = 1e-3
 REPORT = {}
+PARITY_MODES = ["fp32", "exact"]
 
 
 def _report(key, **vals):
@@ -44,22 +46,25 @@ def _onehot(labels, K):
     return torch.nn.functional.one_hot(labels.long(), K).permute(0, 3, 1, 2).float()
 
 
+@pytest.mark.parametrize("prec", PARITY_MODES)
 @pytest.mark.parametrize("tag", ["lidc64", "lidc128", "cs64x128"])
-def test_unet_matches_reference_fixture(cuda_device, tag):
+def test_unet_matches_reference_fixture(cuda_device, tag, prec):
     T, B, C_img, H, W, K, fce, mult, t_probe, steps = GOLDEN_CASES[tag]
     g = golden(tag + ".npz")
     m, image, feat, labels = _case(tag)
+    m.unet.precision = prec
     x = _onehot(labels, K).cuda()
     for t in t_probe:
         out = m.unet(x, image.cuda(), feat.cuda() if feat is not None else None, torch.full((B,), float(t)).cuda())
         p = out["diffusion_out"]
         assert p.shape == (B, K, H, W) and out["logits"] is None
         err = np.abs(p.permute(0, 2, 3, 1).cpu().numpy() - g[f"x0pred_t{t}"]).max()
-        _report(f"unet_{tag}_t{t}", max_abs_err=err)
+        _report(f"unet_{prec}_{tag}_t{t}", max_abs_err=err)
         assert err <= X0_TOL, f"{tag} t={t}: max|dp|={err}"
 
 
-def test_unet_layerwise_vs_oracle(cuda_device):
+@pytest.mark.parametrize("prec", PARITY_MODES)
+def test_unet_layerwise_vs_oracle(cuda_device, prec):
     """Every fused kernel's output against the torch fp32 restatement, layer by layer."""
     from oracle import unet_ref
     tag = "lidc64"
@@ -68,7 +73,7 @@ def test_unet_layerwise_vs_oracle(cuda_device):
     taps = {}
     unet_ref.unet_forward({k: v.cpu() for k, v in m.unet.state_dict().items()}, _onehot(labels, K), image, feat,
                           torch.full((B,), 37.0), taps=taps)
-    tr = m.unet.engine("fp32").trace_step(labels.cuda(), image.cuda(), None, 37.0)
+    tr = m.unet.engine(prec).trace_step(labels.cuda(), image.cuda(), None, 37.0)
     worst = {}
     for name, ref in taps.items():
         key = name if name in tr else (name + ".op" if name + ".op" in tr else name + ".conv")
@@ -78,7 +83,7 @@ def test_unet_layerwise_vs_oracle(cuda_device):
         scale = float(ref.abs().max()) + 1e-6
         worst[name] = float((got - ref).abs().max()) / scale
     assert len(worst) >= 30
-    _report("layerwise_lidc64", worst_rel=max(worst.values()), worst_layer=max(worst, key=worst.get))
+    _report(f"layerwise_{prec}_lidc64", worst_rel=max(worst.values()), worst_layer=max(worst, key=worst.get))
     bad = {k: v for k, v in worst.items() if v > 1e-4}
     assert not bad, bad
 
@@ -136,8 +141,9 @@ def _teacher_forced_check(m, image, feat, fce, K, T, record):
     return stats
 
 
+@pytest.mark.parametrize("prec", PARITY_MODES)
 @pytest.mark.parametrize("tag,noise", [("lidc64", "torch"), ("lidc64", "philox"), ("cs64x128", "torch")])
-def test_chain_teacher_forced_vs_oracle(cuda_device, tag, noise):
+def test_chain_teacher_forced_vs_oracle(cuda_device, tag, noise, prec):
     T, B, C_img, H, W, K, fce, mult, t_probe, steps = GOLDEN_CASES[tag]
     m, image, feat, labels = _case(tag)
     from ccdm_b200 import _lib
@@ -146,19 +152,20 @@ def test_chain_teacher_forced_vs_oracle(cuda_device, tag, noise):
     record = []
     torch.manual_seed(7)
     al, ca = m._schedule_host()
-    m.unet.engine("fp32").run_chain(_onehot(labels, K).cuda(), image.cuda(), feat.cuda() if feat is not None else None, ts,
-                                    al, ca, _lib.DRAW_MAJORITY, noise=noise, seed=1234, record=record)
+    m.unet.engine(prec).run_chain(_onehot(labels, K).cuda(), image.cuda(), feat.cuda() if feat is not None else None, ts,
+                                  al, ca, _lib.DRAW_MAJORITY, noise=noise, seed=1234, record=record)
     assert [r["t"] for r in record] == ts
     stats = _teacher_forced_check(m, image, feat, fce, K, T, record)
-    _report(f"teacher_forced_{tag}_{noise}", **stats)
+    _report(f"teacher_forced_{prec}_{tag}_{noise}", **stats)
     assert stats["max_dx0"] <= X0_TOL
     assert stats["max_dlogp"] <= 1e-3
     assert stats["mismatch_outside_margin"] == 0
     assert stats["mismatch_total"] <= 1e-4 * stats["pixels"] + 2
 
 
+@pytest.mark.parametrize("prec", PARITY_MODES)
 @pytest.mark.parametrize("tag", ["lidc64", "cs64x128"])
-def test_chain_replays_reference_fixture_with_injected_noise(cuda_device, tag):
+def test_chain_replays_reference_fixture_with_injected_noise(cuda_device, tag, prec):
     """The reference's own chain output (CPU generator, seed 42), reproduced on the GPU by injecting
     the same exponential draws.  Free-running: one near-tie flip would propagate, so agreement is
     reported and required to be >= 99.9 %; in practice it is exact."""
@@ -168,6 +175,7 @@ def test_chain_replays_reference_fixture_with_injected_noise(cuda_device, tag):
     noises = [torch.empty(B * H * W, K).exponential_(1) for _ in range(steps - 1)]
     for mode in ("majority", "confidence"):
         m, image, feat, labels = _case(tag, mode)
+        m.precision = prec
         m.noise = [n.cuda() for n in noises]
         out = m(_onehot(labels, K).cuda(), image.cuda(), feat.cuda() if feat is not None else None,
                 t=torch.as_tensor(10000 + steps))["diffusion_out"]
@@ -175,13 +183,13 @@ def test_chain_replays_reference_fixture_with_injected_noise(cuda_device, tag):
         if mode == "majority":
             assert out.dtype == torch.int64 and not out.is_contiguous()  # NHWC-strided view, like the reference
             agree = float((out.argmax(1).cpu().numpy() == g["chain_majority_labels"]).mean())
-            _report(f"fixture_chain_{tag}_majority", agreement=agree)
+            _report(f"fixture_chain_{prec}_{tag}_majority", agreement=agree)
             assert agree >= 0.999
         else:
             assert out.dtype == torch.float32
             err = np.abs(out.permute(0, 2, 3, 1).cpu().numpy() - g["chain_confidence_probs"])
             frac_close = float((err.max(axis=-1) < 1e-3).mean())
-            _report(f"fixture_chain_{tag}_confidence", frac_close=frac_close, median_err=float(np.median(err)))
+            _report(f"fixture_chain_{prec}_{tag}_confidence", frac_close=frac_close, median_err=float(np.median(err)))
             assert frac_close >= 0.995
 
 
