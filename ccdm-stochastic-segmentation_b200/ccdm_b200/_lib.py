@@ -92,7 +92,7 @@ def lib():
     L.ccdm_conv_uses_tc.argtypes = [ctypes.POINTER(Op)]
     L.ccdm_conv_uses_tma.argtypes = [ctypes.POINTER(Op)]
     L.ccdm_conv_stat_layout.argtypes = [ctypes.POINTER(Op), ctypes.POINTER(ctypes.c_int32)]
-    L.ccdm_conv_tc_nt.argtypes = [ctypes.c_int, ctypes.c_int]
+    L.ccdm_conv_tc_nt.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
     L.ccdm_conv_tc_config.argtypes = [ctypes.POINTER(Op), ctypes.POINTER(ctypes.c_int32)]
     L.ccdm_conv_part_floats.restype = ctypes.c_size_t
     L.ccdm_conv_part_floats.argtypes = [ctypes.c_int] * 4

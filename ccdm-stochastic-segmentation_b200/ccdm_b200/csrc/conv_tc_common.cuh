@@ -18,9 +18,10 @@ constexpr int CGW = 16;  // accumulator columns per tcgen05.ld
 // (narrow items: more CTAs busy on small maps, and a weight stage of 9 or 16 taps stays small).  Wider 1x1 layers (the
 // q/k/v convs, Cout = 3C): the largest divisor <= 192, so a sample is 2 items instead of 6 and the input is normalised
 // twice instead of six times.
-inline int tc_nt(int Cout, int taps) {
+// fp16x2 mode: N <= 128, because an MMA of that mode covers 2 NT accumulator columns (hi and lo rows of B at once).
+inline int tc_nt(int Cout, int taps, int x3) {
     const int CoutP = (Cout + 15) / 16 * 16;
-    for (int nt = (CoutP > 128 && taps == 1) ? 192 : 64; nt >= 16; nt -= 16)
+    for (int nt = (CoutP > 128 && taps == 1) ? (x3 ? 128 : 192) : 64; nt >= 16; nt -= 16)
         if (CoutP % nt == 0) return nt;
     return 16;
 }
@@ -53,6 +54,7 @@ struct WsP {
     int RW, NQ, xf;  // conv_tma: window rows, window positions (= plane stride in 16-byte rows), 1 if chunks are transformed in smem
     uint32_t a_stage, w_stage, w_main_bytes, w_skip_bytes, magicP;
     uint32_t idesc;
+    uint32_t idesc2; // x3: the same with N = 2 NT
     int x3;          // fp16x2 storage (CCDM_DT_F16X2): operands are (hi, lo) plane pairs, three MMAs per product
     float descale;   // x3: 2^-acc_shift, applied to the accumulator in the epilogue
 };
@@ -273,7 +275,9 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
         }
         const int buf = p.acc2 ? (acc_it & 1) : 0;
         const uint32_t aph = p.acc2 ? uint32_t((acc_it >> 1) & 1) : uint32_t(acc_it & 1);
-        const uint32_t tbase = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * p.MB * NT * nsub);
+        // fp16x2: 2 NT columns per (M block, parity): [0, NT) the hi*hi products, [NT, 2 NT) the small hi*lo + lo*hi terms
+        constexpr int XA = X3 ? 2 : 1;
+        const uint32_t tbase = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * p.MB * NT * nsub * XA);
         const int ylim = min(p.R, p.H - I.y0), xlim = min(p.Wt, p.W - I.x0);  // rows / columns of real outputs
         bool waited = false;
         for (int cgs = half; cgs < n_cg * nsub; cgs += NHALF) {
@@ -375,8 +379,26 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
                     }
                 }
             };
-            const uint32_t tcol = tbase + uint32_t(sub * NT + cg * CGW), tstep = uint32_t(nsub * NT);
+            const uint32_t tcol = tbase + uint32_t(sub * NT * XA + cg * CGW), tstep = uint32_t(nsub * NT * XA);
             uint32_t ra[CGW], rb[CGW];
+            if constexpr (X3) {
+                // main + small accumulator columns of a row block, summed here in fp32 (round to nearest); the loads of block
+                // mb+1 are in flight while block mb is processed
+                tmem_ld16_issue(tcol, ra);
+                tmem_ld16_issue(tcol + uint32_t(NT), rb);
+                for (int mb = 0; mb < p.MB; ++mb) {
+                    tmem_ld_wait16(ra);
+                    tmem_ld_wait16(rb);
+                    uint32_t sum[CGW];
+#pragma unroll
+                    for (int i = 0; i < CGW; ++i) sum[i] = __float_as_uint(__uint_as_float(ra[i]) + __uint_as_float(rb[i]));
+                    if (mb + 1 < p.MB) {
+                        tmem_ld16_issue(tcol + uint32_t(mb + 1) * tstep, ra);
+                        tmem_ld16_issue(tcol + uint32_t(mb + 1) * tstep + uint32_t(NT), rb);
+                    }
+                    process(sum, mb);
+                }
+            } else {
             tmem_ld16_issue(tcol, ra);
             for (int mb = 0; mb < p.MB; mb += 2) {
                 tmem_ld_wait16(ra);
@@ -387,6 +409,7 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
                     if (mb + 2 < p.MB) tmem_ld16_issue(tcol + uint32_t(mb + 2) * tstep, ra);
                     process(rb, mb + 1);
                 }
+            }
             }
             if (want_stats) {
                 const float r1 = warp_transpose_reduce16(s1, lane);

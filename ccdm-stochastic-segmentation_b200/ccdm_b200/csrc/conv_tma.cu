@@ -457,11 +457,15 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
         // one product: a single bf16 MMA, or the three fp16 MMAs of the split operands (lo plane of A: NQ rows after the
         // hi plane; lo rows of B: NT rows after the hi rows)
         const uint32_t a_lo = uint32_t(NQ), b_lo = uint32_t(NT);
+        // fp16x2: an accumulator is 2 NT columns.  A_hi x [B_hi; B_lo] (the NT hi rows and the NT lo rows of a (plane, tap)
+        // are adjacent: one MMA with N = 2 NT) puts hi*hi into columns [0, NT) and hi*lo into [NT, 2 NT); A_lo x B_hi adds
+        // lo*hi to [NT, 2 NT).  Two instructions instead of three, and the large products accumulate on their own: the
+        // tensor core truncates on every accumulation (measured: error ~ number of accumulating MMAs x 2^-24 |acc|), so the
+        // small terms must not triple the count on the main accumulator.  The epilogue adds the two halves in fp32.
         auto mma = [&](uint32_t d, uint32_t a, uint32_t b, uint32_t acc) {
             if constexpr (X3) {
-                umma_bf16_split(d, a, desc_hi, b + b_lo, desc_hi, p.idesc, acc);
-                umma_bf16_split(d, a + a_lo, desc_hi, b, desc_hi, p.idesc, 1u);
-                umma_bf16_split(d, a, desc_hi, b, desc_hi, p.idesc, 1u);
+                umma_bf16_split(d, a, desc_hi, b, desc_hi, p.idesc2, acc);
+                umma_bf16_split(d + b_lo, a + a_lo, desc_hi, b, desc_hi, p.idesc, 1u);
             } else {
                 umma_bf16_split(d, a, desc_hi, b, desc_hi, p.idesc, acc);
             }
@@ -472,7 +476,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
             mbar_wait(acc_empty + buf, aph ^ 1u);
             tc_fence_after();
             if (mw == 0 && lane == 0) tl(2, it - it_begin, 0);
-            const uint32_t d0 = tmem_base + uint32_t(buf * p.MB * NT * (UP ? 4 : 1));
+            const uint32_t d0 = tmem_base + uint32_t(buf * p.MB * NT * X * (UP ? 4 : 1));
             for (int kc = 0; kc < n_chunks; ++kc) {
                 const bool is_skip = kc >= p.n_main;
                 const int ntap = is_skip ? 1 : p.taps;
@@ -495,7 +499,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
                         const uint32_t arow = aaddr + uint32_t(mb * 128);
 #pragma unroll
                         for (int par = 0; par < 4; ++par) {
-                            const uint32_t d = d0 + uint32_t((mb * 4 + par) * NT);
+                            const uint32_t d = d0 + uint32_t((mb * 4 + par) * NT * X);
                             uint32_t acc = kc > 0 ? 1u : 0u;
 #pragma unroll
                             for (int t = 0; t < 4; ++t) {
@@ -511,7 +515,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
                     }
                 } else if (ntap == 9) {
                     for (int mb = mw; mb < p.MB; mb += MMA_WARPS) {
-                        const uint32_t d = d0 + uint32_t(mb * NT);
+                        const uint32_t d = d0 + uint32_t(mb * NT * X);
                         const uint32_t arow = aaddr + uint32_t(mb * 128);
                         uint32_t acc = kc > 0 ? 1u : 0u;
 #pragma unroll
@@ -534,7 +538,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
                     // 1x1 conv, or the fused 1x1 skip conv of a 3x3 block (centre tap of the window)
                     const uint32_t shift = is_skip ? uint32_t(p.pad * P + p.pad) : 0u;
                     for (int mb = mw; mb < p.MB; mb += MMA_WARPS) {
-                        const uint32_t d = d0 + uint32_t(mb * NT);
+                        const uint32_t d = d0 + uint32_t(mb * NT * X);
                         const uint32_t at = aaddr + uint32_t(mb * 128) + shift;
 #pragma unroll
                         for (int k16 = 0; k16 < PL / 2; ++k16)
@@ -634,7 +638,7 @@ int tm_num_sms() {
     return n;
 }
 
-int tm_nt(int Cout, int taps) { return tc_nt(Cout, taps); }
+int tm_nt(int Cout, int taps, int x3) { return tc_nt(Cout, taps, x3); }
 
 // x3: fp16x2 operands -- a stage holds 2*PL planes and the weights are twice as many rows (conv_tma_kernel<..., X3>)
 bool tm_configure_pl(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout, int ksize, int stride, int up, int x3, int force_pl, TmCfg &best);
@@ -654,7 +658,7 @@ bool tm_configure_pl(int B, int H, int W, int C0, int C1, int S0, int S1, int Co
     const int nsub = up ? 4 : 1;                                 // accumulator sets per M block (output parities)
     const int CoutP = (Cout + 15) / 16 * 16;
     TmCfg c{};
-    c.NT = tm_nt(Cout, taps);
+    c.NT = tm_nt(Cout, taps, x3);
     c.n_cc = CoutP / c.NT;
     const bool all32 = !(C0 % 32) && !(C1 % 32) && !(S0 % 32) && !(S1 % 32);
     c.PL = all32 ? 4 : 2;
@@ -693,7 +697,7 @@ bool tm_configure_pl(int B, int H, int W, int C0, int C1, int S0, int S1, int Co
     bool found = false;
     for (int R = 1; R <= H && 2 * (R + 2 * pad) <= 256; ++R) {
         const int MB = (R * c.P + 127) / 128;
-        if (nsub * MB * c.NT > 512) break;
+        if (nsub * MB * c.NT * X > 512) break;
         const int RW = s2 ? R + 1 : R + 2 * pad, NQ = RW * c.P;
         bool magic_ok = true;
         for (int q = 0; q < NQ + 256; ++q)
@@ -716,16 +720,16 @@ bool tm_configure_pl(int B, int H, int W, int C0, int C1, int S0, int S1, int Co
         double cost = double(per_cta) * item_cost;
         if (NS < 3) cost *= 1.5;
         else if (NS < 4) cost *= 1.1;
-        if (2 * nsub * MB * c.NT > 512) cost *= 1.15;  // single accumulator buffer: epilogue not overlapped
+        if (2 * nsub * MB * c.NT * X > 512) cost *= 1.15;  // single accumulator buffer: epilogue not overlapped
         if (env_r > 0 && W >= 64 && H >= 64) cost = (R == env_r) ? 0.0 : 1e290;
         if (cost < best_cost) {
             best_cost = cost;
             best = c;
             best.R = R; best.RW = RW; best.NQ = NQ; best.MB = MB; best.NS = NS; best.a_stage = uint32_t(a_stage);
-            best.acc2 = 2 * nsub * MB * c.NT <= 512;
+            best.acc2 = 2 * nsub * MB * c.NT * X <= 512;
             best.tiles = tiles; best.n_items = int(items); best.grid = grid;
             int cols = 32;
-            while (cols < (best.acc2 ? 2 : 1) * nsub * MB * c.NT) cols *= 2;
+            while (cols < (best.acc2 ? 2 : 1) * nsub * MB * c.NT * X) cols *= 2;
             best.tmem_cols = cols;
             best.smem = fixed + size_t(NS) * (a_stage + c.w_stage);
             found = true;
@@ -809,7 +813,7 @@ int conv_tma_read_trace(unsigned long long *out, int n) {
     return m;
 }
 
-int conv_tc_nt(int Cout, int taps) { return tm_nt(Cout, taps); }
+int conv_tc_nt(int Cout, int taps, int x3) { return tm_nt(Cout, taps, x3); }
 
 bool conv_tma_supported(const ccdm_op &op) {
     if ((op.dtype != CCDM_DT_BF16 && op.dtype != CCDM_DT_F16X2) || op.src_kind != 0) return false;
@@ -902,6 +906,7 @@ int launch_conv_tma(const ccdm_op &op, cudaStream_t s) {
     const bool x3 = op.dtype == CCDM_DT_F16X2;
     const int X = x3 ? 2 : 1;
     p.idesc = tm_idesc(c.NT, x3);
+    p.idesc2 = tm_idesc(2 * c.NT, x3);
     p.x3 = x3 ? 1 : 0;
     p.descale = x3 ? float(ldexp(1.0, -op.acc_shift)) : 1.0f;
     if (x3 && (op.acc_shift < CCDM_F16X2_SCALE_LOG2 || op.acc_shift > 40)) CCDM_FAIL(-2, "conv_tma: fp16x2 op without a valid acc_shift (%d)", op.acc_shift);

@@ -70,9 +70,9 @@ extern "C" size_t ccdm_sizeof_step_entry(void) { return sizeof(ccdm_step_entry);
 namespace ccdm { size_t conv_part_floats(int B, int Hout, int Wout, int Cout); }
 extern "C" size_t ccdm_conv_part_floats(int B, int Hout, int Wout, int Cout) { return ccdm::conv_part_floats(B, Hout, Wout, Cout); }
 
-namespace ccdm { bool conv_uses_tc(const ccdm_op &op); size_t op_part_floats(const ccdm_op &op); int conv_tc_nt(int Cout, int taps); }
+namespace ccdm { bool conv_uses_tc(const ccdm_op &op); size_t op_part_floats(const ccdm_op &op); int conv_tc_nt(int Cout, int taps, int x3); }
 extern "C" int ccdm_conv_uses_tc(const ccdm_op *op) { return op && ccdm::conv_uses_tc(*op) ? 1 : 0; }
-extern "C" int ccdm_conv_tc_nt(int Cout, int taps) { return ccdm::conv_tc_nt(Cout, taps); }
+extern "C" int ccdm_conv_tc_nt(int Cout, int taps, int x3) { return ccdm::conv_tc_nt(Cout, taps, x3); }
 namespace ccdm { int conv_tma_config(const ccdm_op &op, int32_t *out); bool conv_uses_tma(const ccdm_op &op); }
 extern "C" int ccdm_conv_tc_config(const ccdm_op *op, int32_t *out16) {
     if (!op || !out16 || !ccdm::conv_uses_tma(*op)) return -1;

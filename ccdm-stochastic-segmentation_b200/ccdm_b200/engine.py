@@ -120,7 +120,7 @@ def pack_conv_weight_tc(w: torch.Tensor, nt: Optional[int] = None) -> torch.Tens
     co, ci, kh, kw = w.shape
     assert ci % 8 == 0
     if nt is None:
-        nt = int(_lib.lib().ccdm_conv_tc_nt(co, kh * kw))
+        nt = int(_lib.lib().ccdm_conv_tc_nt(co, kh * kw, 0))
     cop = _ceil(co, 16)
     assert cop % nt == 0
     taps = kh * kw
@@ -146,7 +146,7 @@ def pack_conv_weight_x3(w: torch.Tensor, shift: int, nt: Optional[int] = None) -
     co, ci, kh, kw = w.shape
     assert ci % 8 == 0
     if nt is None:
-        nt = int(_lib.lib().ccdm_conv_tc_nt(co, kh * kw))
+        nt = int(_lib.lib().ccdm_conv_tc_nt(co, kh * kw, 1))
     cop = _ceil(co, 16)
     assert cop % nt == 0
     taps = kh * kw

@@ -157,7 +157,7 @@ size_t ccdm_op_part_floats(const ccdm_op *op);
 int ccdm_conv_uses_tc(const ccdm_op *op);
 /* same (kept for tools; there is one tensor-core conv kernel) */
 int ccdm_conv_uses_tma(const ccdm_op *op);
-int ccdm_conv_tc_nt(int Cout, int taps); /* taps = 1 (1x1), 9 (3x3) or 16 (sub-pixel taps of an upsampling conv) */
+int ccdm_conv_tc_nt(int Cout, int taps, int x3); /* taps = 1 (1x1), 9 (3x3) or 16 (sub-pixel taps of an upsampling conv); x3 = 1 for fp16x2 */
 /* Tile / pipeline configuration the tcgen05 kernel would use for `op` (introspection for DESIGN.md, the
  * bench and tests): out16 = {PL, R, Wt, MB, WN, NT, n_cc, NS, resident, acc2, tmem_cols, tiles, n_items,
  * grid, smem bytes, K chunks per item}.  Returns -1 if `op` does not run on that kernel. */

@@ -207,16 +207,16 @@ def test_tensor_core_weight_packing_and_n_tile_rule():
     L = _lib.lib()
     want = {2: 16, 20: 32, 32: 32, 64: 64, 96: 48, 128: 64, 192: 192, 288: 144, 384: 192, 160: 160, 224: 112}
     for cout, nt in want.items():
-        got = int(L.ccdm_conv_tc_nt(cout, 1))
+        got = int(L.ccdm_conv_tc_nt(cout, 1, 0))
         cop = (cout + 15) // 16 * 16
         assert got == nt and cop % got == 0 and got % 16 == 0 and got <= 192, (cout, got)
-        got9 = int(L.ccdm_conv_tc_nt(cout, 9))  # 3x3 (and sub-pixel) convs: never wider than 64, so a weight stage stays small
+        got9 = int(L.ccdm_conv_tc_nt(cout, 9, 0))  # 3x3 (and sub-pixel) convs: never wider than 64, so a weight stage stays small
         assert got9 == (nt if cout <= 128 else max(d for d in range(16, 65, 16) if cop % d == 0)) and cop % got9 == 0
     g = torch.Generator().manual_seed(5)
     for (co, ci, k) in [(384, 128, 1), (96, 32, 3), (20, 32, 3)]:
         w = torch.randn(co, ci, k, k, generator=g)
         pk = pack_conv_weight_tc(w)
-        nt = int(L.ccdm_conv_tc_nt(co, k * k))
+        nt = int(L.ccdm_conv_tc_nt(co, k * k, 0))
         cop = (co + 15) // 16 * 16
         assert pk.dtype == torch.bfloat16 and pk.shape == (cop // nt, ci // 8, k * k, nt, 8)
         wb = w.to(torch.bfloat16)

@@ -9,7 +9,7 @@ from ccdm_b200 import _lib
 wl = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "lidc"]
 B = int(sys.argv[2]) if len(sys.argv) > 2 else wl["B"]
 m, _ = bench.build_model(wl)
-eng = m.unet.engine("bf16", dry_run=True)
+eng = m.unet.engine(sys.argv[3] if len(sys.argv) > 3 else "bf16", dry_run=True)
 prog = eng.program(B, wl["H"], wl["W"])
 eng.weights.refresh()
 prog.bind(8)
