@@ -1,13 +1,22 @@
 #!/usr/bin/env python
 """Benchmark of the CCDM reverse-process sampler (BASELINE.json: seg samples/sec, full T-step chain).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload lidc|cityscapes] [--precision fp32|bf16]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload lidc|cityscapes] [--precision exact|bf16|fp32]
     python bench.py --impl reference ...      # the reference's own CPU path on the host cores
 
-One "step" = one full T-step reverse chain over one batch of synthetic inputs (random-init weights
-of the named architecture, random conditioning image, uniform random x_T).  Prints ONE JSON line.
-Launch with torchrun for N > 1 (one rank per GPU, weak scaling: every rank runs its own batch and the
-label maps are gathered over NCCL at the end of the chain, inside the timed region).
+One "step" = one full T-step reverse chain over one batch of synthetic inputs (random-init weights of the named
+architecture, random conditioning image, uniform random x_T).  Prints ONE JSON line.  Launch with torchrun for N > 1 (one
+rank per GPU, weak scaling: every rank runs its own batch and the label maps are gathered over NCCL at the end of the
+chain, inside the timed region).
+
+The headline (`value`, `e2e`, `roofline`, `cpu_baseline`) is BASELINE.json configs[1] -- LIDC 128x128, K=2, T=250,
+batch 64 per GPU -- in the PARITY-GRADE precision mode ('exact': fp16 hi+lo operands on the tensor cores, the default of
+DenoisingModel; held to the fp32 tolerances by tests/).  The same line carries, measured in the same run:
+  * `modes.bf16`: the fast mode (bf16 storage) on the same workload, and the free-running label agreement of the two
+    modes over the full T=250 chain on the same Philox noise;
+  * `workloads`: Cityscapes 256x512 K=20 T=250 batch 8 (configs[2]) with its own value / e2e / roofline / cpu_baseline;
+    configs[3] (16 samples of ONE image split over the GPUs: strong scaling) and configs[4] (Cityscapes T=1000);
+  * `per_rank_ms` and `all_gather_ms` so an N > 1 loss can be attributed.
 """
 import argparse
 import json
@@ -35,14 +44,20 @@ WORKLOADS = {
     "cityscapes": dict(name="Cityscapes 256x512, 20-class, T=250, batch=8 (DINO-conditioned)", C_img=3, H=256, W=512, K=20,
                        T=250, B=8, fce=DINO, dataset="datasets.cityscapes", elements=227983360, flops=72.71e9),
 }
+DTYPE_NAME = {"fp32": "f32", "exact": "f16x2 (fp16 hi+lo operands, three tensor-core MMAs per product, fp32 accumulate)", "bf16": "bf16"}
+METRIC = "seg samples/sec (full T-step chain)"
 
 
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         d = json.load(open(path))
-        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops_sustained"], source="measured")
-    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback")
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops_sustained"], source="measured (MEASURED_PEAKS.json, sustained)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+def host_threads():
+    return max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
 
 
 class ClockSampler:
@@ -103,40 +118,56 @@ def build_model(wl, device=None, reference=False):
 # ----------------------------------------------------------------------------------------------
 # CPU arm: the reference's own implementation (bytecode under oracle/_ref) or the oracle port
 # ----------------------------------------------------------------------------------------------
-def cpu_chain_rate(wl, budget_s=20.0, max_steps=None):
-    """Times a bounded sample of the workload (batch 1, the first n steps of the T-step chain) on the
-    host cores and extrapolates to samples/s for the full chain."""
-    from ccdm_b200.synthetic import synthetic_inputs
-    m, kind = build_model(wl, reference=True)
-    image, feat, labels = synthetic_inputs(1, wl["C_img"], wl["H"], wl["W"], wl["K"], 384 if wl["fce"] else 0)
-    x = torch.nn.functional.one_hot(labels.long(), wl["K"]).permute(0, 3, 1, 2).float()
-    T = wl["T"]
-    torch.manual_seed(0)
-    with torch.no_grad():
-        if kind == "reference":
-            def run(n):  # the reference's strided chain with n steps == n reverse steps of identical cost
-                return m(x, image, feat, t=torch.as_tensor(10000 + n))
-        else:
-            from oracle import chain_ref
-            sd = m.unet.state_dict()
-            al, ca = m.diffusion.alphas.numpy(), m.diffusion.cumalphas.numpy()
+class CpuChain:
+    """The reference's `DenoisingModel` on the host cores, on the workload's OWN batch size.  A full chain is
+    T x (seconds per reverse step) -- minutes to hours on a CPU -- so one timed "step" is a BOUNDED SAMPLE: the first n
+    reverse steps of the T-step chain over the whole batch (every reverse step costs the same: same UNet, same posterior,
+    same draw), n chosen to fill the time budget; samples/s = B / (T x measured seconds per reverse step)."""
 
-            def run(n):
-                return chain_ref.reverse_chain(sd, labels.numpy(), image, feat, al, ca, T, 10000 + n, "majority",
-                                               feature_condition_idx=10 if wl["fce"] else None, K=wl["K"])
+    def __init__(self, wl, batch=None):
+        from ccdm_b200.synthetic import synthetic_inputs
+        self.wl, self.B = wl, batch or wl["B"]
+        self.m, self.kind = build_model(wl, reference=True)
+        image, feat, labels = synthetic_inputs(self.B, wl["C_img"], wl["H"], wl["W"], wl["K"], 384 if wl["fce"] else 0)
+        self.image, self.feat, self.labels = image, feat, labels
+        self.x = torch.nn.functional.one_hot(labels.long(), wl["K"]).permute(0, 3, 1, 2).float()
+        torch.manual_seed(0)
+
+    def run(self, n):
+        wl = self.wl
+        with torch.no_grad():
+            if self.kind == "reference":  # the reference's strided chain with n steps == n reverse steps of identical cost
+                return self.m(self.x, self.image, self.feat, t=torch.as_tensor(10000 + n))
+            from oracle import chain_ref
+            m = self.m
+            return chain_ref.reverse_chain(m.unet.state_dict(), self.labels.numpy(), self.image, self.feat, m.diffusion.alphas.numpy(),
+                                           m.diffusion.cumalphas.numpy(), wl["T"], 10000 + n, "majority",
+                                           feature_condition_idx=10 if wl["fce"] else None, K=wl["K"])
+
+    def probe(self):
+        """seconds per reverse step from a 1-step run (also the warm-up: allocator, mkldnn primitives)."""
         t0 = time.perf_counter()
-        run(2)  # warm-up (allocator, mkldnn primitives)
-        per_step = (time.perf_counter() - t0) / 2
-        n = max(2, min(T, int(budget_s / max(per_step, 1e-6))))
-        if max_steps:
-            n = min(n, max_steps)
+        self.run(1)
+        return time.perf_counter() - t0
+
+    def timed(self, n):
         t0 = time.perf_counter()
-        run(n)
-        dt = time.perf_counter() - t0
-    per_step = dt / n
-    return dict(value=1.0 / (per_step * T), unit="samples/s", cores=torch.get_num_threads(), kind=kind,
-                sample=f"batch 1, {n} of {T} reverse steps of the same workload timed ({dt:.1f} s), extrapolated to the full chain",
-                ms_per_reverse_step=per_step * 1e3, host_cpus=os.cpu_count())
+        self.run(n)
+        return time.perf_counter() - t0
+
+
+def cpu_baseline_record(wl, budget_s, batch=None):
+    """`cpu_baseline` of the GPU arm: ONE bounded sample of about `budget_s` seconds."""
+    torch.set_num_threads(host_threads())
+    c = CpuChain(wl, batch)
+    per = c.probe()
+    n = max(1, min(wl["T"], int(budget_s / max(per, 1e-6))))
+    dt = c.timed(n)
+    per = dt / n
+    return dict(value=c.B / (per * wl["T"]), unit="samples/s", cores=torch.get_num_threads(), kind=c.kind, host_cpus=os.cpu_count(),
+                sample=f"batch {c.B} (the workload's), the first {n} of {wl['T']} reverse steps timed ({dt:.1f} s); every reverse "
+                       f"step costs the same, samples/s = batch / (T x s per reverse step)",
+                ms_per_reverse_step=per * 1e3, seconds_timed=dt)
 
 
 def run_reference_arm(args, wl):
@@ -144,20 +175,27 @@ def run_reference_arm(args, wl):
     if rank != 0:
         return
     # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core it can
-    torch.set_num_threads(max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
-    steps = max(1, args.steps)
-    rates = []
-    for i in range(args.warmup + steps):
-        r = cpu_chain_rate(wl, budget_s=max(2.0, 60.0 / (args.warmup + steps)))
-        if i >= args.warmup:
-            rates.append(r)
-    value = sum(r["value"] for r in rates) / len(rates)
-    base = rates[-1]
-    base["value"] = value
-    line = {"impl": "reference", "metric": "seg samples/sec (full T-step chain)", "value": value, "unit": "samples/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["name"], "arm": "reference CPU path on host cores"}, "cpu_baseline": base,
+    torch.set_num_threads(host_threads())
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    c = CpuChain(wl)
+    per = c.probe()
+    # each timed "step" is a bounded sample: n reverse steps over the full batch, sized so the whole run stays within ~2 minutes
+    n = max(1, min(wl["T"], int(120.0 / (steps + warm) / max(per, 1e-6))))
+    for _ in range(warm):
+        c.timed(n)
+    secs = [c.timed(n) for _ in range(steps)]
+    per = sum(secs) / len(secs) / n
+    value = c.B / (per * wl["T"])
+    base = dict(value=value, unit="samples/s", cores=torch.get_num_threads(), kind=c.kind, host_cpus=os.cpu_count(),
+                sample=f"batch {c.B}, {n} of {wl['T']} reverse steps per timed step, {steps} timed steps after {warm} warm-up; "
+                       f"samples/s = batch / (T x s per reverse step)", ms_per_reverse_step=per * 1e3)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "arm": "reference CPU path on host cores", "batch": c.B,
+                       "step": f"bounded sample: {n} reverse steps of the T={wl['T']} chain over the full batch (ms_per_step is its "
+                               f"wall time; a full chain would take {per * wl['T']:.0f} s)"},
+            "ms_per_full_chain_extrapolated": per * wl["T"] * 1e3, "cpu_baseline": base,
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -209,7 +247,7 @@ def op_class(o):
         return f"input_conv {o.K}+{o.C_img}->{o.Cout} @{o.Hout}x{o.Wout}"
     tag = "conv%dx%d" % (o.ksize, o.ksize) + ("/s2" if o.stride == 2 else "") + ("/up" if o.upsample else "")
     return (f"{tag} {o.C0 + o.C1}->{o.Cout}{'+skip' if o.S0 else ''}{'+res' if o.res else ''} @{o.Hout}x{o.Wout}"
-            + (" [ffma]" if (o.exact and o.dtype == _lib.DT_BF16) else ""))
+            + (" [ffma]" if (o.exact and o.dtype != _lib.DT_F32) else ""))
 
 
 def per_op_profile(engine, prog, n_iter=3):
@@ -240,30 +278,69 @@ def per_op_profile(engine, prog, n_iter=3):
     return rows, sum(acc)
 
 
-def run_gpu_arm(args, wl):
+class Dist:
+    """Process-group plumbing of the GPU arm (one rank per GPU, NCCL)."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def sync(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, fn, n):
+        """n calls between barrier + synchronize; returns (max over ranks of the device time in ms, per-rank list)."""
+        self.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        self.sync()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            every = torch.empty(self.world, device=self.dev)
+            self.dist.all_gather_into_tensor(every, ms)
+            return float(every.max().item()), [float(v) for v in every.tolist()]
+        return float(ms.item()), [float(ms.item())]
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def measure_workload(D, wl, precision, steps, warmup, batch=None, one_image=False, e2e=True, op_table=None, dump_ops=None,
+                     op_profile_iters=5, lanes=0, keep_model=None):
+    """Chains of `wl` at `batch` per GPU in `precision`; returns (record dict on every rank, final labels of the last
+    resident chain).  `one_image`: the batch is N samples of ONE image (configs[3])."""
     from ccdm_b200 import _lib
     from ccdm_b200.models.diffusion_denoising import reverse_t_values
     from ccdm_b200.synthetic import synthetic_inputs
-    import torch.distributed as dist
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    _lib.require_device()
-
-    B, T, K, H, W = args.batch or wl["B"], args.T or wl["T"], wl["K"], wl["H"], wl["W"]
-    wl = dict(wl, T=T)
-    m, _ = build_model(wl, dev)
-    m.precision, m.noise, m.seed, m.sample_offset = args.precision, "philox", 2024, rank * B
-    engine = m.unet.engine(args.precision)
-    if args.lanes:
-        engine.lanes = args.lanes
-    lanes = min(engine.lanes, B)
-    image, feat, labels = synthetic_inputs(B, wl["C_img"], H, W, K, 384 if wl["fce"] else 0, seed=1234 + rank)
+    dev, world, rank = D.dev, D.world, D.rank
+    B, T, K, H, W = batch or wl["B"], wl["T"], wl["K"], wl["H"], wl["W"]
+    m = keep_model if keep_model is not None else build_model(wl, dev)[0]
+    m.precision, m.noise, m.seed, m.sample_offset = precision, "philox", 2024, rank * B
+    engine = m.unet.engine(precision)
+    if lanes:
+        engine.lanes = lanes
+    n_lanes = min(engine.lanes, B)
+    if one_image:
+        image, feat, _ = synthetic_inputs(1, wl["C_img"], H, W, K, 384 if wl["fce"] else 0, seed=1234)
+        image = image.repeat_interleave(B, dim=0)  # what the reference's evaluator does (evaluate_lidc_uncertainty.py:96)
+        feat = feat.repeat_interleave(B, dim=0) if feat is not None else None
+        labels = synthetic_inputs(world * B, wl["C_img"], H, W, K, 0, seed=99)[2][rank * B:(rank + 1) * B]
+    else:
+        image, feat, labels = synthetic_inputs(B, wl["C_img"], H, W, K, 384 if wl["fce"] else 0, seed=1234 + rank)
     x_host = torch.nn.functional.one_hot(labels.long(), K).permute(0, 3, 1, 2).float().contiguous().pin_memory()
     image_host = image.pin_memory()
     feat_host = feat.pin_memory() if feat is not None else None
@@ -272,12 +349,14 @@ def run_gpu_arm(args, wl):
     ts = reverse_t_values(T, None)
     al, ca = m._schedule_host()
     gathered = torch.empty((world * B, H, W), dtype=torch.uint8, device=dev) if world > 1 else None
+    last = {}
 
     def chain_resident():
         lab, _ = engine.run_chain(x_dev, image_dev, feat_dev, ts, al, ca, _lib.DRAW_MAJORITY, noise="philox", seed=2024,
                                   sample0=rank * B)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, lab)  # the single collective of the path
+            D.dist.all_gather_into_tensor(gathered, lab)  # the single collective of the path
+        last["labels"] = lab
         return lab
 
     def chain_e2e():
@@ -285,81 +364,71 @@ def run_gpu_arm(args, wl):
                 feat_host.to(dev, non_blocking=True) if feat_host is not None else None)["diffusion_out"]
         lab = out.argmax(dim=1).to(torch.uint8)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, lab)
+            D.dist.all_gather_into_tensor(gathered, lab)
             return gathered.cpu()
         return lab.cpu()
 
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, n):
-        sync_all()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(n):
-            fn()
-        e1.record()
-        sync_all()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
-
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         chain_resident()
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(D.local)
     clocks.start()
-    ms_total = timed(chain_resident, args.steps)
+    ms_total, per_rank = D.timed(chain_resident, steps)
     clk = clocks.stop()
-    ms_step = ms_total / args.steps
-    value = world * B / (ms_step / 1e3)
-
-    chain_e2e()  # warm-up of the host path
-    ms_e2e = timed(chain_e2e, max(1, min(args.steps, 2))) / max(1, min(args.steps, 2))
-    e2e_value = world * B / (ms_e2e / 1e3)
-    h2d = x_host.numel() * 4 + image_host.numel() * 4 + (feat_host.numel() * 4 if feat_host is not None else 0)
-    d2h = world * B * H * W
-
-    # with lanes the batch runs as `lanes` sub-batch programs; the per-op table describes one of them
-    prof_engine = engine._children[0] if lanes > 1 else engine
-    prog = prof_engine.program((B + lanes - 1) // lanes if lanes > 1 else B, H, W)
-    line = None
-    if rank == 0:
-        peaks = measured_peaks()
-        rows, step_ms_eager = per_op_profile(prof_engine, prog, n_iter=0 if args.no_op_profile else 5)
-        if args.dump_ops:
-            with open(args.dump_ops, "w") as fh:
+    ms_step = ms_total / steps
+    rec = {"workload": wl["name"] if not one_image else f"{wl['name'].split(',')[0]}, {wl['K']}-class, T={T}, {world * B} samples of ONE image over {world} GPU(s)",
+           "precision": precision, "dtype": DTYPE_NAME[precision], "batch_per_gpu": B, "T": T, "value": world * B / (ms_step / 1e3),
+           "unit": "samples/s", "ms_per_step": ms_step, "steps": steps, "warmup": warmup, "per_rank_ms": [v / steps for v in per_rank],
+           "clocks": clk, "lanes": n_lanes}
+    if world > 1:  # the collective alone (same buffers), so an N > 1 loss can be attributed
+        lab = last["labels"]
+        ag_ms, _ = D.timed(lambda: D.dist.all_gather_into_tensor(gathered, lab), 20)
+        rec["all_gather_ms"] = ag_ms / 20
+    prof_engine = engine._children[0] if n_lanes > 1 else engine
+    prog = prof_engine.program((B + n_lanes - 1) // n_lanes if n_lanes > 1 else B, H, W)
+    rec["launches_per_reverse_step"] = prog.n_ops
+    rec["gpu_launches"] = prog.n_ops * T * steps * n_lanes
+    if e2e:
+        n_e2e = max(1, min(steps, 2))
+        chain_e2e()  # warm-up of the host path
+        ms_e2e = D.timed(chain_e2e, n_e2e)[0] / n_e2e
+        h2d = x_host.numel() * 4 + image_host.numel() * 4 + (feat_host.numel() * 4 if feat_host is not None else 0)
+        rec["e2e"] = {"value": world * B / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": world * B * H * W,
+                      "ms_per_step": ms_e2e, "api": "DenoisingModel.forward(x one-hot fp32, image[, features]) from pinned host tensors; labels read back"}
+    chain_bytes = (wl["elements"] * prog.esize + 3 * K * H * W * 4) * B * T
+    peaks = measured_peaks()
+    roof_chain = chain_bytes / (ms_step * 1e-3) / 1e9
+    rec["roofline_chain"] = {"bound": "hbm", "achieved": roof_chain, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": roof_chain / peaks["hbm_gbs"],
+                             "bytes_per_sample_step": chain_bytes / (B * T), "storage_bytes_per_element": prog.esize,
+                             "tflops": wl["flops"] * B * T / (ms_step * 1e-3) / 1e12}
+    if rank == 0 and op_profile_iters is not None:
+        rows, step_ms_eager = per_op_profile(prof_engine, prog, n_iter=op_profile_iters)
+        if dump_ops:
+            with open(dump_ops, "w") as fh:
                 json.dump([dict(index=i, op_class=op_class(prog._op_array[i]), bytes=op_bytes(prog._op_array[i], prog.esize),
                                 flops=op_flops(prog._op_array[i])) for i in range(prog.n_ops)], fh, indent=0)
-        if args.op_table:
-            os.makedirs(os.path.dirname(os.path.abspath(args.op_table)), exist_ok=True)
-            with open(args.op_table, "w") as fh:
+        if op_table:
+            os.makedirs(os.path.dirname(os.path.abspath(op_table)), exist_ok=True)
+            with open(op_table, "w") as fh:
                 fh.write("op class | launches | us/launch | ideal us (HBM) | GB/s | TF/s | share\n")
                 for k, v in sorted(rows.items(), key=lambda kv: -kv[1]["ms"]):
                     us = v["ms"] * 1e3 / v["launches"]
                     by = v["bytes"] / v["launches"]
                     fh.write(f"{k} | {v['launches']} | {us:.1f} | {by / peaks['hbm_gbs'] / 1e3:.1f} | {by / us / 1e3:.0f} | "
                              f"{v['flops'] / v['launches'] / us / 1e6:.1f} | {v['ms'] / step_ms_eager:.3f}\n")
-                fh.write(f"sum of per-op times {step_ms_eager:.3f} ms; graph step {ms_step / T:.3f} ms; ops {prog.n_ops}\n")
+                fh.write(f"sum of per-op times {step_ms_eager:.3f} ms; graph step {ms_step / T:.3f} ms; ops {prog.n_ops}; precision {precision}\n")
         top = max(rows.items(), key=lambda kv: kv[1]["ms"])
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch per op class, from the committed ncu capture
+        traffic, traffic_source = None, None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch per op class, from a committed ncu capture
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(args.workload, {}).get(top[0])
+            tj = json.load(open(tpath))
+            key = ("lidc" if wl["K"] == 2 else "cityscapes") + ("" if precision == "bf16" else "_" + precision)
+            traffic = tj.get(key, {}).get(top[0])
+            if traffic is not None:
+                traffic_source = f"static: ncu --set full capture committed under profiles/ ({tj.get('_source', {}).get(key, 'see profiles/README.md')}), not measured in this run"
         per_launch_ms = top[1]["ms"] / top[1]["launches"]
         per_launch_bytes = top[1]["bytes"] / top[1]["launches"]
         achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
-        esize = prog.esize
-        chain_bytes = (wl["elements"] * esize + 3 * K * H * W * 4) * B * T
-        roof_chain = chain_bytes / (ms_step * 1e-3) / 1e9
-        cpu = None
-        if not args.no_cpu_baseline and world == 1:  # reported at N = 1 only (the reference arm covers N > 1)
-            torch.set_num_threads(max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
-            cpu = cpu_chain_rate(wl, budget_s=args.cpu_budget)
-        is_attn = top[0].startswith("attention")
-        if is_attn:  # the attention kernel is bound by the tensor / MUFU pipes, not by HBM
+        if top[0].startswith("attention"):  # the attention kernel is bound by the tensor / MUFU pipes, not by HBM
             tf = top[1]["flops"] / top[1]["launches"] / (per_launch_ms * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": top[0], "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": tf / peaks["bf16_tflops"], "traffic": traffic}
@@ -367,30 +436,96 @@ def run_gpu_arm(args, wl):
             roof = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
                     "tflops": top[1]["flops"] / top[1]["launches"] / (per_launch_ms * 1e-3) / 1e12}
-        roof.update(peak_source=peaks["source"], launches_per_step=top[1]["launches"], avg_launch_ms=per_launch_ms,
+        roof.update(traffic_source=traffic_source, peak_source=peaks["source"], launches_per_step=top[1]["launches"], avg_launch_ms=per_launch_ms,
                     share_of_step=top[1]["ms"] / step_ms_eager, algorithmic_bytes_per_launch=per_launch_bytes)
+        rec["roofline"] = roof
+        rec["kernel_breakdown"] = sorted(([k, round(v["ms"], 4), v["launches"]] for k, v in rows.items()), key=lambda r: -r[1])[:12]
+    return rec, last["labels"], m
+
+
+def agreement(a, b):
+    eq = (a == b).float()
+    return {"labels_equal": float(eq.mean()), "per_sample_min": float(eq.flatten(1).mean(1).min()),
+            "what": "fraction of pixels whose FINAL label is the same after the full free-running T-step chain of each mode on the same "
+                    "inputs and the same in-kernel Philox noise (the chain is chaotic: one flipped pixel feeds back into every later step)"}
+
+
+def run_gpu_arm(args):
+    from ccdm_b200 import _lib
+    D = Dist()
+    _lib.require_device()
+    rank, world = D.rank, D.world
+    steps, warm = args.steps, args.warmup
+    small = max(1, min(steps, 2))  # timed chains of the secondary records
+    head_wl = dict(WORKLOADS[args.workload], T=args.T or WORKLOADS[args.workload]["T"])
+    line = None
+
+    # ---- headline: the named workload in the requested precision -----------------------------------------------------
+    rec, lab_main, m = measure_workload(D, head_wl, args.precision, steps, warm, batch=args.batch or None, op_table=args.op_table or None,
+                                        dump_ops=args.dump_ops or None, op_profile_iters=None if args.no_op_profile else 5, lanes=args.lanes)
+    modes, workloads = {}, {}
+    if not args.headline_only:
+        # ---- the other tensor-core mode on the same workload, same inputs, same noise: speed and T-step agreement ------
+        other = "bf16" if args.precision != "bf16" else "exact"
+        r2, lab2, _ = measure_workload(D, head_wl, other, small, warm, batch=args.batch or None, e2e=False, keep_model=m,
+                                       op_profile_iters=None if args.no_op_profile else 3)
+        r2[f"agreement_with_{args.precision}"] = agreement(lab_main, lab2)
+        modes[other] = r2
+        del m
+        torch.cuda.empty_cache()
+        # ---- the other BASELINE workload (configs[1] <-> configs[2]) ------------------------------------------------------
+        oname = "cityscapes" if args.workload == "lidc" else "lidc"
+        owl = WORKLOADS[oname]
+        r3, lab3, m3 = measure_workload(D, owl, args.precision, small, warm, op_profile_iters=None if args.no_op_profile else 3)
+        r4, lab4, _ = measure_workload(D, owl, other, small, warm, e2e=False, keep_model=m3, op_profile_iters=None)
+        r4[f"agreement_with_{args.precision}"] = agreement(lab3, lab4)
+        r3["modes"] = {other: r4}
+        workloads[oname] = r3
+        del m3
+        torch.cuda.empty_cache()
+        # ---- configs[3]: 16 samples of ONE LIDC image split over the GPUs (strong scaling; 2 per GPU at N = 8) ----------
+        lidc = WORKLOADS["lidc"]
+        if 16 % world == 0:
+            r5, _, m5 = measure_workload(D, lidc, args.precision, small, warm, batch=16 // world, one_image=True, op_profile_iters=None)
+            r5["scaling"] = "strong (16 samples in total)"
+            workloads["lidc_16_samples_one_image"] = r5
+            del m5
+        # ---- configs[4]: Cityscapes T=1000, batch 8 per GPU ----------------------------------------------------------------
+        r6, _, m6 = measure_workload(D, dict(WORKLOADS["cityscapes"], T=1000, name="Cityscapes 256x512, 20-class, T=1000, batch=8 per GPU"),
+                                     args.precision, 1, 1, e2e=False, op_profile_iters=None)
+        r6["note"] = "1 warm-up + 1 timed chain (a chain is ~5 s); not subject to the W >= 3 rule of the headline"
+        workloads["cityscapes_T1000"] = r6
+        del m6
+        torch.cuda.empty_cache()
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:  # reported at N = 1 only (the reference arm covers N > 1)
+            cpu = cpu_baseline_record(head_wl, args.cpu_budget)
+            for k, r in workloads.items():
+                if k in WORKLOADS:
+                    r["cpu_baseline"] = cpu_baseline_record(WORKLOADS[k], args.cpu_budget)
+        B = rec["batch_per_gpu"]
         line = {
-            "metric": "seg samples/sec (full T-step chain)", "value": value, "unit": "samples/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"fp32": "f32", "exact": "f16x2 (fp16 hi+lo operands, fp32 accumulate)", "bf16": "bf16"}[args.precision], "data": "synthetic",
-            "config": {"workload": wl["name"], "batch_per_gpu": B, "T": T, "precision": args.precision,
+            "metric": METRIC, "value": rec["value"], "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": rec["dtype"],
+            "data": "synthetic",
+            "config": {"workload": head_wl["name"], "batch_per_gpu": B, "T": head_wl["T"], "precision": args.precision,
+                       "parity_mode": args.precision if args.precision != "bf16" else None,
                        "noise": "philox (in-kernel)", "parallelism": f"sample-sharded x{world}, 1 NCCL all-gather of labels",
                        "l2_policy": "per-step activation traffic exceeds L2 (126 MB): inputs larger than L2, no flush",
-                       "cuda_graph": True, "lanes": lanes},
-            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e},
-            "gpu_launches": prog.n_ops * T * args.steps * lanes,
-            "clocks": clk,
-            "roofline": roof,
-            "roofline_chain": {"bound": "hbm", "achieved": roof_chain, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                               "frac": roof_chain / peaks["hbm_gbs"],
-                               "bytes_per_sample_step": chain_bytes / (B * T), "tflops": wl["flops"] * B * T / (ms_step * 1e-3) / 1e12},
-            "cpu_baseline": cpu,
-            "kernel_breakdown": sorted(([k, round(v["ms"], 4), v["launches"]] for k, v in rows.items()), key=lambda r: -r[1])[:12],
+                       "cuda_graph": True, "lanes": rec["lanes"]},
+            "e2e": rec.get("e2e"), "gpu_launches": rec["gpu_launches"], "clocks": rec["clocks"], "roofline": rec.get("roofline"),
+            "roofline_chain": rec["roofline_chain"], "cpu_baseline": cpu, "per_rank_ms": rec["per_rank_ms"],
+            "all_gather_ms": rec.get("all_gather_ms"), "kernel_breakdown": rec.get("kernel_breakdown"),
+            "parity": {"mode": args.precision,
+                       "statement": "'exact' and 'fp32' modes are held to max|dx0| <= 2e-4, labels identical outside a 1e-3 race margin, "
+                                    "reference fixture chains replayed exactly (tests/test_gpu_chain.py, tests/test_gpu_fullsize.py at "
+                                    "these sizes); 'bf16' is a fast mode with stated looser bounds",
+                       "committed_report": "profiles/r02_parity_report.json"},
+            "modes": modes, "workloads": workloads,
         }
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    D.close()
     if line is not None:
         print(json.dumps(line), flush=True)
 
@@ -402,22 +537,22 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="lidc", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default=os.environ.get("CCDM_PRECISION", "bf16"), choices=["fp32", "exact", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("CCDM_PRECISION", "exact"), choices=["fp32", "exact", "bf16"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (parity/debug runs)")
     ap.add_argument("--T", type=int, default=0, help="override the chain length (debug runs; invalid as a bench number)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--headline-only", action="store_true", help="skip the `modes` / `workloads` records (A/B and profiler runs)")
     ap.add_argument("--lanes", type=int, default=0, help="sub-batch streams per chain (0: engine default, CCDM_LANES)")
     ap.add_argument("--dump-ops", default="", help="write the op list of one reverse step (launch order, op class, algorithmic bytes) as JSON")
     ap.add_argument("--op-table", default="", help="write the per-op-class CUDA-event table to this file")
     ap.add_argument("--no-op-profile", action="store_true", help="skip the per-op CUDA-event pass (ncu runs)")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
     if args.impl == "reference":
-        return run_reference_arm(args, wl)
+        return run_reference_arm(args, WORKLOADS[args.workload])
     if args.warmup < 3:
         sys.stderr.write("note: fewer than 3 warm-up chains; not a valid bench number\n")
-    run_gpu_arm(args, wl)
+    run_gpu_arm(args)
 
 
 if __name__ == "__main__":

@@ -260,7 +260,7 @@ class UNetModel(nn.Module):
     def feat_channels(self) -> int:
         return sum(b.feat_concat for b in self.arch.blocks)
 
-    def engine(self, precision: str = "fp32", dry_run: bool = False):
+    def engine(self, precision: str = "exact", dry_run: bool = False):
         from ...engine import UNetEngine
         key = (precision, dry_run, next(self.parameters()).device)
         eng = self._engines.get(key)
@@ -278,7 +278,7 @@ class UNetModel(nn.Module):
         """
         assert (y is not None) == (self.num_classes is not None), \
             "must specify y if and only if the model is class-conditional"
-        precision = getattr(self, "precision", "fp32")
+        precision = getattr(self, "precision", "exact")
         probs = self.engine(precision).single_step(x, input_condition, feature_condition, timesteps,
                                                    softmax=self.sofmtax_output)
         return {"diffusion_out": probs, "logits": None}

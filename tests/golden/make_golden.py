@@ -178,8 +178,39 @@ def gen_unet_and_chain(tag, T, B, C_img, H, W, K, fce, channel_mult, t_probe, st
     save(f"{tag}.npz", **out)
 
 
+MANIFEST_CASES = {
+    # tag: (C_img, H, W, K, DINO concat?, channel_mult, base_channels)
+    "lidc128": (1, 128, 128, 2, False, None, 32),
+    "lidc64": (1, 64, 64, 2, False, None, 32),
+    "cs256x512": (3, 256, 512, 20, True, None, 32),
+    "cs64x128": (3, 64, 128, 20, True, (1, 1, 2, 2, 4, 4), 32),
+    "base64_256": (3, 256, 256, 5, False, None, 64),
+}
+
+
+def gen_manifest():
+    """state_dict_manifest.json: key names, order and shapes of the reference ``DenoisingModel.state_dict()`` for five
+    configurations -- what a strict ``load_state_dict`` of a reference checkpoint requires of ``ccdm_b200.models``."""
+    import json
+    man = {}
+    for tag, (C, H, W, K, fce, mult, base) in MANIFEST_CASES.items():
+        p = dict(UNET_PARAMS, channel_mult=mult, base_channels=base)
+        m = models.build_model(250, "cosine", {"s": 0.008}, [(C, H, W), (K, H, W)], (C, H, W), "unet_openai", p, "d", "majority",
+                               DINO if fce else None)
+        man[tag] = dict(args=[C, H, W, K, fce, list(mult) if mult else None, base],
+                        keys=[[k, list(v.shape)] for k, v in m.state_dict().items()])
+    path = os.path.join(HERE, "state_dict_manifest.json")
+    with open(path, "w") as fh:
+        json.dump(man, fh)
+    print(f"state_dict_manifest.json: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if sys.argv[1:] == ["manifest"]:
+        gen_manifest()
+        sys.exit(0)
+    gen_manifest()
     gen_schedules()
     gen_t_values()
     gen_posterior()

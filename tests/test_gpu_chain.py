@@ -221,12 +221,21 @@ def test_chain_is_deterministic_and_sharding_invariant(cuda_device):
     image, _, labels = synthetic_inputs(4, C_img, H, W, K)
     m.noise, m.seed = "philox", 77
     tt = torch.as_tensor(10000 + 6)
-    full = m(_onehot(labels, K).cuda(), image.cuda(), None, t=tt)["diffusion_out"]
-    again = m(_onehot(labels, K).cuda(), image.cuda(), None, t=tt)["diffusion_out"]
-    assert torch.equal(full, again)
-    m.sample_offset = 2
-    shard = m(_onehot(labels[2:], K).cuda(), image[2:].cuda(), None, t=tt)["diffusion_out"]
-    assert torch.equal(full[2:], shard)
+    for prec in ("fp32", "exact"):
+        m.precision, m.sample_offset = prec, 0
+        full = m(_onehot(labels, K).cuda(), image.cuda(), None, t=tt)["diffusion_out"]
+        again = m(_onehot(labels, K).cuda(), image.cuda(), None, t=tt)["diffusion_out"]
+        assert torch.equal(full, again)  # deterministic in every mode
+        m.sample_offset = 2
+        shard = m(_onehot(labels[2:], K).cuda(), image[2:].cuda(), None, t=tt)["diffusion_out"]
+        if prec == "fp32":
+            assert torch.equal(full[2:], shard)
+        else:
+            # tensor-core modes: same noise, same arithmetic per pixel, but the fp32 partial sums of the GroupNorm statistics
+            # are grouped per CTA and the tiling follows the batch: 1e-7-level differences, a near-tie may flip
+            agree = float((full[2:] == shard).float().mean())
+            _report("exact_shard_agreement", agreement=agree)
+            assert agree >= 0.999, agree
 
 
 def test_sub_batch_lanes_do_not_change_the_result(cuda_device):
@@ -237,7 +246,7 @@ def test_sub_batch_lanes_do_not_change_the_result(cuda_device):
     from ccdm_b200.synthetic import synthetic_inputs
     image, _, labels = synthetic_inputs(5, C_img, H, W, K)
     tt = torch.as_tensor(10000 + 5)
-    for prec in ("fp32", "bf16"):
+    for prec in ("fp32", "exact", "bf16"):
         m = build_ours(T, C_img, H, W, K, "majority").cuda()
         m.noise, m.seed, m.precision = "philox", 21, prec
         eng = m.unet.engine(prec)
@@ -253,8 +262,8 @@ def test_sub_batch_lanes_do_not_change_the_result(cuda_device):
             # GroupNorm statistics are grouped per CTA, so a different split changes their summation order (1e-7
             # relative) and a near-tie can flip: agreement, not bit equality
             agree = float((one == three).float().mean())
-            _report("bf16_lanes_agreement", agreement=agree)
-            assert agree >= 0.995, agree
+            _report(f"{prec}_lanes_agreement", agreement=agree)
+            assert agree >= (0.999 if prec == "exact" else 0.995), agree
 
 
 def test_x_T_drawn_on_device_and_label_input(cuda_device):
@@ -290,7 +299,7 @@ def test_graph_replay_equals_eager_launches(cuda_device):
     T, B, C_img, H, W, K, fce, mult, t_probe, steps = GOLDEN_CASES[tag]
     m, image, feat, labels = _case(tag)
     m.noise, m.seed = "philox", 5
-    eng = m.unet.engine("fp32")
+    eng = m.unet.engine(m.precision)
     tt = torch.as_tensor(10000 + 5)
     eng.use_graph = True
     a = m(_onehot(labels, K).cuda(), image.cuda(), None, t=tt)["diffusion_out"]

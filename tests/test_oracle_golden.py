@@ -132,6 +132,33 @@ def test_chain_restatement_matches_reference(tag):
     np.testing.assert_allclose(probs, g["chain_confidence_probs"], rtol=0, atol=2e-6)
 
 
+@pytest.mark.parametrize("tag", ["lidc128_b64", "cs256x512_b2"])
+def test_oracle_matches_reference_fixture_at_benchmark_size(tag):
+    """The BASELINE-size fixtures (tests/golden/make_golden_full.py) pin the oracle as well.  Samples are independent, so
+    the oracle evaluates a subset of the batch: the samples / windows the fixture keeps in full."""
+    from conftest import DINO, build_ours
+    from ccdm_b200.synthetic import synthetic_inputs
+    g = golden(tag + ".npz")
+    T, B, C_img, H, W, K, has_fce, steps, blk = (int(v) for v in g["cfg"])
+    m = build_ours(T, C_img, H, W, K, "majority", DINO if has_fce else None, None)
+    image, feat, labels = synthetic_inputs(B, C_img, H, W, K, 384 if has_fce else 0)
+    sd = m.unet.state_dict()
+    sel = [0, B - 1] if tag == "lidc128_b64" else [0]
+    t = 37 if tag == "lidc128_b64" else 100
+    x = chain_ref.labels_to_onehot(labels[sel].numpy(), K)
+    out = unet_ref.unet_forward(sd, x, image[sel], feat[sel] if feat is not None else None, torch.full((len(sel),), float(t)),
+                                feature_condition_idx=10 if has_fce else None).permute(0, 2, 3, 1).numpy()
+    if tag == "lidc128_b64":
+        for i, b in enumerate(sel):
+            np.testing.assert_allclose(out[i], g[f"x0pred_t{t}_sample{b}"], rtol=0, atol=1e-6)
+    else:
+        for i, (y0, y1, xa, xb) in enumerate(((0, 16, 0, 64), (120, 136, 48, 144), (240, 256, 448, 512))):
+            np.testing.assert_allclose(out[0, y0:y1, xa:xb], g[f"x0pred_t{t}_window{i}"][0], rtol=0, atol=1e-6)
+        assert (out[0].argmax(-1) != g[f"x0pred_t{t}_argmax"][0]).mean() < 1e-4  # batch-1 vs batch-2 blocking in mkldnn: near-ties only
+    bm = out.astype(np.float64).reshape(len(sel), H // blk, blk, W // blk, blk, K).mean(axis=(2, 4))
+    np.testing.assert_allclose(bm, g[f"x0pred_t{t}_blockmean"][sel], rtol=0, atol=1e-6)
+
+
 @pytest.mark.parametrize("K", [2, 20])
 def test_fast_sampling_algebra_agrees_with_exact_path(K):
     """The algebra of the bf16 engine mode's sampling step (head.cu: head_sample_fast) restated in numpy fp32 -- softmax and
