@@ -48,7 +48,7 @@ def _check(out, args, kw, ostat=None, what=""):
         rms = (s2 / n).sqrt()
         # sums of fp32 values accumulated in fp32 per thread / warp / CTA and folded in double: 1e-6 of n * rms
         assert float(((ostat[..., 0].cpu() - s1).abs() / (n * rms + 1e-9)).max()) < 2e-6
-        assert float(((ostat[..., 1].cpu() - s2).abs() / (n * rms * rms + 1e-9)).max()) < 4e-6
+        assert float(((ostat[..., 1].cpu() - s2).abs() / (n * rms * rms + 1e-9)).max()) < 1e-5
 
 
 @pytest.mark.parametrize("B,C0,C1,Cout,H,W", [(2, 32, 0, 32, 128, 128), (1, 32, 32, 32, 64, 64), (2, 64, 32, 64, 32, 32),

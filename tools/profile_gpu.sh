@@ -6,7 +6,8 @@
 # command: duration, DRAM bytes, tensor-pipe activity, instructions), gpurun_out/<tag>_ops.json (the op list, launch
 # order) and --set full captures of the two conv launches and of the first attention launch.
 TAG=${1:-prof}; WL=${2:-lidc}; SKIP_A=${3:-0}; SKIP_B=${4:-0}
-BENCH="python bench.py --workload $WL --precision bf16 --steps 1 --warmup 1 --T 2 --no-cpu-baseline --no-op-profile"
+PREC=${PREC:-exact}
+BENCH="python bench.py --workload $WL --precision $PREC --headline-only --steps 1 --warmup 1 --T 2 --no-cpu-baseline --no-op-profile"
 OURS='regex:conv_|attention_|head_kernel|time_table|encode_input'
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum
 mkdir -p gpurun_out
