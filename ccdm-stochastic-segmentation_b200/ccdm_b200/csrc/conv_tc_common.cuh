@@ -301,7 +301,7 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
             for (int i = 0; i < CGW; ++i) s1[i] = 0.f, s2[i] = 0.f;
             int o = o0, c = c0;
             if (!waited) {
-                mbar_wait(acc_full + buf, aph);
+                mbar_wait<X3 ? 512 : 256>(acc_full + buf, aph);  // the next accumulator is microseconds away
                 tc_fence_after();
                 waited = true;
                 if (tid == 0) CCDM_EPI_TL(it - it_begin, 0);
@@ -423,7 +423,7 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
             }
         }
         if (!waited) {  // a warp without a column group of its own still has to observe the phase
-            mbar_wait(acc_full + buf, aph);
+            mbar_wait<X3 ? 512 : 256>(acc_full + buf, aph);  // the next accumulator is microseconds away
             tc_fence_after();
         }
         // accumulator buffer drained: hand it back to the MMA warps

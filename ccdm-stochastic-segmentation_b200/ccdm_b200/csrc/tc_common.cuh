@@ -20,33 +20,35 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Waits for the phase with the given parity.  try_wait suspends the thread in hardware for up to the
-// time hint and wakes when the phase completes, so a waiting warp does not eat issue slots; a protocol
-// bug must not hang the GPU: after ~2 s the kernel traps (the launch fails loudly instead of wedging).
+// Waits for the phase with the given parity.  One try_wait; if the phase is not complete the thread sleeps SLEEP_NS
+// between further tries.  The loop is five instructions on purpose: a polling warp is always eligible and takes issue
+// slots from the warps that do the work on its scheduler (ncu source page of the fp16x2 conv kernel, round 2: 47 M of 118 M
+// executed warp-instructions were the previous 21-instruction poll loop with its back-off and clock64 bookkeeping), so
+// callers pick SLEEP_NS from how long the wait typically is (an accumulator hand-off is microseconds, a pipeline stage
+// hundreds of nanoseconds).  A protocol bug must not hang the GPU: after ~4 s of polling the kernel traps (the launch
+// fails loudly instead of wedging).
+__device__ __forceinline__ uint32_t mbar_try(uint32_t addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    return ok;
+}
+template <uint32_t SLEEP_NS = 32>
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
-    uint32_t ok, spins = 0;
-    long long t0 = 0;
-    for (;;) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity), "r"(0x989680u)
-            : "memory");
-        if (ok) break;
-        // back off: a polling warp is always eligible and would take issue slots from the warps that do the work
-        // on its scheduler (measured: ~30 % of all issued instructions of conv_tma were polls)
-        if (spins >= 2u) __nanosleep(spins < 16u ? 40u : 200u);
-        if ((++spins & 63u) == 0u) {
-            const long long now = clock64();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000ll) __trap();  // no printf here: its argument block and code would sit in every inlined wait
-        }
-    }
+    if (mbar_try(addr, parity)) return;
+    uint32_t n = 0;
+    do {
+        __nanosleep(SLEEP_NS);
+        if (++n == 4000000000u / SLEEP_NS) __trap();  // no printf here: its argument block and code would sit in every inlined wait
+    } while (!mbar_try(addr, parity));
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

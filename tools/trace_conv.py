@@ -13,7 +13,7 @@ wl = bench.WORKLOADS[wlname]
 L = _lib.lib()
 dev = torch.device("cuda", 0)
 m, _ = bench.build_model(wl, dev)
-eng = m.unet.engine("bf16")
+eng = m.unet.engine(sys.argv[2] if len(sys.argv) > 2 else "bf16")
 B = wl["B"]
 image, feat, labels = synthetic_inputs(B, wl["C_img"], wl["H"], wl["W"], wl["K"], 384 if wl["fce"] else 0)
 al, ca = m._schedule_host()
