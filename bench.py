@@ -400,12 +400,12 @@ def measure_workload(D, wl, precision, steps, warmup, batch=None, one_image=Fals
     rec["roofline_chain"] = {"bound": "hbm", "achieved": roof_chain, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": roof_chain / peaks["hbm_gbs"],
                              "bytes_per_sample_step": chain_bytes / (B * T), "storage_bytes_per_element": prog.esize,
                              "tflops": wl["flops"] * B * T / (ms_step * 1e-3) / 1e12}
+    if rank == 0 and dump_ops:
+        with open(dump_ops, "w") as fh:
+            json.dump([dict(index=i, op_class=op_class(prog._op_array[i]), bytes=op_bytes(prog._op_array[i], prog.esize),
+                            flops=op_flops(prog._op_array[i])) for i in range(prog.n_ops)], fh, indent=0)
     if rank == 0 and op_profile_iters is not None:
         rows, step_ms_eager = per_op_profile(prof_engine, prog, n_iter=op_profile_iters)
-        if dump_ops:
-            with open(dump_ops, "w") as fh:
-                json.dump([dict(index=i, op_class=op_class(prog._op_array[i]), bytes=op_bytes(prog._op_array[i], prog.esize),
-                                flops=op_flops(prog._op_array[i])) for i in range(prog.n_ops)], fh, indent=0)
         if op_table:
             os.makedirs(os.path.dirname(os.path.abspath(op_table)), exist_ok=True)
             with open(op_table, "w") as fh:

@@ -27,7 +27,7 @@ class StepEntry(ctypes.Structure):
 
 _I32 = ["kind", "dtype", "B", "Hin", "Win", "Hout", "Wout", "C0", "C1", "Cout", "ksize", "stride", "upsample", "gn", "silu",
         "S0", "S1", "heads", "head_dim", "K", "C_img", "emb_off", "emb_cols", "emb_bstride", "noise_mode", "sample0",
-        "out_dtype", "src_kind", "exact", "acc_shift", "reserved", "st_slots0", "st_slots1", "st_ips0", "st_ips1", "st_items0", "st_items1",
+        "out_dtype", "src_kind", "exact", "acc_shift", "img_rep", "st_slots0", "st_slots1", "st_ips0", "st_ips1", "st_items0", "st_items1",
         "st_grid0", "st_grid1", "st_rows0", "st_rows1", "pad_align"]
 _U64 = ["seed", "src0", "src1", "stat0", "stat1", "gamma", "beta", "weight", "bias", "emb", "skip0", "skip1", "skip_w", "res",
         "out", "ostat", "part", "ticket", "labels_in", "labels_out", "image", "noise", "probs_out", "noise_out", "steps",
@@ -79,7 +79,9 @@ def lib():
     L.ccdm_time_table.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 6 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
     L.ccdm_onehot_to_labels.argtypes = [ctypes.c_void_p] + [ctypes.c_int64] * 4 + [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_void_p]
     L.ccdm_labels_to_onehot_i64.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
-    L.ccdm_nchw_to_nhwc_stats.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 5 + [ctypes.c_void_p] * 3
+    L.ccdm_nchw_to_nhwc_stats.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 5 + [ctypes.c_void_p] * 2 + [ctypes.c_int, ctypes.c_void_p]
+    L.ccdm_vote.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                            ctypes.c_void_p]
     L.ccdm_posterior_draw.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                       ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32,
                                       ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]

@@ -16,7 +16,7 @@ LIB = os.path.join(HERE, "libccdm_b200.so")
 STAMP = os.path.join(HERE, "libccdm_b200.stamp")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr",
-         "-Xcompiler", "-fPIC,-fvisibility=default", "-Xptxas", "-v"] + (["-DCCDM_TRACE"] if os.environ.get("CCDM_TRACE") == "1" else []) + (
+         "-Xcompiler", "-fPIC,-fvisibility=default", "-Xptxas", "-v"] + (["-DCCDM_TRACE"] if os.environ.get("CCDM_TRACE") == "1" else []) + (["-DCCDM_ABLATE"] if os.environ.get("CCDM_ABLATE_BUILD") == "1" else []) + (
              ["-DCCDM_SILU_EXPERIMENTS"] if os.environ.get("CCDM_SILU_EXPERIMENTS") == "1" else [])
 
 

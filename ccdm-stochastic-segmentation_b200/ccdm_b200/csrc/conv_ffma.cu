@@ -50,6 +50,7 @@ struct ConvP {
     int B, Hin, Win, Hout, Wout, C0, C1, Cin, CinP, Cout, CoutP;
     int upsample, gn, silu, S0, S1, K, C_img, emb_off, emb_cols, emb_bstride, src_kind, out_f32;
     int tiles_x, tiles_y;
+    int img_rep;  // samples per conditioning image (>= 1)
 };
 
 // Element offset of channels c..c+3 of pixel `pix` (index inside the sample) of sample b in an activation
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_ffma_kernel(const ConvP p) {
                     if (c < p.K)
                         v = (p.labels[(size_t(b) * p.Hin + iy) * p.Win + ix] == c) ? 1.f : 0.f;
                     else
-                        v = p.image[((size_t(b) * p.C_img + (c - p.K)) * p.Hin + iy) * p.Win + ix];
+                        v = p.image[((size_t(b / p.img_rep) * p.C_img + (c - p.K)) * p.Hin + iy) * p.Win + ix];
                 }
                 sIn[cc * G::PLANE + pix] = v;
             }
@@ -414,6 +415,7 @@ int launch_conv(const ccdm_op &op, cudaStream_t s) {
     p.upsample = op.upsample; p.gn = op.gn; p.silu = op.silu; p.S0 = op.S0; p.S1 = op.S1;
     p.K = op.K; p.C_img = op.C_img; p.emb_off = op.emb_off; p.emb_cols = op.emb_cols; p.emb_bstride = op.emb_bstride;
     p.out_f32 = (op.out_dtype == CCDM_DT_F32);
+    p.img_rep = op.img_rep > 1 ? op.img_rep : 1;
     p.tiles_x = (op.Wout + TW - 1) / TW; p.tiles_y = (op.Hout + TH - 1) / TH;
 
     if (op.B <= 0 || op.Cout <= 0 || p.Cin <= 0) CCDM_FAIL(-2, "conv: empty shape");

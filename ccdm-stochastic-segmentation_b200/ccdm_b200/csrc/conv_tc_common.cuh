@@ -57,6 +57,7 @@ struct WsP {
     uint32_t idesc2; // x3: the same with N = 2 NT
     int x3;          // fp16x2 storage (CCDM_DT_F16X2): operands are (hi, lo) plane pairs, three MMAs per product
     float descale;   // x3: 2^-acc_shift, applied to the accumulator in the epilogue
+    int dbg;         // CCDM_ABLATE builds only: bit 0 skip the MMAs, bit 1 skip the transform maths, bit 2 skip the epilogue's stores
 };
 
 struct Item {
@@ -321,6 +322,9 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
                 float v[CGW];
 #pragma unroll
                 for (int i = 0; i < CGW; ++i) v[i] = __uint_as_float(raw[i]);
+#ifdef CCDM_ABLATE
+                if (p.dbg & 4) return;
+#endif
                 if (valid) {
 #pragma unroll
                     for (int i = 0; i < CGW; ++i) v[i] = X3 ? fmaf(v[i], p.descale, add[i]) : v[i] + add[i];

@@ -400,6 +400,10 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
                         mbar_wait<64>(raw_full + stage, phase);
                         if (pt == 0 && it == it_begin && kc == 0) trace(kTraceRaw0);
                         const uint32_t addr = sA32 + uint32_t(stage) * p.a_stage + (uint32_t(X * plane) * uint32_t(NQ) + uint32_t(q0)) * 16u;
+#ifdef CCDM_ABLATE
+                        if (p.dbg & 2) {
+                        } else
+#endif
                         if constexpr (X3) {
                             const uint32_t lo_off = uint32_t(NQ) * 16u;
                             if (need_mask) {
@@ -463,6 +467,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
         // tensor core truncates on every accumulation (measured: error ~ number of accumulating MMAs x 2^-24 |acc|), so the
         // small terms must not triple the count on the main accumulator.  The epilogue adds the two halves in fp32.
         auto mma = [&](uint32_t d, uint32_t a, uint32_t b, uint32_t acc) {
+#ifdef CCDM_ABLATE
+            if (p.dbg & 1) return;
+#endif
             if constexpr (X3) {
                 umma_bf16_split(d, a, desc_hi, b, desc_hi, p.idesc2, acc);
                 umma_bf16_split(d + b_lo, a + a_lo, desc_hi, b, desc_hi, p.idesc, 1u);
@@ -921,6 +928,10 @@ int launch_conv_tma(const ccdm_op &op, cudaStream_t s) {
     const int X = x3 ? 2 : 1;
     p.idesc = tm_idesc(c.NT, x3);
     p.idesc2 = tm_idesc(2 * c.NT, x3);
+#ifdef CCDM_ABLATE
+    static const int env_dbg = getenv("CCDM_ABLATE") ? atoi(getenv("CCDM_ABLATE")) : 0;
+    p.dbg = env_dbg;
+#endif
     p.x3 = x3 ? 1 : 0;
     p.descale = x3 ? float(ldexp(1.0, -op.acc_shift)) : 1.0f;
     if (x3 && (op.acc_shift < CCDM_F16X2_SCALE_LOG2 || op.acc_shift > 40)) CCDM_FAIL(-2, "conv_tma: fp16x2 op without a valid acc_shift (%d)", op.acc_shift);

@@ -91,14 +91,14 @@ __global__ void labels_to_onehot_i64_kernel(const uint8_t *__restrict__ labels, 
 // double -> float path every step.
 template <typename T, bool X3 = false>
 __global__ void __launch_bounds__(256) nchw_to_nhwc_stats_kernel(const float *__restrict__ src, int C, int HW, T *__restrict__ dst,
-                                                                 double *__restrict__ stat) {
+                                                                 double *__restrict__ stat, int rep) {
     __shared__ float tile[32][33];
-    const int b = blockIdx.z;
+    const int b = blockIdx.z, bs = b / rep;  // bs: entry of `src` this sample reads (rep samples per image)
     const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
     for (int j = ty; j < 32; j += 8) {
         int c = c0 + j, p = p0 + tx;
-        tile[j][tx] = (c < C && p < HW) ? src[(size_t(b) * C + c) * HW + p] : 0.f;
+        tile[j][tx] = (c < C && p < HW) ? src[(size_t(bs) * C + c) * HW + p] : 0.f;
     }
     __syncthreads();
     for (int j = ty; j < 32; j += 8) {
@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_stats_kernel(const float *__
 // X3: fp16x2 [B][CP/8][2][HW][8] -- one thread writes the hi row and the lo row of its (pixel, group).
 template <bool X3>
 __global__ void __launch_bounds__(256) encode_input_kernel(const uint8_t *__restrict__ labels, const float *__restrict__ image, int K,
-                                                           int C_img, int planes, size_t HW, size_t total, __nv_bfloat16 *__restrict__ out) {
+                                                           int C_img, int planes, size_t HW, size_t total, int img_rep,
+                                                           __nv_bfloat16 *__restrict__ out) {
     const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     pdl_launch_dependents();
     pdl_wait();
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(256) encode_input_kernel(const uint8_t *__rest
     const int g = int(bg % planes);
     const size_t b = bg / planes;
     const int lab = labels[b * HW + pix];
+    const size_t bi = b / size_t(img_rep);  // conditioning image of this sample
     uint32_t pk[4], pl[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(256) encode_input_kernel(const uint8_t *__rest
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int c = g * 8 + 2 * j + e;
-            v[e] = c < K ? (c == lab ? 1.f : 0.f) : (c < K + C_img ? image[(b * C_img + (c - K)) * HW + pix] : 0.f);
+            v[e] = c < K ? (c == lab ? 1.f : 0.f) : (c < K + C_img ? image[(bi * C_img + (c - K)) * HW + pix] : 0.f);
         }
         if (X3) {
             split_f16x2(v[0], v[1], pk[j], pl[j]);
@@ -180,6 +182,28 @@ __global__ void __launch_bounds__(256) encode_input_kernel(const uint8_t *__rest
     }
 }
 
+// Vote over the N samples of an image: one thread per (image, pixel) counts the labels of its N samples (uint8 reads,
+// coalesced across the warp) and writes the K class frequencies (NCHW, coalesced per class) and the majority label.
+__global__ void __launch_bounds__(256) vote_kernel(const uint8_t *__restrict__ labels, int N, size_t n_pix, int K, size_t total,
+                                                   float *__restrict__ freq, uint8_t *__restrict__ majority) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const size_t img = i / n_pix, pix = i - img * n_pix;
+    const uint8_t *src = labels + img * size_t(N) * n_pix + pix;
+    const float inv = 1.0f / float(N);
+    int best = 0, best_n = -1;
+    for (int k = 0; k < K; ++k) {  // K passes over N bytes that stay in L1: no per-thread count array, any K <= 255
+        int n = 0;
+        for (int s = 0; s < N; ++s) n += (src[size_t(s) * n_pix] == k) ? 1 : 0;
+        freq[(img * K + k) * n_pix + pix] = float(n) * inv;
+        if (n > best_n) {
+            best_n = n;
+            best = k;
+        }
+    }
+    if (majority != nullptr) majority[i] = uint8_t(best);
+}
+
 }  // namespace
 
 int launch_encode_input(const ccdm_op &op, cudaStream_t s) {
@@ -190,7 +214,8 @@ int launch_encode_input(const ccdm_op &op, cudaStream_t s) {
     const size_t HW = size_t(op.Hin) * op.Win, total = size_t(op.B) * (CP / 8) * HW;
     if (total == 0) return 0;
     CCDM_CUDA(launch_pdl(x3 ? encode_input_kernel<true> : encode_input_kernel<false>, dim3(unsigned((total + 255) / 256)), dim3(256), 0, s,
-                         (const uint8_t *)op.labels_in, (const float *)op.image, op.K, op.C_img, CP / 8, HW, total, (__nv_bfloat16 *)op.out));
+                         (const uint8_t *)op.labels_in, (const float *)op.image, op.K, op.C_img, CP / 8, HW, total, op.img_rep > 1 ? op.img_rep : 1,
+                         (__nv_bfloat16 *)op.out));
     CCDM_LAUNCH_CHECK("encode_input_kernel");
     return 0;
 }
@@ -228,19 +253,30 @@ extern "C" int ccdm_labels_to_onehot_i64(const uint8_t *labels, size_t n_pix, in
     return 0;
 }
 
-extern "C" int ccdm_nchw_to_nhwc_stats(const float *src, int B, int C, int H, int W, int dtype, void *dst, double *stat,
+extern "C" int ccdm_nchw_to_nhwc_stats(const float *src, int B, int C, int H, int W, int dtype, void *dst, double *stat, int rep,
                                        void *stream) {
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
+    if (rep < 1) rep = 1;
+    if (B % rep) CCDM_FAIL(-2, "nchw_to_nhwc_stats: batch %d is not a multiple of rep %d", B, rep);
     cudaStream_t s = (cudaStream_t)stream;
     CCDM_CUDA(cudaMemsetAsync(stat, 0, sizeof(double) * 2 * size_t(B) * C, s));
     const int HW = H * W;
     dim3 grid((HW + 31) / 32, (C + 31) / 32, B);
     if (dtype == CCDM_DT_F16X2)
-        nchw_to_nhwc_stats_kernel<__nv_bfloat16, true><<<grid, 256, 0, s>>>(src, C, HW, (__nv_bfloat16 *)dst, stat);
+        nchw_to_nhwc_stats_kernel<__nv_bfloat16, true><<<grid, 256, 0, s>>>(src, C, HW, (__nv_bfloat16 *)dst, stat, rep);
     else if (dtype == CCDM_DT_BF16)
-        nchw_to_nhwc_stats_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(src, C, HW, (__nv_bfloat16 *)dst, stat);
+        nchw_to_nhwc_stats_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(src, C, HW, (__nv_bfloat16 *)dst, stat, rep);
     else
-        nchw_to_nhwc_stats_kernel<float><<<grid, 256, 0, s>>>(src, C, HW, (float *)dst, stat);
+        nchw_to_nhwc_stats_kernel<float><<<grid, 256, 0, s>>>(src, C, HW, (float *)dst, stat, rep);
     CCDM_LAUNCH_CHECK("nchw_to_nhwc_stats_kernel");
+    return 0;
+}
+
+extern "C" int ccdm_vote(const uint8_t *labels, int B_img, int N, size_t n_pix, int K, float *freq, uint8_t *majority, void *stream) {
+    if (B_img <= 0 || n_pix == 0) return 0;
+    if (N < 1 || K < 1 || K > 255 || !labels || !freq) CCDM_FAIL(-2, "vote: N=%d K=%d", N, K);
+    const size_t total = size_t(B_img) * n_pix;
+    vote_kernel<<<unsigned((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(labels, N, n_pix, K, total, freq, majority);
+    CCDM_LAUNCH_CHECK("vote_kernel");
     return 0;
 }

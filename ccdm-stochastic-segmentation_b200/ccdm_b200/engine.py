@@ -370,10 +370,13 @@ class PackedWeights:
 class Program:
     """One reverse step for fixed (B, H, W): op list + workspace, bound to device addresses."""
 
-    def __init__(self, engine: "UNetEngine", B: int, H: int, W: int, rows_per_sample: int):
+    def __init__(self, engine: "UNetEngine", B: int, H: int, W: int, rows_per_sample: int, img_rep: int = 1):
         unet, arch = engine.unet, engine.unet.arch
         self.engine = engine
         self.B, self.H, self.W = B, H, W
+        if img_rep < 1 or B % img_rep:
+            raise ValueError(f"batch {B} is not a multiple of the samples per image ({img_rep})")
+        self.img_rep = img_rep  # consecutive samples that share one conditioning image / feature map (SURVEY 8f-2)
         self.K = unet.out_channels
         self.C_img = unet.in_channels - self.K
         self.dt, self.esize, tc_mode = PRECISIONS[engine.precision]
@@ -426,12 +429,12 @@ class Program:
                     # then input_blocks[0] is an ordinary tensor-core conv without a norm
                     cp = _ceil(Ly.cin, 16)
                     xin = emit(_lib.OP_ENCODE_INPUT, [], new(p + ":x", cp, ch, cw, stat=False), Hin=ch, Win=cw, Hout=ch, Wout=cw,
-                               Cout=cp, K=self.K, C_img=self.C_img, _labels=True)
+                               Cout=cp, K=self.K, C_img=self.C_img, img_rep=img_rep, _labels=True)
                     h = emit(_lib.OP_CONV, [xin], new(p, Ly.cout, ch, cw), ksize=3, stride=1, gn=0, silu=0, Hin=ch, Win=cw,
                              Hout=ch, Wout=cw, Cout=Ly.cout, _src=[xin], _w=p + ":w", _b=p + ":b")
                 elif Ly.kind == "conv_in":
                     h = emit(_lib.OP_INPUT_CONV, [], new(p, Ly.cout, ch, cw), src_kind=1, ksize=3, stride=1, Hin=ch, Win=cw,
-                             Hout=ch, Wout=cw, Cout=Ly.cout, K=self.K, C_img=self.C_img, _w=p + ":w", _b=p + ":b")
+                             Hout=ch, Wout=cw, Cout=Ly.cout, K=self.K, C_img=self.C_img, img_rep=img_rep, _w=p + ":w", _b=p + ":b")
                 elif Ly.kind == "res":
                     if len(srcs) == 2 and not Ly.skip_conv:
                         raise NotImplementedError("identity skip over a concatenated input")
@@ -741,14 +744,14 @@ class UNetEngine:
         self._children: List["UNetEngine"] = []
 
     # -- helpers ----------------------------------------------------------------------
-    def program(self, B, H, W, rows_per_sample=0) -> Program:
-        key = (B, H, W, rows_per_sample)
+    def program(self, B, H, W, rows_per_sample=0, img_rep=1) -> Program:
+        key = (B, H, W, rows_per_sample, img_rep)
         prog = self.programs.get(key)
         if prog is None:
             # bounded cache: a ragged last batch or a change of batch size must not pile up ~1 GB workspaces
             while len(self.programs) >= PROGRAM_CACHE:
                 self.programs.popitem(last=False)
-            prog = self.programs[key] = Program(self, B, H, W, rows_per_sample)
+            prog = self.programs[key] = Program(self, B, H, W, rows_per_sample, img_rep)
         else:
             self.programs.move_to_end(key)
         return prog
@@ -770,18 +773,19 @@ class UNetEngine:
             _lib.check(L.ccdm_onehot_to_labels(xf.data_ptr(), sb, sk, sh, sw, B, K, H, W, prog.labels.data_ptr(), self._sp()),
                        "onehot_to_labels")
             xf.record_stream(self.stream)
-        if tuple(condition.shape) != (B, prog.C_img, H, W):
-            raise ValueError(f"condition must be [B,{prog.C_img},{H},{W}]; got {tuple(condition.shape)}")
-        prog.image.copy_(condition.to(device=dev, dtype=torch.float32, non_blocking=True))
+        n_img = B // prog.img_rep  # img_rep samples share one image: the kernels index it by sample // img_rep
+        if tuple(condition.shape) != (n_img, prog.C_img, H, W):
+            raise ValueError(f"condition must be [{n_img},{prog.C_img},{H},{W}]; got {tuple(condition.shape)}")
+        prog.image[:n_img].copy_(condition.to(device=dev, dtype=torch.float32, non_blocking=True))
         if prog.feat is not None:
             if feature_condition is None:
                 raise ValueError("this UNet was built with a feature_cond_encoder: feature_condition is required")
             f = prog.feat
-            if tuple(feature_condition.shape) != (B, f.C, f.H, f.W):
-                raise ValueError(f"feature_condition must be [B,{f.C},{f.H},{f.W}]; got {tuple(feature_condition.shape)}")
+            if tuple(feature_condition.shape) != (n_img, f.C, f.H, f.W):
+                raise ValueError(f"feature_condition must be [{n_img},{f.C},{f.H},{f.W}]; got {tuple(feature_condition.shape)}")
             fcond = feature_condition.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
-            _lib.check(L.ccdm_nchw_to_nhwc_stats(fcond.data_ptr(), B, f.C, f.H, f.W, prog.dt, f.addr, f.stat_addr, self._sp()),
-                       "nchw_to_nhwc_stats")
+            _lib.check(L.ccdm_nchw_to_nhwc_stats(fcond.data_ptr(), B, f.C, f.H, f.W, prog.dt, f.addr, f.stat_addr, prog.img_rep,
+                                                 self._sp()), "nchw_to_nhwc_stats")
             fcond.record_stream(self.stream)
         # (unet.py:770: a feature_condition passed to a UNet without an encoder slot is ignored)
 
@@ -872,7 +876,7 @@ class UNetEngine:
 
     @torch.no_grad()
     def run_chain(self, x, condition, feature_condition, t_values: Sequence[int], alphas, cumalphas, last_mode: int,
-                  noise: str = "torch", seed: int = 0, sample0: int = 0, record=None, _parent_stream=None):
+                  noise: str = "torch", seed: int = 0, sample0: int = 0, record=None, _parent_stream=None, img_rep: int = 1):
         """Runs the reverse chain; returns (labels uint8 [B,H,W], probs fp32 [B,H,W,K] or None).
 
         ``alphas``/``cumalphas``: host float lists (the DiffusionModel buffers).  ``noise``:
@@ -898,13 +902,13 @@ class UNetEngine:
         elif noise not in ("torch", "philox"):
             raise ValueError(f"noise={noise!r}")
         n_lanes = min(self.lanes, B)
-        if n_lanes > 1 and noise == "philox" and noise_list is None and record is None:
+        if n_lanes > 1 and noise == "philox" and noise_list is None and record is None and img_rep == 1:
             return self._run_chain_lanes(n_lanes, x, condition, feature_condition, t_values, alphas, cumalphas, last_mode, seed, sample0)
         cur = _parent_stream if _parent_stream is not None else torch.cuda.current_stream(self.device)
         self.stream.wait_stream(cur)
         with torch.cuda.stream(self.stream):
             self.weights.refresh()
-            prog = self.program(B, H, W, rows_per_sample=0)
+            prog = self.program(B, H, W, rows_per_sample=0, img_rep=img_rep)
             self._load_inputs(prog, x, condition, feature_condition)
             entries = []
             n = len(t_values)

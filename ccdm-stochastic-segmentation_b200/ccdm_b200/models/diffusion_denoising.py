@@ -172,6 +172,47 @@ class DenoisingModel(nn.Module):
                                          labels.data_ptr(), sp), "uniform_labels")
         return labels
 
+    @torch.no_grad()
+    def sample_many(self, condition: Tensor, n_samples: int, feature_condition: Optional[Tensor] = None,
+                    init_t: Optional[int] = None) -> dict:
+        """N stochastic segmentations per image in ONE batched chain, with everything the evaluators do around the sampler
+        call moved onto the device:
+
+        * x_T is drawn on the device (``draw_x_T``) instead of on the host + a copy of [B*N, K, H, W] floats
+          (evaluate_lidc_uncertainty.py:100);
+        * the image (and the feature map) are NOT replicated: the kernels read entry ``sample // N`` -- the reference does
+          ``image.repeat_interleave(N, dim=0)`` (evaluate_lidc_uncertainty.py:96);
+        * the vote over the N samples runs as one kernel on the uint8 label maps: ``mean_onehot`` [B, K, H, W] is the mean
+          of the N one-hot maps (what ``predict_multiple`` accumulates, eval_cdm.py:176-193, and what
+          ``prediction.reshape(B, N, ...)`` feeds the metrics, evaluate_lidc_uncertainty.py:103), ``majority`` its argmax.
+
+        ``condition`` [B, C_img, H, W], ``feature_condition`` [B, F, H/8, W/8] or None.  Noise is the in-kernel Philox
+        stream keyed by (``seed``, ``sample_offset`` + global sample index), so the result does not depend on how the
+        B*N samples are batched or sharded.  Returns ``labels`` uint8 [B, N, H, W], ``mean_onehot`` fp32 [B, K, H, W] (in
+        ``confidence`` mode: the mean of the N normalised probability maps) and ``majority`` uint8 [B, H, W]."""
+        L = _lib.lib()
+        if n_samples < 1:
+            raise ValueError("n_samples must be >= 1")
+        B_img, _, H, W = condition.shape
+        B, K = B_img * n_samples, self.diffusion.num_classes
+        dev = next(self.unet.parameters()).device
+        t_values = reverse_t_values(self.time_steps, init_t)
+        alphas, cumalphas = self._schedule_host()
+        confidence = self.step_T_sample == "confidence"
+        base = int(self.sample_offset)  # global index of this call's first SAMPLE (image-major, sample-minor)
+        x = self.draw_x_T(B, H, W, dev)
+        labels, probs = self.unet.engine(self.precision).run_chain(
+            x, condition, feature_condition, t_values, alphas, cumalphas, _lib.DRAW_CONFIDENCE if confidence else _lib.DRAW_MAJORITY,
+            noise="philox", seed=self.seed, sample0=base, img_rep=n_samples)
+        freq = torch.empty((B_img, K, H, W), dtype=torch.float32, device=dev)
+        majority = torch.empty((B_img, H, W), dtype=torch.uint8, device=dev)
+        sp = _lib.stream_ptr(torch.cuda.current_stream(dev))
+        _lib.check(L.ccdm_vote(labels.data_ptr(), B_img, n_samples, H * W, K, freq.data_ptr(), majority.data_ptr(), sp), "vote")
+        if confidence and probs is not None:
+            freq = probs.view(B_img, n_samples, H, W, K).mean(dim=1).permute(0, 3, 1, 2)
+            majority = freq.argmax(dim=1).to(torch.uint8)
+        return {"labels": labels.view(B_img, n_samples, H, W), "mean_onehot": freq, "majority": majority}
+
     def forward_step(self, x: Tensor, condition: Tensor, feature_condition: Tensor, t: Tensor) -> dict:
         """One denoiser evaluation (:161-162).  Inference only: no autograd graph is built."""
         self.unet.precision = self.precision

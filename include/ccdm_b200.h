@@ -106,7 +106,9 @@ typedef struct ccdm_op {
                          * steps use approximate exp2/log2/reciprocal (same Philox bits, no IEEE divisions) */
     int32_t acc_shift;  /* fp16x2 convs: packed weights are scaled by 2^(acc_shift - CCDM_F16X2_SCALE_LOG2); the epilogue
                          * multiplies the accumulator by 2^-acc_shift (powers of two: exact) */
-    int32_t reserved;
+    int32_t img_rep;    /* input conv / encode_input: consecutive samples that share ONE conditioning image (`image` then has
+                         * B / img_rep entries and sample b reads entry b / img_rep); 0 or 1: one image per sample.  Replaces
+                         * the evaluators' image.repeat_interleave(N) (evaluate_lidc_uncertainty.py:96) */
     /* Layout of stat0 / stat1.  st_slots[i] == 0: double2 [B, C] {sum, sum of squares}, folded by the producer.
      * st_slots[i] > 0 ("deferred fold", tensor-core producers): fp32 per-CTA partial rows [B][st_slots][st_rows][2] exactly
      * as the producer's epilogue wrote them (ccdm_conv_stat_layout); the consumer folds rows
@@ -192,10 +194,17 @@ int ccdm_onehot_to_labels(const float *x, int64_t sb, int64_t sk, int64_t sh, in
 /* labels -> one-hot int64 [B,H,W,K] (max_prob_sample, one_hot_categorical.py:46-50). */
 int ccdm_labels_to_onehot_i64(const uint8_t *labels, size_t n_pix, int K, int64_t *out, void *stream);
 
-/* NCHW fp32 -> NHWC (fp32|bf16) + per-(sample,channel) stats; used once per chain
- * for the feature condition (unet.py:784-786). */
-int ccdm_nchw_to_nhwc_stats(const float *src, int B, int C, int H, int W, int dtype, void *dst, double *stat,
+/* NCHW fp32 -> NHWC (fp32|bf16|fp16x2) + per-(sample,channel) stats; used once per chain
+ * for the feature condition (unet.py:784-786).  rep > 1: `src` holds B / rep entries and sample b converts entry
+ * b / rep (N samples per image without a repeat_interleave copy). */
+int ccdm_nchw_to_nhwc_stats(const float *src, int B, int C, int H, int W, int dtype, void *dst, double *stat, int rep,
                             void *stream);
+
+/* Vote over the N samples of each image (evaluate_lidc_uncertainty.py:103-125 `prediction.reshape(B, N, ...)`,
+ * eval_cdm.py:176-193 `predict_multiple`'s running mean): labels uint8 [B_img * N, n_pix] (image-major, sample-minor) ->
+ * freq fp32 [B_img, K, n_pix] = fraction of the N samples that chose class k (the mean of the one-hot maps; NCHW like the
+ * reference's result) and, if `majority` is not NULL, uint8 [B_img, n_pix] = argmax_k freq (first maximum). */
+int ccdm_vote(const uint8_t *labels, int B_img, int N, size_t n_pix, int K, float *freq, uint8_t *majority, void *stream);
 
 /* Standalone posterior + draw on probabilities theta fp32 [n_pix_total, K]
  * (diffusion_denoising.py:99-128,204-212; one_hot_categorical.py:30-54).

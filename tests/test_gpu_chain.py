@@ -404,3 +404,29 @@ def test_bf16_chain_teacher_forced_label_agreement(cuda_device, tag):
     _report(f"bf16_teacher_forced_{tag}", label_mismatch_frac=frac, **stats)
     assert stats["max_dx0"] <= BF16_X0_MAX
     assert frac <= BF16_LABEL_FRAC
+
+
+def test_sample_many_indexes_the_image_and_votes_on_device(cuda_device):
+    """N samples per image in one chain without image.repeat_interleave(N) (the kernels read entry
+    sample // N), x_T drawn on the device, the vote over the N samples as one kernel.  Same labels as the evaluator-style
+    call on the replicated batch (evaluate_lidc_uncertainty.py:96-103); the vote equals the mean of the one-hot maps."""
+    from ccdm_b200.synthetic import synthetic_inputs
+    for tag, n in (("lidc64", 3), ("cs64x128", 2)):
+        T, _, C_img, H, W, K, fce, mult, t_probe, steps = GOLDEN_CASES[tag]
+        m = build_ours(T, C_img, H, W, K, "majority", fce, mult).cuda()
+        image, feat, _ = synthetic_inputs(2, C_img, H, W, K, 384 if fce else 0)
+        m.noise, m.seed = "philox", 31
+        for prec in ("exact", "bf16"):
+            m.precision = prec
+            out = m.sample_many(image.cuda(), n, feat.cuda() if feat is not None else None, init_t=10000 + 4)
+            assert out["labels"].dtype == torch.uint8 and tuple(out["labels"].shape) == (2, n, H, W)
+            # the evaluator's way: replicate, draw the same x_T, one call
+            x = m.draw_x_T(2 * n, H, W)
+            ref = m(x, image.repeat_interleave(n, dim=0).cuda(), feat.repeat_interleave(n, dim=0).cuda() if feat is not None else None,
+                    t=torch.as_tensor(10000 + 4))["diffusion_out"]
+            assert torch.equal(out["labels"].reshape(2 * n, H, W).long(), ref.argmax(1))
+            onehot = torch.nn.functional.one_hot(out["labels"].long(), K).float()          # [2, n, H, W, K]
+            assert torch.allclose(out["mean_onehot"], onehot.mean(dim=1).permute(0, 3, 1, 2), atol=1e-6)
+            assert torch.equal(out["majority"].long(), out["mean_onehot"].argmax(dim=1))
+    with pytest.raises(ValueError):
+        m.sample_many(image.cuda(), 0)

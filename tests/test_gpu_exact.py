@@ -153,7 +153,7 @@ def test_x3_encode_input_and_feature_planes(L):
     x = _rand(B, C, H, W, seed=9).cuda() * 2
     dst = torch.full((B, C // 8, 2, H, W, 8), float("nan"), dtype=torch.float16, device="cuda")
     stat = torch.zeros(B, C, 2, dtype=torch.float64, device="cuda")
-    _lib.check(L.ccdm_nchw_to_nhwc_stats(x.data_ptr(), B, C, H, W, _lib.DT_F16X2, dst.data_ptr(), stat.data_ptr(), sp()))
+    _lib.check(L.ccdm_nchw_to_nhwc_stats(x.data_ptr(), B, C, H, W, _lib.DT_F16X2, dst.data_ptr(), stat.data_ptr(), 1, sp()))
     torch.cuda.synchronize()
     assert float((from_pm_x3(dst) - x.permute(0, 2, 3, 1)).abs().max()) <= 2.0 ** -22 * float(x.abs().max())
     xd = x.double()

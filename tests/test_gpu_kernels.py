@@ -493,7 +493,7 @@ def test_nchw_to_nhwc_stats(L):
     x = _rand(B, C, H, W, seed=81).cuda()
     dst = torch.zeros((B, H, W, C), device="cuda")
     stat = torch.zeros((B, C, 2), dtype=torch.float64, device="cuda")
-    _lib.check(L.ccdm_nchw_to_nhwc_stats(x.data_ptr(), B, C, H, W, _lib.DT_F32, dst.data_ptr(), stat.data_ptr(), _sp()))
+    _lib.check(L.ccdm_nchw_to_nhwc_stats(x.data_ptr(), B, C, H, W, _lib.DT_F32, dst.data_ptr(), stat.data_ptr(), 1, _sp()))
     torch.cuda.synchronize()
     assert torch.equal(dst, x.permute(0, 2, 3, 1).contiguous())
     xd = x.double()
