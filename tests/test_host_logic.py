@@ -301,3 +301,46 @@ def test_subpixel_weights_reproduce_upsample_conv():
                     acc = acc + torch.einsum("bchw,oc->bohw", win, wc[:, :, 2 * py + px, 2 * ry + rx])
             out[:, :, py::2, px::2] = acc
     assert float((out - ref).abs().max()) < 1e-4
+
+
+def test_every_conv_lands_on_the_tensor_core_kernel():
+    """Dry-run plans (no GPU) of the shipped architectures -- base_channels 32 AND 64, LIDC 128x128 and Cityscapes 256x512
+    with the DINO concat -- in both tensor-core modes: every conv-shaped op is taken by conv_tma (so its packed weights are
+    the layout the kernel reads), no FFMA op is handed deferred-fold statistics rows, and the statistics layout a GroupNorm
+    consumer is told matches what its producer writes."""
+    import ctypes
+    from ccdm_b200 import _lib, models
+    from ccdm_b200.synthetic import fill_synthetic_
+    L = _lib.lib()
+    for prec in ("bf16", "exact"):
+        for base in (32, 64):
+            for (C, H, W, K, fce, B) in ((1, 128, 128, 2, False, 64), (3, 256, 512, 20, True, 8), (1, 64, 64, 2, False, 3)):
+                m = _build(C, H, W, K, fce, None, base).eval()
+                fill_synthetic_(m.unet, 0)
+                eng = m.unet.engine(prec, dry_run=True)
+                eng.weights.refresh()
+                prog = eng.program(B, H, W)
+                prog.bind(4)
+                ops = prog._op_array
+                n_conv = sum(1 for o in prog._op_dicts if o["kind"] == _lib.OP_CONV)
+                assert prog.n_tc == n_conv and not prog.off_tc, (prec, base, H, W, prog.off_tc)
+                producers = {}
+                for i, o in enumerate(prog._op_dicts):
+                    op = ops[i]
+                    if op.kind == _lib.OP_CONV:
+                        assert L.ccdm_conv_uses_tc(ctypes.byref(op)) == 1 and op.exact == 0
+                        for si, sten in enumerate(o.get("_src", [])[:2]):
+                            slots = getattr(op, "st_slots%d" % si)
+                            if o.get("gn") and sten.stat_layout is not None:
+                                want = producers[id(sten)]
+                                got = tuple(getattr(op, "%s%d" % (n, si)) for n in ("st_slots", "st_ips", "st_items", "st_grid", "st_rows"))
+                                assert got == want and getattr(op, "stat%d" % si) == sten.part_addr
+                            else:
+                                assert slots == 0
+                        if o["_out"] is not None and o["_out"].stat_layout is not None:
+                            lay = (ctypes.c_int32 * 5)()
+                            assert L.ccdm_conv_stat_layout(ctypes.byref(op), lay) == 0
+                            producers[id(o["_out"])] = tuple(int(v) for v in lay)
+                            assert op.ostat == 0 and op.part == o["_out"].part_addr
+                if prec == "exact":
+                    assert all(ops[i].acc_shift == eng.weights.shift + 4 for i in range(prog.n_ops) if ops[i].kind == _lib.OP_CONV)

@@ -21,7 +21,48 @@ def main():
     B = int(sys.argv[2]) if len(sys.argv) > 2 else (16 if name == "lidc" else 2)
     if len(sys.argv) > 3:
         wl["T"] = int(sys.argv[3])
-    print(json.dumps(measure(wl, B, modes=("fp32", "exact", "bf16"))))
+    res = measure(wl, B, modes=("fp32", "exact", "bf16"))
+    res["vs_reference_eager_gpu"] = reference_leg(wl, B)
+    print(json.dumps(res))
+
+
+def reference_leg(wl, B, seed=7):
+    """The UNMODIFIED reference (bytecode under oracle/_ref) run eagerly by PyTorch on this GPU, against this library in
+    the reference's noise mode (noise='torch': both consume the device generator identically -- one exponential_ draw of
+    [B*H*W, K] per step), same x_T, same seed.  Also the reference against ITSELF with cuDNN/cuBLAS TF32 on (its default
+    on this GPU) and off: the noise floor of "identical samples" for this chaotic chain."""
+    from ccdm_b200.synthetic import synthetic_inputs
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ref, kind = bench.build_model(wl, dev, reference=True)
+    if kind != "reference":
+        return {"unavailable": "oracle/_ref bytecode missing"}
+    ours, _ = bench.build_model(wl, dev)
+    image, feat, labels = synthetic_inputs(B, wl["C_img"], wl["H"], wl["W"], wl["K"], 384 if wl["fce"] else 0, seed=77)
+    x = torch.nn.functional.one_hot(labels.long(), wl["K"]).permute(0, 3, 1, 2).float().to(dev)
+    image, feat = image.to(dev), (feat.to(dev) if feat is not None else None)
+    out = {}
+
+    def run_ref(tf32):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.manual_seed(seed)
+        with torch.no_grad():
+            return ref(x, image, feat)["diffusion_out"].argmax(1)
+
+    labs = {"reference_tf32_on": run_ref(True), "reference_tf32_off": run_ref(False)}
+    torch.backends.cudnn.allow_tf32 = True
+    ours.noise = "torch"
+    for prec in ("exact", "fp32", "bf16"):
+        ours.precision = prec
+        torch.manual_seed(seed)
+        labs["ours_" + prec] = ours(x, image, feat)["diffusion_out"].argmax(1)
+    names = list(labs)
+    for i in range(len(names)):
+        for j in range(i + 1, len(names)):
+            out[f"{names[i]}_vs_{names[j]}"] = float((labs[names[i]] == labs[names[j]]).float().mean())
+    out["note"] = ("final labels after the full free-running chain, torch generator seed %d on every run; reference_tf32_on is how the "
+                   "reference runs on this GPU out of the box (torch.backends.cudnn.allow_tf32 defaults to True)" % seed)
+    return out
 
 
 def measure(wl, B, modes=("exact", "bf16"), seed=2024, dev=None):
