@@ -46,8 +46,9 @@ def _check(out, args, kw, ostat=None, what=""):
         s2 = (ref64 * ref64).sum(dim=(2, 3))
         n = ref64.shape[2] * ref64.shape[3]
         rms = (s2 / n).sqrt()
-        # sums of fp32 values accumulated in fp32 per thread / warp / CTA and folded in double: 1e-6 of n * rms
-        assert float(((ostat[..., 0].cpu() - s1).abs() / (n * rms + 1e-9)).max()) < 2e-6
+        # sums of fp32 values accumulated in fp32 per thread / warp / CTA and folded in double; the accumulator truncation of the
+        # tensor core is one-sided, so the error of a sum is the error of its terms (X3_REL), not a random walk
+        assert float(((ostat[..., 0].cpu() - s1).abs() / (n * rms + 1e-9)).max()) < X3_REL
         assert float(((ostat[..., 1].cpu() - s2).abs() / (n * rms * rms + 1e-9)).max()) < 1e-5
 
 
