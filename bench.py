@@ -351,9 +351,15 @@ def measure_workload(D, wl, precision, steps, warmup, batch=None, one_image=Fals
     gathered = torch.empty((world * B, H, W), dtype=torch.uint8, device=dev) if world > 1 else None
     last = {}
 
+    chain_events = []
+
     def chain_resident():
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
         lab, _ = engine.run_chain(x_dev, image_dev, feat_dev, ts, al, ca, _lib.DRAW_MAJORITY, noise="philox", seed=2024,
                                   sample0=rank * B)
+        eb.record()  # this rank's own chain, before it meets the others in the collective
+        chain_events.append((ea, eb))
         if world > 1:
             D.dist.all_gather_into_tensor(gathered, lab)  # the single collective of the path
         last["labels"] = lab
@@ -372,12 +378,21 @@ def measure_workload(D, wl, precision, steps, warmup, batch=None, one_image=Fals
         chain_resident()
     clocks = ClockSampler(D.local)
     clocks.start()
+    del chain_events[:]
     ms_total, per_rank = D.timed(chain_resident, steps)
     clk = clocks.stop()
     ms_step = ms_total / steps
+    own = torch.tensor([sum(a.elapsed_time(b) for a, b in chain_events) / max(1, len(chain_events))], device=dev)
+    if world > 1:
+        every = torch.empty(world, device=dev)
+        D.dist.all_gather_into_tensor(every, own)
+        own_ms = [float(v) for v in every.tolist()]
+    else:
+        own_ms = [float(own.item())]
     rec = {"workload": wl["name"] if not one_image else f"{wl['name'].split(',')[0]}, {wl['K']}-class, T={T}, {world * B} samples of ONE image over {world} GPU(s)",
            "precision": precision, "dtype": DTYPE_NAME[precision], "batch_per_gpu": B, "T": T, "value": world * B / (ms_step / 1e3),
            "unit": "samples/s", "ms_per_step": ms_step, "steps": steps, "warmup": warmup, "per_rank_ms": [v / steps for v in per_rank],
+           "per_rank_chain_ms": own_ms,  # each rank's own chain (before the all-gather couples the ranks)
            "clocks": clk, "lanes": n_lanes}
     if world > 1:  # the collective alone (same buffers), so an N > 1 loss can be attributed
         lab = last["labels"]
@@ -516,7 +531,7 @@ def run_gpu_arm(args):
                        "l2_policy": "per-step activation traffic exceeds L2 (126 MB): inputs larger than L2, no flush",
                        "cuda_graph": True, "lanes": rec["lanes"]},
             "e2e": rec.get("e2e"), "gpu_launches": rec["gpu_launches"], "clocks": rec["clocks"], "roofline": rec.get("roofline"),
-            "roofline_chain": rec["roofline_chain"], "cpu_baseline": cpu, "per_rank_ms": rec["per_rank_ms"],
+            "roofline_chain": rec["roofline_chain"], "cpu_baseline": cpu, "per_rank_ms": rec["per_rank_ms"], "per_rank_chain_ms": rec["per_rank_chain_ms"],
             "all_gather_ms": rec.get("all_gather_ms"), "kernel_breakdown": rec.get("kernel_breakdown"),
             "parity": {"mode": args.precision,
                        "statement": "'exact' and 'fp32' modes are held to max|dx0| <= 2e-4, labels identical outside a 1e-3 race margin, "
