@@ -15,7 +15,7 @@ DT_F32, DT_BF16, DT_F16X2 = 0, 1, 2
 F16X2_SCALE_LOG2 = 4
 DRAW_SAMPLE, DRAW_MAJORITY, DRAW_CONFIDENCE, DRAW_X0, DRAW_POSTERIOR = 0, 1, 2, 3, 4
 NOISE_TENSOR, NOISE_PHILOX = 0, 1
-OP_INPUT_CONV, OP_CONV, OP_ATTENTION, OP_HEAD, OP_ENCODE_INPUT, OP_INPUT_LUT = 1, 2, 3, 4, 5, 6
+OP_INPUT_CONV, OP_CONV, OP_ATTENTION, OP_HEAD, OP_ENCODE_INPUT = 1, 2, 3, 4, 5
 ABI_VERSION = 3
 
 

@@ -33,7 +33,6 @@ int launch_conv(const ccdm_op &op, cudaStream_t s);
 int launch_attention(const ccdm_op &op, cudaStream_t s);
 int launch_head(const ccdm_op &op, cudaStream_t s);
 int launch_encode_input(const ccdm_op &op, cudaStream_t s);
-int launch_input_lut(const ccdm_op &op, cudaStream_t s);
 
 // ---- programmatic dependent launch (PDL) -----------------------------------------
 // Every kernel of the reverse step is launched with programmatic stream serialization: the next kernel's

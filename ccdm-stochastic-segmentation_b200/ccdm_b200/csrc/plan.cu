@@ -47,7 +47,6 @@ static int launch_any(const ccdm_op &op, cudaStream_t s) {
         case CCDM_OP_ATTENTION: return launch_attention(op, s);
         case CCDM_OP_HEAD: return launch_head(op, s);
         case CCDM_OP_ENCODE_INPUT: return launch_encode_input(op, s);
-        case CCDM_OP_INPUT_LUT: return launch_input_lut(op, s);
         default: CCDM_FAIL(-2, "unknown op kind %d", op.kind);
     }
 }
@@ -80,21 +79,12 @@ extern "C" int ccdm_conv_tc_config(const ccdm_op *op, int32_t *out16) {
     return ccdm::conv_tma_config(*op, out16);
 }
 extern "C" int ccdm_conv_uses_tma(const ccdm_op *op) { return op && ccdm::conv_uses_tma(*op) ? 1 : 0; }
-namespace ccdm {
-int conv_tma_stat_layout(const ccdm_op &op, int32_t *out5);
-int input_lut_stat_layout(const ccdm_op &op, int32_t *out5);
-size_t input_lut_part_floats(const ccdm_op &op);
-}
+namespace ccdm { int conv_tma_stat_layout(const ccdm_op &op, int32_t *out5); }
 extern "C" int ccdm_conv_stat_layout(const ccdm_op *op, int32_t *out5) {
-    if (!op || !out5) return -1;
-    if (op->kind == CCDM_OP_INPUT_LUT) return ccdm::input_lut_stat_layout(*op, out5);
-    if (!ccdm::conv_uses_tc(*op)) return -1;
+    if (!op || !out5 || !ccdm::conv_uses_tc(*op)) return -1;
     return ccdm::conv_tma_stat_layout(*op, out5);
 }
-extern "C" size_t ccdm_op_part_floats(const ccdm_op *op) {
-    if (!op) return 0;
-    return op->kind == CCDM_OP_INPUT_LUT ? ccdm::input_lut_part_floats(*op) : ccdm::op_part_floats(*op);
-}
+extern "C" size_t ccdm_op_part_floats(const ccdm_op *op) { return op ? ccdm::op_part_floats(*op) : 0; }
 
 extern "C" int ccdm_check_device(void) {
     int dev = 0;

@@ -109,9 +109,6 @@ def pack_conv_weight(w: torch.Tensor, cin_pad: Optional[int] = None) -> torch.Te
 # A/B switch: identity residuals of the bf16 mode as an extra 1x1 MMA chunk with identity weights (default) or as a
 # read-and-add in the epilogue (CCDM_IDENT_SKIP=0)
 _IDENT_SKIP = os.environ.get("CCDM_IDENT_SKIP", "1") != "0"
-# A/B switch: the input conv of the tensor-core modes as one lookup kernel on the labels (default) or as encode_input + a
-# tensor-core conv over the materialised one-hot ++ image tensor (CCDM_INPUT_LUT=0: round 1's path)
-_INPUT_LUT = os.environ.get("CCDM_INPUT_LUT", "1") != "0"
 
 
 def pack_conv_weight_tc(w: torch.Tensor, nt: Optional[int] = None) -> torch.Tensor:
@@ -427,12 +424,7 @@ class Program:
                 srcs = [h, hs.pop()]
             for Ly in blk.layers:
                 p = Ly.path
-                if Ly.kind == "conv_in" and self.exact == 0 and _INPUT_LUT:
-                    # tensor-core modes: concat + first conv in one launch on the labels (one-hot branch = 9-tap weight-row
-                    # lookup, image branch = FMAs on a shared-memory tile); nothing is materialised
-                    h = emit(_lib.OP_INPUT_LUT, [], new(p, Ly.cout, ch, cw), ksize=3, stride=1, Hin=ch, Win=cw, Hout=ch, Wout=cw,
-                             Cout=Ly.cout, K=self.K, C_img=self.C_img, img_rep=img_rep, _w=p + ":w", _b=p + ":b")
-                elif Ly.kind == "conv_in" and self.exact == 0:
+                if Ly.kind == "conv_in" and self.exact == 0:
                     # bf16: materialise one-hot(x_t) ++ image as a plane-major tensor (16 bytes per pixel and plane),
                     # then input_blocks[0] is an ordinary tensor-core conv without a norm
                     cp = _ceil(Ly.cin, 16)
@@ -623,7 +615,7 @@ class Program:
         for i, o in enumerate(self._op_dicts):
             op = base_op(o)
             src = o.get("_src", [])
-            if o["kind"] in (_lib.OP_INPUT_CONV, _lib.OP_ENCODE_INPUT, _lib.OP_INPUT_LUT):
+            if o["kind"] in (_lib.OP_INPUT_CONV, _lib.OP_ENCODE_INPUT):
                 op.labels_in = self.addr["labels"]
                 op.image = self.addr["image"]
             if o["kind"] == _lib.OP_CONV and o.get("gn"):
@@ -661,10 +653,7 @@ class Program:
             out = o["_out"]
             if out is not None:
                 op.out = out.addr
-                tc_producer = use_tc[i] or o["kind"] == _lib.OP_INPUT_LUT  # kernels that can leave per-CTA partial rows
-                deferred = tc_producer and all(use_tc[j] for j in gn_readers.get(id(out), []))
-                if out.want_stat and not deferred and o["kind"] == _lib.OP_INPUT_LUT:
-                    raise _lib.CcdmError("input_lut only writes deferred-fold statistics; its consumer must be a tensor-core conv")
+                deferred = use_tc[i] and all(use_tc[j] for j in gn_readers.get(id(out), []))
                 if out.want_stat and deferred:
                     # deferred fold: the epilogue only writes its per-CTA partial rows into a buffer owned by the
                     # tensor; the consumers' GroupNorm prologue folds them (no ticket, fence or atomic in the producer)

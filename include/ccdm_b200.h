@@ -80,11 +80,6 @@ typedef struct ccdm_step_entry {
                                   Cout = ceil16(K + C_img) channels (zero padded), the input of input_blocks[0] run as
                                   an ordinary tensor-core conv */
 
-#define CCDM_OP_INPUT_LUT 6  /* tensor-core modes: unet.py:760 + input_blocks[0] in ONE launch on the uint8 labels: the one-hot branch
-                                  of the conv as a 9-tap lookup of weight rows, the image branch as FMAs on a shared-memory tile;
-                                  `weight` fp32 [9][ceil8(K + C_img)][ceil32(Cout)], output in the mode's plane-major storage with
-                                  deferred-fold statistics rows */
-
 typedef struct ccdm_op {
     int32_t kind; /* CCDM_OP_* */
     int32_t dtype; /* CCDM_DT_* of activations in/out */

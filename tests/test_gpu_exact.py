@@ -187,47 +187,3 @@ def test_x3_attention(L, B, heads, T):
     err = float((got - ref).abs().max()) / float(ref.abs().max())
     print(f"x3 attention T={T}: rel err {err:.2e}")
     assert err < 3e-6, err
-
-
-@pytest.mark.parametrize("dt", ["x3", "bf16"])
-@pytest.mark.parametrize("B,K,C_img,H,W,rep", [(3, 2, 1, 40, 72, 1), (2, 20, 3, 24, 40, 1), (4, 2, 1, 128, 128, 2), (1, 4, 3, 9, 11, 1)])
-def test_input_lut_matches_conv_of_onehot_and_image(L, dt, B, K, C_img, H, W, rep):
-    """CCDM_OP_INPUT_LUT == conv3x3(cat[one_hot(labels), image]) (unet.py:760 + :516-518): the one-hot branch as a 9-tap row
-    lookup, the image indexed by sample // rep, output in the mode's planes, statistics as deferred-fold partial rows."""
-    from ccdm_b200 import _lib
-    from ccdm_b200.engine import from_pm, from_pm_x3, pack_bias, pack_conv_weight
-    from gpu_util import sp
-    Cout = 32
-    g = torch.Generator().manual_seed(11)
-    labels = torch.randint(0, K, (B, H, W), generator=g, dtype=torch.uint8)
-    image = torch.randn((B // rep, C_img, H, W), generator=g) * 2
-    w = _rand(Cout, K + C_img, 3, 3, seed=5) / math.sqrt(9 * (K + C_img))
-    b = _rand(Cout, seed=6) * 0.1
-    x = torch.cat([torch.nn.functional.one_hot(labels.long(), K).permute(0, 3, 1, 2).double(),
-                   image.repeat_interleave(rep, dim=0).double()], dim=1)
-    ref = torch.nn.functional.conv2d(x, w.double(), b.double(), padding=1)  # float64 yardstick
-    x3 = dt == "x3"
-    code = _lib.DT_F16X2 if x3 else _lib.DT_BF16
-    wp = pack_conv_weight(w.cuda(), (K + C_img + 7) // 8 * 8).contiguous()
-    bp = pack_bias(b.cuda())
-    lab_d, img_d = labels.cuda(), image.cuda().contiguous()
-    out = torch.full((B, Cout // 8, 2 if x3 else 1, H, W, 8), float("nan"), dtype=torch.float16 if x3 else torch.bfloat16, device="cuda")
-    op = _lib.Op(kind=_lib.OP_INPUT_LUT, dtype=code, out_dtype=code, B=B, Hin=H, Win=W, Hout=H, Wout=W, Cout=Cout, ksize=3, stride=1,
-                 K=K, C_img=C_img, img_rep=rep)
-    op.labels_in, op.image, op.weight, op.bias, op.out = lab_d.data_ptr(), img_d.data_ptr(), wp.data_ptr(), bp.data_ptr(), out.data_ptr()
-    lay = (ctypes.c_int32 * 5)()
-    assert L.ccdm_conv_stat_layout(ctypes.byref(op), lay) == 0
-    slots, ips, items, grid, rows = (int(v) for v in lay)
-    op.part = 1
-    part = torch.zeros(L.ccdm_op_part_floats(ctypes.byref(op)), dtype=torch.float32, device="cuda")
-    assert part.numel() == B * slots * rows * 2
-    op.part = part.data_ptr()
-    _lib.check(L.ccdm_launch_op(ctypes.byref(op), sp()))
-    torch.cuda.synchronize()
-    got = (from_pm_x3(out) if x3 else from_pm(out[:, :, 0]).float()).double().permute(0, 3, 1, 2).cpu()
-    err = float((got - ref).abs().max()) / float(ref.abs().max())
-    assert err <= (2e-6 if x3 else 8e-3), err  # fp32 FMAs; the store rounds to 22 bits (fp16x2) or 8 bits (bf16)
-    st = part.view(B, slots, rows, 2).double().sum(dim=1)[:, :Cout].cpu()
-    n = H * W
-    assert float(((st[..., 0] - ref.sum(dim=(2, 3))).abs() / n).max()) < 1e-5
-    assert float(((st[..., 1] - (ref * ref).sum(dim=(2, 3))).abs() / n).max()) < 1e-5

@@ -327,11 +327,6 @@ def test_every_conv_lands_on_the_tensor_core_kernel():
                 producers = {}
                 for i, o in enumerate(prog._op_dicts):
                     op = ops[i]
-                    if op.kind == _lib.OP_INPUT_LUT:  # the input conv on the labels: a producer of deferred-fold rows too
-                        lay = (ctypes.c_int32 * 5)()
-                        assert L.ccdm_conv_stat_layout(ctypes.byref(op), lay) == 0 and o["_out"].stat_layout == tuple(int(v) for v in lay)
-                        producers[id(o["_out"])] = tuple(int(v) for v in lay)
-                        assert op.ostat == 0 and op.part == o["_out"].part_addr and op.weight == eng.weights.addr(o["_w"])
                     if op.kind == _lib.OP_CONV:
                         assert L.ccdm_conv_uses_tc(ctypes.byref(op)) == 1 and op.exact == 0
                         for si, sten in enumerate(o.get("_src", [])[:2]):
