@@ -3,6 +3,8 @@
 // +embedding +residual -> plane-major bf16 / fp16x2 / NHWC fp32 store + GroupNorm statistics of the output).
 #pragma once
 
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace ccdm {
@@ -114,6 +116,25 @@ __device__ __forceinline__ void gn_build_affine(const WsP &p, int b, float *sAff
             q = e.y;
         } else {
             const int rows = p.st_rows[i], n = n_rows[i];
+            if (p.x3) {
+                // fp16x2 producers accumulate their statistics in double from the first addition (see the epilogue): the
+                // rows are double2 and their sum does not depend on how the producer's items were grouped
+                const double2 *pp = reinterpret_cast<const double2 *>(st) + size_t(b) * p.st_slots[i] * rows + cs;
+                for (int r0 = 0; r0 < n; r0 += 4) {
+                    double2 v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = r0 + u < n ? r0 + u : r0;
+                        v[u] = __ldcg(pp + size_t(r) * rows);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (r0 + u < n) {
+                            s += v[u].x;
+                            q += v[u].y;
+                        }
+                }
+            } else {
             const float2 *pp = reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(st) + (size_t(b) * p.st_slots[i] * rows + cs) * 2);
             for (int r0 = 0; r0 < n; r0 += 4) {
                 float2 v[4];
@@ -128,6 +149,7 @@ __device__ __forceinline__ void gn_build_affine(const WsP &p, int b, float *sAff
                         s += double(v[u].x);
                         q += double(v[u].y);
                     }
+            }
             }
         }
         sSum[c] = make_double2(s, q);
@@ -183,12 +205,25 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
     // GroupNorm statistics of the output: per-thread sums over an item -> warp transpose-reduce ->
     // per-warp running sums in shared memory (sAcc), flushed to global ONCE per (CTA, sample): a CTA's
     // items are contiguous, so this is one or two partial rows per CTA instead of one per item.
-    float *sAcc = sRed;  // [NEW][CoutP][2]
+    // fp16x2 ("exact" mode): an item's partial sums (per thread over its rows, then across the warp) are fp32 in a fixed order
+    // -- a function of the tile only -- and everything ABOVE the item is double: the per-warp running sums over the CTA's items,
+    // the cross-warp sum, the partial rows, the consumer's fold.  Sums of the same fp32 item partials in double are exact to
+    // 1e-16 whatever their grouping, so with a batch-independent tiling (ccdm_op::tile_batch) a sample's statistics -- and its
+    // result -- do not depend on the batch split or the number of GPUs.  (Double from the first addition was measured: +30 % per
+    // step -- FP64 issue rate.)  bf16 mode keeps fp32 throughout.
+    using ST = typename std::conditional<X3, double, float>::type;
+    // running sums: one row per warp (bf16, fp32) or per TMEM lane quarter (fp16x2, double: the two warps of a quarter own
+    // different column groups, so they never touch the same entry -- and four rows of doubles are the bytes of eight of floats)
+    // (upsampling convs: the two warps of a quarter split the output PARITIES of the same channels, so they keep a row each)
+    constexpr int ACC_ROWS = (X3 && NSUB == 1) ? 4 : NEW;
+    ST *sAcc = reinterpret_cast<ST *>(sRed);  // [ACC_ROWS][CoutP][2]
+    ST *part = reinterpret_cast<ST *>(p.part);
     const int CoutP = p.CoutP;
+    const int acc_row = ACC_ROWS == 4 ? (warp & 3) : warp;
     const bool want_stats = p.part != nullptr;  // with ostat: folded here (ticket); without: deferred to the consumer
-    if (want_stats) {
+    if (want_stats && warp < ACC_ROWS) {  // (the first use is behind the named barrier of the first item's bias load)
 #pragma unroll 1
-        for (int e = lane; e < CoutP * 2; e += 32) sAcc[warp * CoutP * 2 + e] = 0.f;
+        for (int e = lane; e < CoutP * 2; e += 32) sAcc[warp * CoutP * 2 + e] = ST(0);
         __syncwarp();
     }
     auto flush_stats = [&](int b, int n_done) {
@@ -197,13 +232,13 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
         const int slot = int(blockIdx.x) - c_first;
 #pragma unroll 1
         for (int e = tid; e < CoutP * 2; e += NTHR) {
-            float s = 0.f;
+            ST s = ST(0);
 #pragma unroll
-            for (int r = 0; r < NEW; ++r) {
+            for (int r = 0; r < ACC_ROWS; ++r) {
                 s += sAcc[r * CoutP * 2 + e];
-                sAcc[r * CoutP * 2 + e] = 0.f;
+                sAcc[r * CoutP * 2 + e] = ST(0);
             }
-            p.part[(size_t(b) * p.slots + slot) * CoutP * 2 + e] = s;
+            part[(size_t(b) * p.slots + slot) * CoutP * 2 + e] = s;
         }
         if (p.ostat == nullptr) {  // deferred fold: the partial row IS the result; the kernel boundary publishes it
             named_bar_sync(2, NTHR);
@@ -225,7 +260,7 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
             const int n_slots = c_last - c_first + 1;
 #pragma unroll 1
             for (int e = tid; e < p.Cout * 2; e += NTHR) {
-                const float *pp = p.part + size_t(b) * p.slots * CoutP * 2 + e;
+                const ST *pp = part + size_t(b) * p.slots * CoutP * 2 + e;
                 double s = 0.0;
 #pragma unroll 2
                 for (int t = 0; t < n_slots; ++t) s += double(__ldcg(pp + size_t(t) * CoutP * 2));
@@ -416,13 +451,13 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
             }
             }
             if (want_stats) {
-                const float r1 = warp_transpose_reduce16(s1, lane);
-                const float r2 = warp_transpose_reduce16(s2, lane);
+                const float r1 = warp_transpose_reduce16<float>(s1, lane);
+                const float r2 = warp_transpose_reduce16<float>(s2, lane);
                 if ((lane & 1) == 0) {
                     const int ch = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                    float *a = sAcc + (warp * CoutP + cobase + ch) * 2;
-                    a[0] += r1;
-                    a[1] += r2;
+                    ST *a = sAcc + (acc_row * CoutP + cobase + ch) * 2;
+                    a[0] += ST(r1);
+                    a[1] += ST(r2);
                 }
             }
         }

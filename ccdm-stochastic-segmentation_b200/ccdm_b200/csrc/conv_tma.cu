@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
     float *sAff = reinterpret_cast<float *>(sW + w_region);  // [2][Cin]
     float *sAdd = sAff + 2 * p.Cin;                          // [NT]
     float *sRed = sAdd + NT;                                 // [8][CoutP][2]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sRed + TM_EPI_WARPS * p.CoutP * 2);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sRed + TM_EPI_WARPS * p.CoutP * 2 * ((X3 && UP) ? 2 : 1));  // (fp16x2: four rows of doubles = the same bytes; eight when upsampling)
     uint64_t *raw_full = bars, *xf_full = bars + MAX_STAGES, *empty = bars + 2 * MAX_STAGES;
     uint64_t *acc_full = bars + 3 * MAX_STAGES, *acc_empty = acc_full + 2, *w_res = acc_empty + 2;
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(w_res + 1);
@@ -650,13 +650,33 @@ int tm_nt(int Cout, int taps, int x3) { return tc_nt(Cout, taps, x3); }
 // x3: fp16x2 operands -- a stage holds 2*PL planes and the weights are twice as many rows (conv_tma_kernel<..., X3>)
 bool tm_configure_pl(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout, int ksize, int stride, int up, int x3, int force_pl,
                      size_t res_max, TmCfg &best);
+bool tm_configure_b(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout, int ksize, int stride, int up, int x3, TmCfg &best);
+
+// tile_batch > 0: choose the tile for that batch size, then lay the REAL batch out on it (items, grid, statistics slots)
+bool tm_configure(int B, int tile_batch, int H, int W, int C0, int C1, int S0, int S1, int Cout, int ksize, int stride, int up, int x3,
+                  TmCfg &best) {
+    if (tile_batch <= 0 || tile_batch == B) return tm_configure_b(B, H, W, C0, C1, S0, S1, Cout, ksize, stride, up, x3, best);
+    if (!tm_configure_b(tile_batch, H, W, C0, C1, S0, S1, Cout, ksize, stride, up, x3, best)) return false;
+    const long long items = (long long)B * best.tiles * best.n_cc;
+    const int sms = tm_num_sms();
+    best.n_items = int(items);
+    best.grid = int(items < sms ? items : sms);
+    best.ips = best.tiles * best.n_cc;
+    best.slots = 1;
+    for (int b = 0; b < B; ++b) {
+        const int c_first = int((((long long)b * best.ips + 1) * best.grid - 1) / best.n_items);
+        const int c_last = int(((long long)(b + 1) * best.ips * best.grid - 1) / best.n_items);
+        if (c_last - c_first + 1 > best.slots) best.slots = c_last - c_first + 1;
+    }
+    return true;
+}
 
 // Weights stay in shared memory for the whole launch when they are small (<= 80 KB).  CCDM_TMA_RESMAX=<KB> raises the
 // ceiling for layers that still fit next to >= 3 activation stages (A/B runs).  MEASURED (round 2, 176 KB: the 64-channel
 // convs of the 32x32 level and 96->32 @64x64 become resident, at the price of 3-4-row tiles): LIDC exact 4.12 vs 4.07 ms per
 // reverse step, Cityscapes 4.97 vs 4.94 -- the re-streamed weights come out of L2 and were not what bounds those launches
 // (the tensor pipe is: 60 % busy fetching A operands), the smaller tiles cost more halo.  Off by default.
-bool tm_configure(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout, int ksize, int stride, int up, int x3, TmCfg &best) {
+bool tm_configure_b(int B, int H, int W, int C0, int C1, int S0, int S1, int Cout, int ksize, int stride, int up, int x3, TmCfg &best) {
     static const size_t env_res = getenv("CCDM_TMA_RESMAX") ? size_t(atoi(getenv("CCDM_TMA_RESMAX"))) * 1024 : kTmResidentMax;
     TmCfg big;
     if (env_res > kTmResidentMax && tm_configure_pl(B, H, W, C0, C1, S0, S1, Cout, ksize, stride, up, x3, 0, env_res, big) && big.resident &&
@@ -712,7 +732,7 @@ bool tm_configure_pl(int B, int H, int W, int C0, int C1, int S0, int S1, int Co
     c.resident = (c.n_cc == 1 && w_total <= res_max) ? 1 : 0;
     c.w_stage = c.resident ? 0u : uint32_t(c.PL * taps * c.NT * 16 * X);
     const size_t slack = (size_t(128 + 2 * pad * c.P + 2 * pad) * 16 + 127) & ~size_t(127);
-    const size_t fixed = sizeof(float) * (2 * size_t(Cin) + c.NT + size_t(TM_EPI_WARPS) * CoutP * 2) + (3 * MAX_STAGES + 5) * 8 + 64 + 16 * size_t(Cin) + 16 + slack +
+    const size_t fixed = sizeof(float) * (2 * size_t(Cin) + c.NT + size_t(TM_EPI_WARPS) * CoutP * 2 * ((x3 && up) ? 2 : 1)) + (3 * MAX_STAGES + 5) * 8 + 64 + 16 * size_t(Cin) + 16 + slack +
                          (c.resident ? w_total : 0) + 1024;
     double best_cost = 1e300;
     bool found = false;
@@ -771,8 +791,8 @@ bool tm_configure_pl(int B, int H, int W, int C0, int C1, int S0, int S1, int Co
 
 bool tm_configure_op(const ccdm_op &op, TmCfg &c) {
     const int x3 = op.dtype == CCDM_DT_F16X2;
-    if (op.upsample) return tm_configure(op.B, op.Hin, op.Win, op.C0, op.C1, op.S0, op.S1, op.Cout, op.ksize, op.stride, 1, x3, c);
-    return tm_configure(op.B, op.Hout, op.Wout, op.C0, op.C1, op.S0, op.S1, op.Cout, op.ksize, op.stride, 0, x3, c);
+    if (op.upsample) return tm_configure(op.B, op.tile_batch, op.Hin, op.Win, op.C0, op.C1, op.S0, op.S1, op.Cout, op.ksize, op.stride, 1, x3, c);
+    return tm_configure(op.B, op.tile_batch, op.Hout, op.Wout, op.C0, op.C1, op.S0, op.S1, op.Cout, op.ksize, op.stride, 0, x3, c);
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
@@ -879,7 +899,7 @@ int conv_tma_stat_layout(const ccdm_op &op, int32_t *out5) {
 size_t conv_tma_part_floats(const ccdm_op &op) {
     TmCfg c;
     if (!tm_configure_op(op, c)) return 0;
-    return size_t(op.B) * c.slots * ((op.Cout + 15) / 16 * 16) * 2;
+    return size_t(op.B) * c.slots * ((op.Cout + 15) / 16 * 16) * 2 * (op.dtype == CCDM_DT_F16X2 ? 2 : 1);  // fp16x2: rows of doubles
 }
 
 // fp16x2 instruction descriptor / bf16: cute::UMMA::InstrDescriptor -- D = f32 (bit 4), A and B formats at bits 7 and 10

@@ -205,7 +205,10 @@ __device__ __forceinline__ void split_f16x2(float a, float b, uint32_t &hi, uint
 // Transpose-reduce: on entry every lane holds 16 per-channel partial sums; on exit lane l holds
 // the warp total of channel ((l>>4)&1)*8 + ((l>>3)&1)*4 + ((l>>2)&1)*2 + ((l>>1)&1) (both lanes
 // of a pair hold the same value).  Fixed order of additions -> deterministic.
-__device__ __forceinline__ float warp_transpose_reduce16(float (&v)[16], int lane) {
+template <typename T>
+__device__ __forceinline__ T warp_transpose_reduce16(T (&v)[16], int lane);
+template <>
+__device__ __forceinline__ float warp_transpose_reduce16<float>(float (&v)[16], int lane) {
     const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
     float a8[8], a4[4], a2[2], a1;
 #pragma unroll

@@ -370,13 +370,14 @@ class PackedWeights:
 class Program:
     """One reverse step for fixed (B, H, W): op list + workspace, bound to device addresses."""
 
-    def __init__(self, engine: "UNetEngine", B: int, H: int, W: int, rows_per_sample: int, img_rep: int = 1):
+    def __init__(self, engine: "UNetEngine", B: int, H: int, W: int, rows_per_sample: int, img_rep: int = 1, tile_batch: int = 0):
         unet, arch = engine.unet, engine.unet.arch
         self.engine = engine
         self.B, self.H, self.W = B, H, W
         if img_rep < 1 or B % img_rep:
             raise ValueError(f"batch {B} is not a multiple of the samples per image ({img_rep})")
         self.img_rep = img_rep  # consecutive samples that share one conditioning image / feature map (SURVEY 8f-2)
+        self.tile_batch = tile_batch  # ccdm_op::tile_batch of every conv: batch-independent tiling (0: tiles follow B)
         self.K = unet.out_channels
         self.C_img = unet.in_channels - self.K
         self.dt, self.esize, tc_mode = PRECISIONS[engine.precision]
@@ -572,6 +573,8 @@ class Program:
             """Shape / variant fields of an op: everything the kernel dispatch depends on (no statistics, no weights)."""
             f = {k: v for k, v in o.items() if not k.startswith("_")}
             fields = dict(dtype=self.dt, B=self.B, exact=self.exact, out_dtype=self.dt)
+            if o["kind"] == _lib.OP_CONV:
+                fields["tile_batch"] = self.tile_batch
             fields.update(f)
             op = Op(**fields)
             src = o.get("_src", [])
@@ -741,17 +744,21 @@ class UNetEngine:
         # it stays off; see DESIGN.md section 9.
         import os
         self.lanes = max(1, int(os.environ.get("CCDM_LANES", "1")))
+        # Batch-independent tiling (ccdm_op::tile_batch): 0 = every conv picks its tile height from its own batch (fastest);
+        # N > 0 = as if the batch were N.  With a fixed value the `exact` mode's result for a sample is bit-identical
+        # whatever batch it runs in (DenoisingModel.tile_batch; sample_sharded sets 64).
+        self.tile_batch = 0
         self._children: List["UNetEngine"] = []
 
     # -- helpers ----------------------------------------------------------------------
     def program(self, B, H, W, rows_per_sample=0, img_rep=1) -> Program:
-        key = (B, H, W, rows_per_sample, img_rep)
+        key = (B, H, W, rows_per_sample, img_rep, self.tile_batch)
         prog = self.programs.get(key)
         if prog is None:
             # bounded cache: a ragged last batch or a change of batch size must not pile up ~1 GB workspaces
             while len(self.programs) >= PROGRAM_CACHE:
                 self.programs.popitem(last=False)
-            prog = self.programs[key] = Program(self, B, H, W, rows_per_sample, img_rep)
+            prog = self.programs[key] = Program(self, B, H, W, rows_per_sample, img_rep, self.tile_batch)
         else:
             self.programs.move_to_end(key)
         return prog
@@ -844,9 +851,11 @@ class UNetEngine:
             c = UNetEngine.__new__(UNetEngine)
             c.dry_run, c.unet, c.precision, c.device, c.weights = False, self.unet, self.precision, self.device, self.weights
             c.programs, c.stream, c.use_graph, c.lanes, c._children = OrderedDict(), torch.cuda.Stream(device=self.device), self.use_graph, 1, []
+            c.tile_batch = self.tile_batch
             self._children.append(c)
         for c in self._children:
             c.use_graph = self.use_graph
+            c.tile_batch = self.tile_batch
         return self._children[:n]
 
     @torch.no_grad()

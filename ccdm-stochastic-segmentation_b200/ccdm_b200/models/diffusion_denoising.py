@@ -18,6 +18,10 @@ Knobs that do not exist in the reference (plain attributes; the defaults are the
                  keyed by (seed, global sample index, step, pixel): sharding-invariant, no noise traffic, the whole
                  chain replays as CUDA graphs -- ~1.0x (LIDC) .. 1.3x (Cityscapes) faster; what the benchmark uses)
   ``seed``, ``sample_offset``  Philox key / global index of local sample 0.
+  ``tile_batch``  0 (default): every conv picks its tile height from the batch it is given (fastest).  N > 0: as if the batch
+                 were N -- the tiling, and with it the summation order of the GroupNorm statistics, no longer depends on how
+                 the samples are batched, so in 'exact' mode a sample's result is bit-identical on 1 GPU or 8, in a batch of
+                 64 or of 2 (``sample_sharded`` sets 64; costs throughput only when the real batch is much smaller).
 """
 import logging
 import math
@@ -130,6 +134,7 @@ class DenoisingModel(nn.Module):
         self.noise = "torch"
         self.seed = 0
         self.sample_offset = 0
+        self.tile_batch = 0
         self._sched_host = None
 
     @property
@@ -201,7 +206,9 @@ class DenoisingModel(nn.Module):
         confidence = self.step_T_sample == "confidence"
         base = int(self.sample_offset)  # global index of this call's first SAMPLE (image-major, sample-minor)
         x = self.draw_x_T(B, H, W, dev)
-        labels, probs = self.unet.engine(self.precision).run_chain(
+        engine = self.unet.engine(self.precision)
+        engine.tile_batch = int(self.tile_batch)
+        labels, probs = engine.run_chain(
             x, condition, feature_condition, t_values, alphas, cumalphas, _lib.DRAW_CONFIDENCE if confidence else _lib.DRAW_MAJORITY,
             noise="philox", seed=self.seed, sample0=base, img_rep=n_samples)
         freq = torch.empty((B_img, K, H, W), dtype=torch.float32, device=dev)
@@ -238,6 +245,7 @@ class DenoisingModel(nn.Module):
         if not (self.step_T_sample is None or self.step_T_sample in ("majority", "confidence")):
             raise ValueError(f"step_T_sample={self.step_T_sample!r}")
         engine = self.unet.engine(self.precision)
+        engine.tile_batch = int(self.tile_batch)
         labels, probs = engine.run_chain(x, condition, feature_condition, t_values, alphas, cumalphas,
                                          _lib.DRAW_CONFIDENCE if confidence else _lib.DRAW_MAJORITY,
                                          noise=self.noise, seed=self.seed, sample0=self.sample_offset)

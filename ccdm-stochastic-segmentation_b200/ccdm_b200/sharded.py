@@ -19,7 +19,9 @@ from typing import Optional, Tuple
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "padded_shard", "gather_shards", "sample_sharded"]
+__all__ = ["shard_range", "padded_shard", "gather_shards", "sample_sharded", "CANONICAL_TILE_BATCH"]
+
+CANONICAL_TILE_BATCH = 64  # DenoisingModel.tile_batch that sample_sharded uses unless the caller set one
 
 
 def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
@@ -83,6 +85,11 @@ def sample_sharded(model, x: torch.Tensor, condition: torch.Tensor, feature_cond
     elif not isinstance(old_noise, str):
         raise ValueError("sample_sharded: explicit noise tensors cannot be sharded; use noise='philox'")
     model.sample_offset = old_offset + b
+    # batch-independent tiling: a sample's result must not depend on how many ranks share the batch (bit-identical in the
+    # 'exact' mode; see DenoisingModel.tile_batch)
+    old_tile = getattr(model, "tile_batch", 0)
+    if not old_tile:
+        model.tile_batch = CANONICAL_TILE_BATCH
     try:
         if e > b:
             out = model(x[b:e], condition[b:e], feature_condition[b:e] if feature_condition is not None else None, t)["diffusion_out"]
@@ -93,6 +100,7 @@ def sample_sharded(model, x: torch.Tensor, condition: torch.Tensor, feature_cond
     finally:
         model.sample_offset = old_offset
         model.noise = old_noise
+        model.tile_batch = old_tile
     if out.dtype == torch.int64:  # majority: ship 1 byte per pixel, rebuild the one-hot view after the gather
         K = out.shape[1]
         labels = gather_shards(out.argmax(dim=1).to(torch.uint8), n, group)

@@ -114,7 +114,11 @@ typedef struct ccdm_op {
      * as the producer's epilogue wrote them (ccdm_conv_stat_layout); the consumer folds rows
      * [0, CTAs that touched sample b) in order, in double -- same sums, no ticket / fence / atomic in the producer. */
     int32_t st_slots[2], st_ips[2], st_items[2], st_grid[2], st_rows[2];
-    int32_t pad_align;
+    int32_t tile_batch; /* tensor-core convs: batch size the TILE SELECTION assumes (0: this op's own B).  The tile height is chosen
+                         * from the number of work items, i.e. from the batch; a fixed value makes the tiling -- and with it the
+                         * fp32 per-item partial sums of the GroupNorm statistics -- independent of how a batch is split over
+                         * calls or GPUs (bit-identical results in the fp16x2 mode), at the price of fewer, larger items when the
+                         * real batch is small */
     uint64_t seed;      /* Philox key */
     /* device pointers (0 = absent) */
     uint64_t src0, src1;       /* inputs NHWC                                             */

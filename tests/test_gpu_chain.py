@@ -231,11 +231,18 @@ def test_chain_is_deterministic_and_sharding_invariant(cuda_device):
         if prec == "fp32":
             assert torch.equal(full[2:], shard)
         else:
-            # tensor-core modes: same noise, same arithmetic per pixel, but the fp32 partial sums of the GroupNorm statistics
-            # are grouped per CTA and the tiling follows the batch: 1e-7-level differences, a near-tie may flip
+            # default tiling follows the batch: the fp32 per-item partial sums of the GroupNorm statistics differ at the 1e-7
+            # level between a batch of 4 and a batch of 2, a near-tie may flip
             agree = float((full[2:] == shard).float().mean())
-            _report("exact_shard_agreement", agreement=agree)
+            _report("exact_shard_agreement_default_tiling", agreement=agree)
             assert agree >= 0.999, agree
+            # batch-independent tiling (what sample_sharded sets): bit-identical
+            m.tile_batch, m.sample_offset = 64, 0
+            full = m(_onehot(labels, K).cuda(), image.cuda(), None, t=tt)["diffusion_out"]
+            m.sample_offset = 2
+            shard = m(_onehot(labels[2:], K).cuda(), image[2:].cuda(), None, t=tt)["diffusion_out"]
+            m.tile_batch = 0
+            assert torch.equal(full[2:], shard)
 
 
 def test_sub_batch_lanes_do_not_change_the_result(cuda_device):

@@ -142,3 +142,28 @@ def test_chain_replays_reference_fixture_at_benchmark_size(cuda_device, tag, pre
     agree = float((got == want).mean())
     _report(f"fullsize_fixture_chain_{prec}_{tag}", agreement=agree)
     assert agree >= 0.999, agree
+
+
+def test_exact_mode_is_identical_under_any_batch_split(cuda_device):
+    """With a batch-independent tiling (`DenoisingModel.tile_batch`), the parity mode's result for a sample does not depend on
+    which other samples share its batch: LIDC 128x128, the same 12
+    samples run as one batch of 12, as 8 + 4 and as 5 + 7 (different tile heights, grids and CTA-to-sample assignments in every
+    layer), 12 strided steps, in-kernel Philox noise keyed by the global sample index -> bit-identical label maps.  This is what
+    makes `sample_sharded` / `bench.py --gpus N` return the same samples on 1, 2, 4 or 8 GPUs."""
+    from ccdm_b200.synthetic import synthetic_inputs
+    T, _, C_img, H, W, K, fce = FULL_CASES["lidc128_b64"][:7]
+    m = build_ours(T, C_img, H, W, K, "majority", fce, None).cuda()
+    image, _, labels = synthetic_inputs(12, C_img, H, W, K)
+    m.noise, m.seed, m.precision = "philox", 5, "exact"
+    m.tile_batch = 64  # batch-independent tiling (what sample_sharded sets)
+    tt = torch.as_tensor(10000 + 12)
+
+    def run(b0, b1):
+        m.sample_offset = b0
+        return m(labels[b0:b1].cuda(), image[b0:b1].cuda(), None, t=tt)["diffusion_out"].argmax(1)
+
+    whole = run(0, 12)
+    for cut in (8, 5):
+        parts = torch.cat([run(0, cut), run(cut, 12)], 0)
+        assert torch.equal(whole, parts), cut
+    m.sample_offset = 0
