@@ -80,6 +80,8 @@ def lib():
     L.ccdm_onehot_to_labels.argtypes = [ctypes.c_void_p] + [ctypes.c_int64] * 4 + [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_void_p]
     L.ccdm_labels_to_onehot_i64.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
     L.ccdm_nchw_to_nhwc_stats.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 5 + [ctypes.c_void_p] * 2 + [ctypes.c_int, ctypes.c_void_p]
+    L.ccdm_pairwise_distance.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_size_t,
+                                         ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
     L.ccdm_vote.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                             ctypes.c_void_p]
     L.ccdm_posterior_draw.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_float,

@@ -204,6 +204,55 @@ __global__ void __launch_bounds__(256) vote_kernel(const uint8_t *__restrict__ l
     if (majority != nullptr) majority[i] = uint8_t(best);
 }
 
+// One CTA per (image, sample n, sample m): integer counts of |x==c & y==c|, |x==c|, |y==c| for c = 1..K-1 over the pixels.
+// K <= 8: warp ballots, counters in registers (uniform across the warp); larger K: shared-memory histograms.
+__global__ void __launch_bounds__(256) pairwise_distance_kernel(const uint8_t *__restrict__ x, const uint8_t *__restrict__ y, int N, int M,
+                                                                size_t n_pix, int K, double *__restrict__ dist) {
+    __shared__ unsigned int s_cnt[3][256];  // [inter | x | y][class]
+    const int m = blockIdx.x % M, n = blockIdx.x / M, b = blockIdx.y;
+    const uint8_t *px = x + (size_t(b) * N + n) * n_pix, *py = y + (size_t(b) * M + m) * n_pix;
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int e = tid; e < 3 * 256; e += 256) (&s_cnt[0][0])[e] = 0u;
+    __syncthreads();
+    if (K <= 8) {
+        unsigned int ci[8] = {0}, cx[8] = {0}, cy[8] = {0};
+        const size_t n_round = (n_pix + 255) / 256 * 256;  // every lane takes part in every ballot
+        for (size_t i = tid; i < n_round; i += 256) {
+            const int vx = i < n_pix ? px[i] : 255, vy = i < n_pix ? py[i] : 255;
+#pragma unroll
+            for (int c = 1; c < 8; ++c)
+                if (c < K) {
+                    const unsigned bx = __ballot_sync(0xffffffffu, vx == c), by = __ballot_sync(0xffffffffu, vy == c);
+                    ci[c] += __popc(bx & by);
+                    cx[c] += __popc(bx);
+                    cy[c] += __popc(by);
+                }
+        }
+        if (lane == 0)
+            for (int c = 1; c < K; ++c) {
+                atomicAdd(&s_cnt[0][c], ci[c]);
+                atomicAdd(&s_cnt[1][c], cx[c]);
+                atomicAdd(&s_cnt[2][c], cy[c]);
+            }
+    } else {
+        for (size_t i = tid; i < n_pix; i += 256) {
+            const int vx = px[i], vy = py[i];
+            atomicAdd(&s_cnt[1][vx], 1u);
+            atomicAdd(&s_cnt[2][vy], 1u);
+            if (vx == vy) atomicAdd(&s_cnt[0][vx], 1u);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double acc = 0.0;
+        for (int c = 1; c < K; ++c) {
+            const unsigned int inter = s_cnt[0][c], uni = s_cnt[1][c] + s_cnt[2][c] - inter;
+            acc += uni == 0u ? 1.0 : double(inter) / double(uni);  // utils.py:131: NaN (0/0) -> 1
+        }
+        dist[(size_t(b) * N + n) * M + m] = 1.0 - acc / double(K - 1);
+    }
+}
+
 }  // namespace
 
 int launch_encode_input(const ccdm_op &op, cudaStream_t s) {
@@ -278,5 +327,15 @@ extern "C" int ccdm_vote(const uint8_t *labels, int B_img, int N, size_t n_pix, 
     const size_t total = size_t(B_img) * n_pix;
     vote_kernel<<<unsigned((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(labels, N, n_pix, K, total, freq, majority);
     CCDM_LAUNCH_CHECK("vote_kernel");
+    return 0;
+}
+
+extern "C" int ccdm_pairwise_distance(const uint8_t *x, const uint8_t *y, int B, int N, int M, size_t n_pix, int K, double *dist,
+                                      void *stream) {
+    if (B <= 0 || N <= 0 || M <= 0) return 0;
+    if (K < 2 || K > 255 || !x || !y || !dist || n_pix == 0) CCDM_FAIL(-2, "pairwise_distance: K=%d n_pix=%zu", K, n_pix);
+    if (size_t(N) * M > 0x7fffffffull || B > 65535) CCDM_FAIL(-2, "pairwise_distance: too many pairs for one launch");
+    pairwise_distance_kernel<<<dim3(unsigned(N * M), unsigned(B)), 256, 0, (cudaStream_t)stream>>>(x, y, N, M, n_pix, K, dist);
+    CCDM_LAUNCH_CHECK("pairwise_distance_kernel");
     return 0;
 }

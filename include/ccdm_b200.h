@@ -228,6 +228,15 @@ int ccdm_philox_bits(uint64_t seed, uint32_t draw, uint32_t sample0, uint32_t n_
 int ccdm_uniform_labels(uint64_t seed, uint32_t draw, uint32_t sample0, uint32_t n_samples, uint32_t n_pix,
                         int K, uint8_t *labels, void *stream);
 
+/* Pairwise segmentation distance between two sets of label maps of the same images -- the kernel under the LIDC metrics
+ * (SURVEY.md 8f-4): ddpm/utils.py:129-142 `iou` + `batched_distance` (also evaluate_lidc_uncertainty.py:27-41), which
+ * `calc_batched_generalised_energy_distance` (:145-158) and `batched_hungarian_matching` (:161-174) are built on.
+ * x uint8 [B, N, n_pix], y uint8 [B, M, n_pix] -> dist double [B, N, M]:
+ *   dist[b,n,m] = 1 - mean over classes c = 1..K-1 (background excluded) of |x==c & y==c| / |x==c | y==c|, 0/0 := 1.
+ * The reference builds [B,N,M,n_pix,K] boolean broadcasts on the host; here one CTA per (b, n, m) counts in integers and
+ * does the final divisions in double, so the result equals numpy's to the last bits of the class mean. */
+int ccdm_pairwise_distance(const uint8_t *x, const uint8_t *y, int B, int N, int M, size_t n_pix, int K, double *dist, void *stream);
+
 /* ---- programs: the whole reverse step as one launch sequence / CUDA graph --- */
 typedef struct ccdm_plan ccdm_plan;
 
