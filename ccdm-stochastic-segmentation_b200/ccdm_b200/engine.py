@@ -292,6 +292,13 @@ class PackedWeights:
     def _current_stamp(self):
         return tuple((p.data_ptr(), p._version) for p in self.unet.parameters())
 
+    def invalidate(self):
+        """Force a repack on the next call.  The staleness stamp is (data_ptr, _version) of every parameter: it sees
+        ``load_state_dict``, ``.to()`` and in-place tensor ops (the reference's Polyak averager writes ``dst[...] = value``), but
+        NOT writes through ``p.data`` (``p.data.mul_()``, ``p.data.copy_()``), which do not bump ``_version`` -- code that updates
+        weights that way calls this (``model.unet.engine(prec).weights.invalidate()``)."""
+        self._stamp = None
+
     def refresh(self) -> bool:
         """(Re)pack if any parameter changed since the last call.  Returns True if repacked."""
         stamp = self._current_stamp()
