@@ -312,7 +312,8 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
         const int buf = p.acc2 ? (acc_it & 1) : 0;
         const uint32_t aph = p.acc2 ? uint32_t((acc_it >> 1) & 1) : uint32_t(acc_it & 1);
         // fp16x2: 2 NT columns per (M block, parity): [0, NT) the hi*hi products, [NT, 2 NT) the small hi*lo + lo*hi terms
-        constexpr int XA = X3 ? 2 : 1;
+        // (upsampling convs keep ONE accumulator per parity -- four parities x two halves would not leave room to double-buffer)
+        constexpr int XA = (X3 && NSUB == 1) ? 2 : 1;
         const uint32_t tbase = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * p.MB * NT * nsub * XA);
         const int ylim = min(p.R, p.H - I.y0), xlim = min(p.Wt, p.W - I.x0);  // rows / columns of real outputs
         bool waited = false;
@@ -420,7 +421,7 @@ __device__ __forceinline__ void conv_epilogue_role(const WsP &p, float *sAdd, fl
             };
             const uint32_t tcol = tbase + uint32_t(sub * NT * XA + cg * CGW), tstep = uint32_t(nsub * NT * XA);
             uint32_t ra[CGW], rb[CGW];
-            if constexpr (X3) {
+            if constexpr (X3 && NSUB == 1) {
                 // main + small accumulator columns of a row block, summed here in fp32 (round to nearest); the loads of block
                 // mb+1 are in flight while block mb is processed
                 tmem_ld16_issue(tcol, ra);

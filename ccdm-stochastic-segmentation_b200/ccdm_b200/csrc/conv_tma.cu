@@ -470,9 +470,16 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
 #ifdef CCDM_ABLATE
             if (p.dbg & 1) return;
 #endif
-            if constexpr (X3) {
+            if constexpr (X3 && !UP) {
                 umma_bf16_split(d, a, desc_hi, b, desc_hi, p.idesc2, acc);
                 umma_bf16_split(d + b_lo, a + a_lo, desc_hi, b, desc_hi, p.idesc, 1u);
+            } else if constexpr (X3) {
+                // upsampling conv: four parity accumulators per M block already; the three split products share one accumulator
+                // (N = NT) so that two sets of them still fit the 512 TMEM columns and the epilogue overlaps the next item's MMAs
+                // (measured with single-buffered N-concatenated accumulators: 5.7 us per item of pure hand-off latency)
+                umma_bf16_split(d, a, desc_hi, b + b_lo, desc_hi, p.idesc, acc);
+                umma_bf16_split(d, a + a_lo, desc_hi, b, desc_hi, p.idesc, 1u);
+                umma_bf16_split(d, a, desc_hi, b, desc_hi, p.idesc, 1u);
             } else {
                 umma_bf16_split(d, a, desc_hi, b, desc_hi, p.idesc, acc);
             }
@@ -483,7 +490,8 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
             mbar_wait<128>(acc_empty + buf, aph ^ 1u);
             tc_fence_after();
             if (mw == 0 && lane == 0) tl(2, it - it_begin, 0);
-            const uint32_t d0 = tmem_base + uint32_t(buf * p.MB * NT * X * (UP ? 4 : 1));
+            constexpr int XA = (X3 && !UP) ? 2 : 1;  // accumulator columns per (M block, parity) in units of NT
+            const uint32_t d0 = tmem_base + uint32_t(buf * p.MB * NT * XA * (UP ? 4 : 1));
             for (int kc = 0; kc < n_chunks; ++kc) {
                 const bool is_skip = kc >= p.n_main;
                 const int ntap = is_skip ? 1 : p.taps;
@@ -506,7 +514,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
                         const uint32_t arow = aaddr + uint32_t(mb * 128);
 #pragma unroll
                         for (int par = 0; par < 4; ++par) {
-                            const uint32_t d = d0 + uint32_t((mb * 4 + par) * NT * X);
+                            const uint32_t d = d0 + uint32_t((mb * 4 + par) * NT * XA);
                             uint32_t acc = kc > 0 ? 1u : 0u;
 #pragma unroll
                             for (int t = 0; t < 4; ++t) {
@@ -522,7 +530,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
                     }
                 } else if (ntap == 9) {
                     for (int mb = mw; mb < p.MB; mb += MMA_WARPS) {
-                        const uint32_t d = d0 + uint32_t(mb * NT * X);
+                        const uint32_t d = d0 + uint32_t(mb * NT * XA);
                         const uint32_t arow = aaddr + uint32_t(mb * 128);
                         uint32_t acc = kc > 0 ? 1u : 0u;
 #pragma unroll
@@ -545,7 +553,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
                     // 1x1 conv, or the fused 1x1 skip conv of a 3x3 block (centre tap of the window)
                     const uint32_t shift = is_skip ? uint32_t(p.pad * P + p.pad) : 0u;
                     for (int mb = mw; mb < p.MB; mb += MMA_WARPS) {
-                        const uint32_t d = d0 + uint32_t(mb * NT * X);
+                        const uint32_t d = d0 + uint32_t(mb * NT * XA);
                         const uint32_t at = aaddr + uint32_t(mb * 128) + shift;
 #pragma unroll
                         for (int k16 = 0; k16 < PL / 2; ++k16)
@@ -738,7 +746,8 @@ bool tm_configure_pl(int B, int H, int W, int C0, int C1, int S0, int S1, int Co
     bool found = false;
     for (int R = 1; R <= H && 2 * (R + 2 * pad) <= 256; ++R) {
         const int MB = (R * c.P + 127) / 128;
-        if (nsub * MB * c.NT * X > 512) break;
+        const int XA = (x3 && !up) ? 2 : 1;  // accumulator columns per (M block, parity) in units of NT
+        if (nsub * MB * c.NT * XA > 512) break;
         const int RW = s2 ? R + 1 : R + 2 * pad, NQ = RW * c.P;
         bool magic_ok = true;
         for (int q = 0; q < NQ + 256; ++q)
@@ -761,16 +770,18 @@ bool tm_configure_pl(int B, int H, int W, int C0, int C1, int S0, int S1, int Co
         double cost = double(per_cta) * item_cost;
         if (NS < 3) cost *= 1.5;
         else if (NS < 4) cost *= 1.1;
-        if (2 * nsub * MB * c.NT * X > 512) cost *= 1.15;  // single accumulator buffer: epilogue not overlapped
+        // single accumulator buffer: the epilogue is not overlapped with the next item's MMAs -- costly for the upsampling convs,
+        // whose epilogue drains four parity accumulators per M block (measured: ~5.7 us per item of serialised hand-offs)
+        if (2 * nsub * MB * c.NT * XA > 512) cost *= (up && x3) ? 1.6 : 1.15;
         if (env_r > 0 && W >= 64 && H >= 64) cost = (R == env_r) ? 0.0 : 1e290;
         if (cost < best_cost) {
             best_cost = cost;
             best = c;
             best.R = R; best.RW = RW; best.NQ = NQ; best.MB = MB; best.NS = NS; best.a_stage = uint32_t(a_stage);
-            best.acc2 = 2 * nsub * MB * c.NT * X <= 512;
+            best.acc2 = 2 * nsub * MB * c.NT * XA <= 512;
             best.tiles = tiles; best.n_items = int(items); best.grid = grid;
             int cols = 32;
-            while (cols < (best.acc2 ? 2 : 1) * nsub * MB * c.NT * X) cols *= 2;
+            while (cols < (best.acc2 ? 2 : 1) * nsub * MB * c.NT * XA) cols *= 2;
             best.tmem_cols = cols;
             best.smem = fixed + size_t(NS) * (a_stage + c.w_stage);
             found = true;
