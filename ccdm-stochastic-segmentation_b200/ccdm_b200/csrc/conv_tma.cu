@@ -729,9 +729,20 @@ bool tm_configure_pl(int B, int H, int W, int C0, int C1, int S0, int S1, int Co
     c.n_skip = Sk / KC;
     const int n_chunks = c.n_main + c.n_skip;
     const bool s2 = stride == 2;  // H, W: OUTPUT size; the stage holds 4 parity sub-images of (R+1) x (Wt+1) positions
-    c.Wt = W > 64 ? 64 : W;
+    // Tile width.  bf16: 64 columns (or the whole row).  fp16x2: 64 or 32 -- its accumulators (2 NT columns per M block) cap a
+    // tile at 4 M blocks, and 15 x 32 pixels carry less halo than 7 x 64 (1.20 vs 1.33: every role's work scales with it;
+    // measured 4.00 vs 4.09 ms per LIDC step); the cost model below picks.  CCDM_TMA_WT overrides (A/B runs).
+    static const int env_wt = getenv("CCDM_TMA_WT") ? atoi(getenv("CCDM_TMA_WT")) : 0;
+    int widths[2] = {W > 64 ? 64 : W, 0};
+    int n_widths = 1;
+    if (env_wt >= 16 && env_wt <= 64 && W >= 64 && W % env_wt == 0) widths[0] = env_wt;
+    else if (x3 && W >= 64 && W % 32 == 0) widths[n_widths++] = 32;
+    double best_cost = 1e300;
+    bool found = false;
+    for (int wi = 0; wi < n_widths; ++wi) {
+    c.Wt = widths[wi];
     c.P = s2 ? c.Wt + 1 : c.Wt + 2 * pad;
-    if (2 * c.P > 256) return false;  // TMA box limit (8-byte elements)
+    if (2 * c.P > 256) continue;  // TMA box limit (8-byte elements)
     c.magicP = uint32_t(((1u << 20) + c.P - 1) / c.P);
     c.tiles_x = (W + c.Wt - 1) / c.Wt;
     c.w_main_bytes = uint32_t(size_t(Cin) * taps * c.NT * 2 * X);
@@ -742,8 +753,6 @@ bool tm_configure_pl(int B, int H, int W, int C0, int C1, int S0, int S1, int Co
     const size_t slack = (size_t(128 + 2 * pad * c.P + 2 * pad) * 16 + 127) & ~size_t(127);
     const size_t fixed = sizeof(float) * (2 * size_t(Cin) + c.NT + size_t(TM_EPI_WARPS) * CoutP * 2 * ((x3 && up) ? 2 : 1)) + (3 * MAX_STAGES + 5) * 8 + 64 + 16 * size_t(Cin) + 16 + slack +
                          (c.resident ? w_total : 0) + 1024;
-    double best_cost = 1e300;
-    bool found = false;
     for (int R = 1; R <= H && 2 * (R + 2 * pad) <= 256; ++R) {
         const int MB = (R * c.P + 127) / 128;
         const int XA = (x3 && !up) ? 2 : 1;  // accumulator columns per (M block, parity) in units of NT
@@ -787,6 +796,7 @@ bool tm_configure_pl(int B, int H, int W, int C0, int C1, int S0, int S1, int Co
             found = true;
         }
     }
+    }  // tile widths
     (void)n_chunks;
     if (found) {
         best.ips = best.tiles * best.n_cc;
