@@ -295,7 +295,8 @@ __global__ void __launch_bounds__(NTHREADS) conv_ffma_kernel(const ConvP p) {
                 v.z += r.z;
                 v.w += r.w;
             }
-            if (co + 3 < p.Cout) {
+            // (fp32 NHWC logits: a pixel's row of Cout floats is 16-byte aligned only when Cout % 4 == 0 -- K = 5, 19 take the tail path)
+            if (co + 3 < p.Cout && !(p.out_f32 && (p.Cout & 3))) {
                 v = p.out_f32 ? store4<float>(reinterpret_cast<float *>(p.out) + pix * p.Cout + co, v)
                               : store4<T>(reinterpret_cast<T *>(p.out) + act_off<T>(b, hw, p.Cout, pin, co), v);
             } else {  // ragged channel tail (Cout = K classes): fp32 logits only

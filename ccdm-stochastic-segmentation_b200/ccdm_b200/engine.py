@@ -272,12 +272,24 @@ class PackedWeights:
                     self._reserve(p + ":wproj", L.cin * L.cin, (1, L.cin, L.cin)); self._reserve(p + ":bproj", L.cin)
         # bf16 mode folds identity residuals (ResBlock skip = Identity, attention x + proj) into the MMA as a 1x1
         # "skip conv" with identity weights: x * I accumulates exactly in fp32 and the epilogue loses a load
-        for c in sorted({L.cout for blk in arch.blocks for L in blk.layers if L.kind in ("res", "attn")}):
-            self._reserve("ident:%d" % c, 1, (1, c, c))
+        # (the packed layout depends on the N tile of the conv the chunk rides on: a ResBlock's 3x3 conv and an attention
+        # block's 1x1 projection of the same width use different tiles above 128 channels -- one matrix per (width, tile))
+        for L in (L for blk in arch.blocks for L in blk.layers if L.kind in ("res", "attn")):
+            name = self.ident_name(L.cout, 9 if L.kind == "res" else 1)
+            if name not in self.slots:
+                self._reserve(name, 1, (1, L.cout, L.cout))
         K = self.unet.out_channels
         c_head = int(self.unet.channel_mult[0] * mc)
         self._reserve("out:g", c_head); self._reserve("out:be", c_head)
         self._reserve("out:w", 9 * c_head * _ceil(K, 32), (9, c_head, K)); self._reserve("out:b", _ceil(K, 32))
+
+    def _nt(self, cout: int, taps: int) -> int:
+        """N tile of the tensor-core conv with `taps` taps and `cout` output channels (the kernel's own rule)."""
+        return int(_lib.lib().ccdm_conv_tc_nt(int(cout), int(taps), 1 if self.x3 else 0))
+
+    def ident_name(self, c: int, taps: int) -> str:
+        """Slot of the c x c identity matrix packed for the N tile of a conv with `taps` taps (its fused residual chunk)."""
+        return "ident:%d:%d" % (c, self._nt(c, taps))
 
     def addr(self, name) -> int:
         return self.buf.data_ptr() + 4 * self.slots[name][0]
@@ -318,13 +330,15 @@ class PackedWeights:
                     wmax = max(wmax, float(v.abs().max()) * (4.0 if k.endswith(".conv.weight") else 1.0))
             self.shift = int(max(0, min(13, math.floor(math.log2(32768.0 / wmax)))))
 
-        def put(name, t, raw=None):
+        def put(name, t, raw=None, nt=None):
+            # nt: N tile of the conv that reads these weights when it is not the tile of a stand-alone conv of their shape
+            # (the 1x1 skip conv and the identity residual are extra K chunks of a 3x3 conv and follow ITS tile)
             v = self.view(name)
             v.zero_()
             v[:t.numel()].copy_(t.reshape(-1))
             if raw is not None and name in self.slots16:
                 off, n = self.slots16[name]
-                tc = (pack_conv_weight_x3(raw, self.shift) if self.x3 else pack_conv_weight_tc(raw)).reshape(-1)
+                tc = (pack_conv_weight_x3(raw, self.shift, nt) if self.x3 else pack_conv_weight_tc(raw, nt)).reshape(-1)
                 assert tc.numel() == n, (name, tc.numel(), n)
                 self.buf16[off:off + n].copy_(tc)
 
@@ -352,7 +366,7 @@ class PackedWeights:
                     b2 = sd[p + ".out_layers.3.bias"]
                     if L.skip_conv:
                         ws = sd[p + ".skip_connection.weight"]  # [Cout, Cin, 1, 1] -> [Cin][Cout]
-                        put(p + ":ws", ws[:, :, 0, 0].t().contiguous(), ws)
+                        put(p + ":ws", ws[:, :, 0, 0].t().contiguous(), ws, nt=self._nt(L.cout, 9) if self.with_tc else None)
                         b2 = b2 + sd[p + ".skip_connection.bias"]
                     put(p + ":b2", b2)
                     emb_w.append(sd[p + ".emb_layers.1.weight"]); emb_b.append(sd[p + ".emb_layers.1.bias"])
@@ -363,8 +377,8 @@ class PackedWeights:
         put("emb_w", torch.cat(emb_w, 0)); put("emb_b", torch.cat(emb_b, 0))
         for name in self.slots16:
             if name.startswith("ident:"):
-                c = int(name[6:])
-                put(name, torch.zeros(1, device=self.device), torch.eye(c, device=self.device).reshape(c, c, 1, 1))
+                c, nt = (int(v) for v in name.split(":")[1:])
+                put(name, torch.zeros(1, device=self.device), torch.eye(c, device=self.device).reshape(c, c, 1, 1), nt=nt)
         put("out:g", sd["out.0.weight"]); put("out:be", sd["out.0.bias"])
         put("out:w", conv_w(sd["out.2.weight"]), sd["out.2.weight"]); put("out:b", padded(sd["out.2.bias"]))
         self._stamp = stamp
@@ -456,7 +470,7 @@ class Program:
                     if Ly.skip_conv:
                         f.update(_skip=srcs, _ws=p + ":ws")
                     elif self.exact == 0 and (_IDENT_SKIP or self.x3):
-                        f.update(_skip=[srcs[0]], _ws="ident:%d" % Ly.cout)
+                        f.update(_skip=[srcs[0]], _ws=engine.weights.ident_name(Ly.cout, 9))
                     else:
                         f.update(_res=srcs[0])
                     h = emit(_lib.OP_CONV, [h1] + srcs, new(p, Ly.cout, ch, cw), **f)
@@ -469,7 +483,7 @@ class Program:
                                _w=p + ":wqkv", _b=p + ":bqkv")
                     a = emit(_lib.OP_ATTENTION, [qkv], new(p + ":a", C, ch, cw, stat=False), Hin=ch, Win=cw, Hout=ch, Wout=cw,
                              Cout=C, heads=Ly.heads, head_dim=C // Ly.heads, _src=[qkv])
-                    fr = dict(_skip=[x], _ws="ident:%d" % C) if self.exact == 0 and (_IDENT_SKIP or self.x3) else dict(_res=x)
+                    fr = dict(_skip=[x], _ws=engine.weights.ident_name(C, 1)) if self.exact == 0 and (_IDENT_SKIP or self.x3) else dict(_res=x)
                     h = emit(_lib.OP_CONV, [a, x], new(p, C, ch, cw), ksize=1, stride=1, gn=0, silu=0, Hin=ch, Win=cw, Hout=ch,
                              Wout=cw, Cout=C, _src=[a], _w=p + ":wproj", _b=p + ":bproj", **fr)
                     srcs = [h]

@@ -120,8 +120,10 @@ def run_conv(srcs, weight, bias, *, gn=None, silu=False, ksize=3, stride=1, upsa
             keep += [g, be]
             op.gamma, op.beta = g.data_ptr(), be.data_ptr()
     if skip is not None:
-        sw = (pack_conv_weight_x3(skip_w.to(dev), shift).contiguous() if x3 else
-              pack_conv_weight_tc(skip_w.to(dev)).contiguous() if tc else skip_w.to(dev).float()[:, :, 0, 0].t().contiguous())
+        # the fused skip conv is an extra K chunk of THIS conv: its weights follow this conv's N tile
+        nt = int(L.ccdm_conv_tc_nt(Cout, 16 if upsample else ksize * ksize, 1 if x3 else 0))
+        sw = (pack_conv_weight_x3(skip_w.to(dev), shift, nt).contiguous() if x3 else
+              pack_conv_weight_tc(skip_w.to(dev), nt).contiguous() if tc else skip_w.to(dev).float()[:, :, 0, 0].t().contiguous())
         keep.append(sw)
         op.skip0, op.S0 = skip[0].data_ptr(), skip_ch[0]
         if len(skip) > 1:

@@ -85,6 +85,25 @@ def test_x3_second_half_skip_identity_upsample(L):
     _check(out, ([h1], w, b), dict(upsample=True), ostat, "upsample")
 
 
+@pytest.mark.parametrize("B,C,Cs,H,W", [(3, 192, 128, 16, 16), (2, 256, 192, 8, 8), (1, 160, 96, 16, 16)])
+def test_x3_wide_second_half_with_fused_skip(L, B, C, Cs, H, W):
+    """More than 128 output channels (base_channels = 64 nets): the fused skip chunks follow the 3x3 conv's N tile."""
+    from gpu_util import X3, nhwc, run_conv
+    h1, xs = _rand(B, C, H, W, seed=21), _rand(B, Cs, H, W, seed=22)
+    w, b = _rand(C, C, 3, 3, seed=24) / math.sqrt(9 * C), _rand(C, seed=25) * 0.1
+    ws, bs = _rand(C, Cs, 1, 1, seed=26) / math.sqrt(Cs), _rand(C, seed=27) * 0.1
+    gn = (1 + 0.1 * _rand(C, seed=28), 0.1 * _rand(C, seed=29))
+    out, ostat = run_conv([nhwc(h1)], w, b + bs, gn=gn, silu=True, skip=[nhwc(xs)], skip_w=ws, dtype=X3, tc=True)
+    _check(out, ([h1], w, b), dict(gn=gn, silu=True, skip=[xs], skip_w=ws, skip_b=bs), ostat, f"wide res {C} + 1x1 skip {Cs}")
+    x = _rand(B, C, H, W, seed=30) * 3.0
+    eye = torch.eye(C).reshape(C, C, 1, 1)
+    out, ostat = run_conv([nhwc(h1)], w, b, gn=gn, silu=True, skip=[nhwc(x)], skip_w=eye, dtype=X3, tc=True)
+    _check(out, ([h1], w, b), dict(gn=gn, silu=True, res=x), ostat, f"wide res {C} + identity chunk")
+    wp, bp = _rand(C, C, 1, 1, seed=37) / math.sqrt(C), _rand(C, seed=38) * 0.1   # attention proj_out + x
+    out, ostat = run_conv([nhwc(h1)], wp, bp, ksize=1, skip=[nhwc(x)], skip_w=eye, dtype=X3, tc=True)
+    _check(out, ([h1], wp, bp), dict(res=x), ostat, f"wide proj {C} + residual")
+
+
 @pytest.mark.parametrize("B,C,H,W", [(2, 32, 128, 128), (3, 64, 32, 32), (2, 96, 16, 16), (1, 128, 8, 16), (1, 32, 21, 37)])
 def test_x3_downsample_stride2(L, B, C, H, W):
     from gpu_util import X3, nhwc, run_conv

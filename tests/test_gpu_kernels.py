@@ -317,6 +317,27 @@ def test_tc_conv_second_half_with_skip_residual_and_upsample(L):
     _tc_check(out, ref_conv([h1], w, b, upsample=True), ostat)
 
 
+@pytest.mark.parametrize("B,C,Cs,H,W", [(3, 192, 128, 16, 16), (2, 256, 192, 8, 8), (1, 160, 96, 16, 16)])
+def test_tc_wide_second_half_with_fused_skip(L, B, C, Cs, H, W):
+    """More than 128 output channels (base_channels = 64 nets): three to five N tiles per sample, and the fused 1x1 skip
+    conv / identity residual chunk follows the 3x3 conv's tile, not the (wider) tile of a stand-alone 1x1 conv."""
+    from gpu_util import nhwc, ref_conv, run_conv
+    bf = torch.bfloat16
+    h1, xs = _bf(_rand(B, C, H, W, seed=21)), _bf(_rand(B, Cs, H, W, seed=22))
+    w, b = _bf(_rand(C, C, 3, 3, seed=24) / math.sqrt(9 * C)), _rand(C, seed=25) * 0.1
+    ws, bs = _bf(_rand(C, Cs, 1, 1, seed=26) / math.sqrt(Cs)), _rand(C, seed=27) * 0.1
+    gn = (1 + 0.1 * _rand(C, seed=28), 0.1 * _rand(C, seed=29))
+    out, ostat = run_conv([nhwc(h1, bf)], w, b + bs, gn=gn, silu=True, skip=[nhwc(xs, bf)], skip_w=ws, dtype=bf, tc=True)
+    _tc_check(out, ref_conv([h1], w, b, gn=gn, silu=True, skip=[xs], skip_w=ws, skip_b=bs), ostat)
+    x = _bf(_rand(B, C, H, W, seed=30))
+    eye = torch.eye(C).reshape(C, C, 1, 1)
+    out, ostat = run_conv([nhwc(h1, bf)], w, b, gn=gn, silu=True, skip=[nhwc(x, bf)], skip_w=eye, dtype=bf, tc=True)
+    _tc_check(out, ref_conv([h1], w, b, gn=gn, silu=True, res=x), ostat)
+    wp, bp = _bf(_rand(C, C, 1, 1, seed=37) / math.sqrt(C)), _rand(C, seed=38) * 0.1   # attention proj_out + x
+    out, ostat = run_conv([nhwc(h1, bf)], wp, bp, ksize=1, skip=[nhwc(x, bf)], skip_w=eye, dtype=bf, tc=True)
+    _tc_check(out, ref_conv([h1], wp, bp, res=x), ostat)
+
+
 @pytest.mark.parametrize("B,C,H,W", [(2, 32, 128, 128), (3, 64, 32, 32), (2, 96, 16, 16), (1, 128, 8, 16), (1, 32, 21, 37)])
 def test_tc_conv_downsample_stride2(L, B, C, H, W):
     """Downsample (unet.py:136-139) on the TMA-fed tensor-core kernel: four parity sub-images gathered by

@@ -329,6 +329,18 @@ def test_every_conv_lands_on_the_tensor_core_kernel():
                     op = ops[i]
                     if op.kind == _lib.OP_CONV:
                         assert L.ccdm_conv_uses_tc(ctypes.byref(op)) == 1 and op.exact == 0
+                        if o.get("_ws"):
+                            # a fused skip chunk (1x1 skip conv / identity residual) is packed for the N tile of the conv it
+                            # rides on, not for the tile a stand-alone 1x1 conv of its shape would get (they differ above 128
+                            # output channels: found by tests/test_gpu_variants.py at base_channels = 64)
+                            cfg = (ctypes.c_int32 * 16)()
+                            assert L.ccdm_conv_tc_config(ctypes.byref(op), cfg) == 0
+                            taps = 9 if op.ksize == 3 else 1
+                            assert cfg[5] == L.ccdm_conv_tc_nt(op.Cout, taps, 1 if prec == "exact" else 0)
+                            if o["_ws"].startswith("ident:"):
+                                assert int(o["_ws"].split(":")[2]) == cfg[5], (o["_ws"], cfg[5])
+                            else:
+                                assert taps == 9  # ResBlock skip convs are always fused into the block's second 3x3 conv
                         for si, sten in enumerate(o.get("_src", [])[:2]):
                             slots = getattr(op, "st_slots%d" % si)
                             if o.get("gn") and sten.stat_layout is not None:
