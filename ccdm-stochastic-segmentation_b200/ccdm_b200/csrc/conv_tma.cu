@@ -782,6 +782,10 @@ bool tm_configure_pl(int B, int H, int W, int C0, int C1, int S0, int S1, int Co
         // single accumulator buffer: the epilogue is not overlapped with the next item's MMAs -- costly for the upsampling convs,
         // whose epilogue drains four parity accumulators per M block (measured: ~5.7 us per item of serialised hand-offs)
         if (2 * nsub * MB * c.NT * XA > 512) cost *= (up && x3) ? 1.6 : 1.15;
+        // fp16x2, full-resolution level, items of two K chunks and no skip chunks (32->32, 32->K): measured per op class, the
+        // 64-wide tile wins there (LIDC 130 -> 115 us, 99 -> 90 us; Cityscapes 111 -> 108) although it loses on every other class
+        // of that level (+9 .. +18 us) and on two-chunk items of the smaller levels (36 -> 43 us at 128x256, B = 8)
+        if (x3 && !up && !s2 && n_chunks == 2 && Sk == 0 && (long long)B * H * W >= (1ll << 20) && c.Wt == 32) cost *= 1.3;
         if (env_r > 0 && W >= 64 && H >= 64) cost = (R == env_r) ? 0.0 : 1e290;
         if (cost < best_cost) {
             best_cost = cost;
@@ -797,7 +801,6 @@ bool tm_configure_pl(int B, int H, int W, int C0, int C1, int S0, int S1, int Co
         }
     }
     }  // tile widths
-    (void)n_chunks;
     if (found) {
         best.ips = best.tiles * best.n_cc;
         best.slots = 1;
