@@ -28,6 +28,8 @@
 // B x heads x query tiles < 2 x 148 (Cityscapes B=8), or a second query tile per CTA.)
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace ccdm {
@@ -57,6 +59,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float *v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+        "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+        "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+        "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+        "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 struct AtP {
     const __nv_bfloat16 *qkv;  // [B][3C/8][T][8]
     __nv_bfloat16 *out;        // [B][C/8][T][8]
@@ -69,7 +87,7 @@ struct AtP {
 // adjacent), both products are three fp16 MMAs (hi*lo + lo*hi + hi*hi), the softmax is the same fp32 arithmetic, and P
 // is split into hi + lo before the P V product -- fp32-grade attention on the tensor cores.
 template <int NK, bool X3>
-__global__ void __launch_bounds__(AT_QT, 3) attention_tc_kernel(const AtP p) {
+__global__ void __launch_bounds__(AT_QT, X3 ? 2 : 3) attention_tc_kernel(const AtP p) {  // (fp16x2: 80 KB of shared memory per CTA -- two per SM anyway)
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int X = X3 ? 2 : 1;
     constexpr uint32_t Q_BYTES = X * AT_PLANES * AT_QT * 16;  // 8 KB
@@ -144,103 +162,153 @@ __global__ void __launch_bounds__(AT_QT, 3) attention_tc_kernel(const AtP p) {
         }
     };
 
-    float o[AT_D];
-#pragma unroll
-    for (int d = 0; d < AT_D; ++d) o[d] = 0.f;
+    // O accumulates in TMEM over all key tiles (the P V MMAs of tile t add to it) -- it is read back once, at the end.  The
+    // exponentials are taken against a REFERENCE maximum m that may lag the true running maximum of the row by up to LAG
+    // (log2 units: p <= 2^LAG, far inside bf16 / fp16 range; softmax is shift-invariant, so nothing else changes); only
+    // when a tile exceeds it by more does the row rescale what it has accumulated (l, and its O lane through
+    // tcgen05.ld / st) -- after the first tile that is rare.  So per tile a thread waits ONCE (for S), and the issuing
+    // thread queues P V(t) and S(t+1) back to back.  (Before: o = o * corr + O_tile in registers every tile -- a second
+    // commit -> mbarrier -> tcgen05.ld round trip and 32 FMAs per tile.)
+    // fp16x2: the tensor core truncates its accumulator on every accumulating MMA (tests/test_gpu_exact.py), so an O that
+    // collects all 12 x n_tiles MMAs in TMEM drifts (8e-6 of the output's scale at T = 2048); every FLUSH tiles the row moves
+    // what TMEM holds into fp32 registers (round to nearest) and the next P V starts the accumulator afresh.
+    constexpr float LAG = 8.0f;
+    constexpr int FLUSH = 8;
     float m = -INFINITY, l = 0.f;
     const float c = p.scale_log2;
+    float o[AT_D];
+    if constexpr (X3) {
+#pragma unroll
+        for (int d = 0; d < AT_D; ++d) o[d] = 0.f;
+    }
+
+    auto issue_s = [&](int t) {  // thread 0: S(t) = Q K(t)^T into the S columns
+        const int buf = t & 1;
+        mbar_wait(kv_full + buf, uint32_t(t >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t k_lo = (smem_u32(sK + buf * KV_BYTES) >> 4) | (uint32_t(X * NK) << 16);
+#pragma unroll
+        for (int j = 0; j < AT_D / 16; ++j)
+            mma(tmem_s, q_lo + uint32_t(j * 2 * X * AT_QT), desc_hi, uint32_t(AT_QT), k_lo + uint32_t(j * 2 * X * NK), desc_hi, uint32_t(NK), p.idesc_s,
+                j > 0 ? 1u : 0u);
+        umma_commit(s_done);
+    };
+    if (tid == 0) {
+        if (n_tiles > 1) load_kv(1, 1, 0u);
+        issue_s(0);
+    }
 
     for (int t = 0; t < n_tiles; ++t) {
         const int buf = t & 1;
         const int nk = min(NK, T - t * NK);
-        if (tid == 0) {
-            if (t + 1 < n_tiles) load_kv(t + 1, buf ^ 1, 0u);  // that buffer's last reader (P V of tile t-1) has completed
-            mbar_wait(kv_full + buf, uint32_t(t >> 1) & 1u);
-            tc_fence_after();
-            const uint32_t k_lo = (smem_u32(sK + buf * KV_BYTES) >> 4) | (uint32_t(X * NK) << 16);
-#pragma unroll
-            for (int j = 0; j < AT_D / 16; ++j)
-                mma(tmem_s, q_lo + uint32_t(j * 2 * X * AT_QT), desc_hi, uint32_t(AT_QT), k_lo + uint32_t(j * 2 * X * NK), desc_hi, uint32_t(NK), p.idesc_s,
-                    j > 0 ? 1u : 0u);
-            umma_commit(s_done);
-        }
-        mbar_wait(s_done, uint32_t(t) & 1u);
+        mbar_wait(s_done, uint32_t(t) & 1u);  // S(t) is complete -- and with it every MMA issued before it, P V(t-1) included
         tc_fence_after();
-        // pass 1: row maximum of the tile
-        // (four independent partial maxima / sums: a single running value would be a 128-long dependent chain per
-        // tile, and with two CTAs of four warps per SM there is nothing to hide its latency behind)
-        float tm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        if (tid == 0 && t >= 1 && t + 1 < n_tiles) load_kv(t + 1, buf ^ 1, 0u);  // that buffer's readers (S, P V of tile t-1) have completed
+        const bool flushed = X3 && t > 0 && (t % FLUSH) == 0;  // (uniform) O is quiescent here: P V(t-1) has completed, P V(t) is not issued yet
+        if (flushed) {
+            float ot[32];
+            tmem_ld32(tmem_o + trow, ot);
 #pragma unroll
-        for (int c0 = 0; c0 < NK; c0 += 32) {
-            if (c0 < nk) {
-                float s[32];
-                tmem_ld32(tmem_s + trow + uint32_t(c0), s);
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (c0 + i < nk) tm[i & 3] = fmaxf(tm[i & 3], s[i]);
-            }
+            for (int d = 0; d < AT_D; ++d) o[d] += ot[d];
         }
-        const float tmax = fmaxf(fmaxf(tm[0], tm[1]), fmaxf(tm[2], tm[3]));
-        const float m_new = fmaxf(m, tmax);
-        const float corr = ex2_approx((m - m_new) * c);  // m = -inf on the first tile -> 0
-        const float mc = m_new * c;
-        float rs[4] = {0.f, 0.f, 0.f, 0.f};
-        // pass 2: P = exp2(S*c - m*c) as bf16 (fp16x2: hi + lo), K-major rows for the P V product
+        // one tile of the online softmax; FULL: all NK keys are real (every tile but possibly the last) -- no per-element predicates
+        auto softmax_tile = [&](auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
+            // pass 1: row maximum of the tile
+            // (four independent partial maxima / sums: a single running value would be a 128-long dependent chain per
+            // tile, and with two CTAs of four warps per SM there is nothing to hide its latency behind)
+            float tm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int c0 = 0; c0 < NK; c0 += 32) {
-            uint32_t pk[16], pl[16];
-            if (c0 < nk) {
-                float s[32];
-                tmem_ld32(tmem_s + trow + uint32_t(c0), s);
+            for (int c0 = 0; c0 < NK; c0 += 32) {
+                if (FULL || c0 < nk) {
+                    float s[32];
+                    tmem_ld32(tmem_s + trow + uint32_t(c0), s);
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float p0 = (c0 + i < nk) ? ex2_approx(fmaf(s[i], c, -mc)) : 0.f;
-                    float p1 = (c0 + i + 1 < nk) ? ex2_approx(fmaf(s[i + 1], c, -mc)) : 0.f;
-                    if (X3) {
-                        split_f16x2(p0, p1, pk[i / 2], pl[i / 2]);  // hi + lo reproduces p to 2^-23: the sum the MMA sees is the fp32 sum
-                        rs[(i >> 1) & 3] += p0 + p1;
-                    } else {
-                        pk[i / 2] = pack_bf16(p0, p1);
-                        const float2 f = unpack_bf16(pk[i / 2]);  // the sum of what the MMA will actually see
-                        rs[(i >> 1) & 3] += f.x + f.y;
-                    }
+                    for (int i = 0; i < 32; ++i)
+                        if (FULL || c0 + i < nk) tm[i & 3] = fmaxf(tm[i & 3], s[i]);
                 }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) pk[i] = 0u, pl[i] = 0u;
             }
+            const float tmax = fmaxf(fmaxf(tm[0], tm[1]), fmaxf(tm[2], tm[3]));
+            const bool grow = (tmax - m) * c > LAG;  // always on the first tile (m = -inf)
+            if (__any_sync(0xffffffffu, grow)) {     // warp-uniform: tcgen05.ld / st are warp-wide instructions
+                const float m_new = grow ? tmax : m;
+                if (t > 0) {
+                    const float corr = ex2_approx((m - m_new) * c);  // 1 on the lanes that keep their maximum
+                    if (!flushed) {  // (after a flush TMEM holds nothing that counts: the next P V overwrites it)
+                        float ot[32];
+                        tmem_ld32(tmem_o + trow, ot);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {  // key planes c0/8 .. c0/8+3, this thread's row
-                *reinterpret_cast<uint4 *>(sP + (size_t((c0 / 8 + g) * X) * AT_QT + tid) * 16) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-                if (X3)
-                    *reinterpret_cast<uint4 *>(sP + (size_t((c0 / 8 + g) * X + 1) * AT_QT + tid) * 16) = make_uint4(pl[4 * g], pl[4 * g + 1], pl[4 * g + 2], pl[4 * g + 3]);
+                        for (int d = 0; d < AT_D; ++d) ot[d] *= corr;
+                        tmem_st32(tmem_o + trow, ot);
+                    }
+                    if constexpr (X3) {
+#pragma unroll
+                        for (int d = 0; d < AT_D; ++d) o[d] *= corr;
+                    }
+                    l *= corr;
+                }
+                m = m_new;
             }
-        }
-        l = l * corr + ((rs[0] + rs[1]) + (rs[2] + rs[3]));
-        m = m_new;
+            const float mc = m * c;
+            float rs[4] = {0.f, 0.f, 0.f, 0.f};
+            // pass 2: P = exp2(S*c - m*c) as bf16 (fp16x2: hi + lo), K-major rows for the P V product
+#pragma unroll
+            for (int c0 = 0; c0 < NK; c0 += 32) {
+                uint32_t pk[16], pl[16];
+                if (FULL || c0 < nk) {
+                    float s[32];
+                    tmem_ld32(tmem_s + trow + uint32_t(c0), s);
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        float p0 = (FULL || c0 + i < nk) ? ex2_approx(fmaf(s[i], c, -mc)) : 0.f;
+                        float p1 = (FULL || c0 + i + 1 < nk) ? ex2_approx(fmaf(s[i + 1], c, -mc)) : 0.f;
+                        if (X3) {
+                            split_f16x2(p0, p1, pk[i / 2], pl[i / 2]);  // hi + lo reproduces p to 2^-23: the sum the MMA sees is the fp32 sum
+                            rs[(i >> 1) & 3] += p0 + p1;
+                        } else {
+                            pk[i / 2] = pack_bf16(p0, p1);
+                            const float2 f = unpack_bf16(pk[i / 2]);  // the sum of what the MMA will actually see
+                            rs[(i >> 1) & 3] += f.x + f.y;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) pk[i] = 0u, pl[i] = 0u;
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {  // key planes c0/8 .. c0/8+3, this thread's row
+                    *reinterpret_cast<uint4 *>(sP + (size_t((c0 / 8 + g) * X) * AT_QT + tid) * 16) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+                    if (X3)
+                        *reinterpret_cast<uint4 *>(sP + (size_t((c0 / 8 + g) * X + 1) * AT_QT + tid) * 16) = make_uint4(pl[4 * g], pl[4 * g + 1], pl[4 * g + 2], pl[4 * g + 3]);
+                }
+            }
+            l += (rs[0] + rs[1]) + (rs[2] + rs[3]);
+        };
+        if (nk == NK) softmax_tile(std::true_type{});
+        else softmax_tile(std::false_type{});
         fence_proxy_async();
         tc_fence_before();
-        __syncthreads();  // P complete and visible to the tensor core; every thread is done reading S
+        __syncthreads();  // P (and a rescaled O) complete and visible to the tensor core; every thread is done reading S
         if (tid == 0) {
             tc_fence_after();
             const uint32_t v_lo = (smem_u32(sV + buf * KV_BYTES) >> 4) | (8u << 16);  // LBO = 128 B between groups of 8 keys
 #pragma unroll
             for (int j = 0; j < NK / 16; ++j)
-                mma(tmem_o, p_lo + uint32_t(j * 2 * X * AT_QT), desc_hi, uint32_t(AT_QT), v_lo + uint32_t(j * 16), v_hi, uint32_t(NK), p.idesc_pv, j > 0 ? 1u : 0u);
-            umma_commit(o_done);
+                mma(tmem_o, p_lo + uint32_t(j * 2 * X * AT_QT), desc_hi, uint32_t(AT_QT), v_lo + uint32_t(j * 16), v_hi, uint32_t(NK), p.idesc_pv,
+                    ((t > 0 && !flushed) || j > 0) ? 1u : 0u);
+            // S(t+1) right behind it: it overwrites S, which every thread finished reading before the barrier above; P is
+            // rewritten only after S(t+1) -- and so P V(t) -- has completed
+            if (t + 1 < n_tiles) issue_s(t + 1);
+            else umma_commit(o_done);
         }
-        mbar_wait(o_done, uint32_t(t) & 1u);
-        tc_fence_after();
-        {
-            float ot[32];
-            tmem_ld32(tmem_o + trow, ot);
+    }
+    mbar_wait(o_done, 0u);
+    tc_fence_after();
+    {
+        float ot[32];
+        tmem_ld32(tmem_o + trow, ot);
 #pragma unroll
-            for (int d = 0; d < AT_D; ++d) o[d] = fmaf(o[d], corr, ot[d]);
-        }
-        // No CTA barrier here: the next S MMA overwrites S, which every thread finished reading before the
-        // barrier above; the next P V overwrites O only after the next iteration's barrier, which every
-        // thread reaches after this read; the K/V buffer refilled next was last read by MMAs that completed.
-        tc_fence_before();
+        for (int d = 0; d < AT_D; ++d) o[d] = X3 ? o[d] + ot[d] : ot[d];
     }
 
     if (tid < nq) {

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import UNET_PARAMS
+from conftest import DINO, UNET_PARAMS
 from test_gpu_chain import (BF16_LABEL_FRAC, BF16_X0_MAX, BF16_X0_MEAN, PARITY_MODES, X0_TOL, _onehot, _report,
                             _teacher_forced_check)
 
@@ -23,7 +23,12 @@ VARIANTS = {
     "lidc_48x80": (32, (1, 1, 2, 3, 4), [32, 16, 8], 1, 48, 80, 2, 2),   # 3x5 maps at the bottom: attention over 15 and 60 tokens
     "head_dim_64": (64, (1, 2), [1, 2], 1, 32, 32, 3, 2),                # num_head_channels = 64 (FFMA attention only: 'fp32')
 }
+VARIANTS.update({
+    "size512_mult": (64, (0.5, 1, 1, 2, 2, 4, 4), [32, 16, 8], 1, 128, 128, 2, 1),  # seven levels, 2x2 maps at the bottom
+    "cs_vitb_768": (32, (1, 1, 2, 2, 4, 4), [32, 16, 8], 3, 64, 128, 20, 2),         # a 768-channel feature condition (dino_vitb8)
+})
 EXTRA = {"head_dim_64": dict(num_head_channels=64)}
+FCE = {"cs_vitb_768": dict(DINO, model="dino_vitb8", channels=768)}
 ONLY = {"head_dim_64": ("fp32",)}
 
 
@@ -33,9 +38,10 @@ def _variant(tag):
     base, mult, att, C_img, H, W, K, B = VARIANTS[tag]
     p = dict(UNET_PARAMS, base_channels=base, channel_mult=mult, attention_resolutions=att, **EXTRA.get(tag, {}))
     m = models.build_model(50, "cosine", {"s": 0.008}, [(C_img, H, W), (K, H, W)], (C_img, H, W), "unet_openai", p,
-                           "datasets.lidc", "majority", None).eval()
+                           "datasets.lidc", "majority", FCE.get(tag)).eval()
     fill_synthetic_(m.unet, 3)
-    image, _, labels = synthetic_inputs(B, C_img, H, W, K)
+    image, feat, labels = synthetic_inputs(B, C_img, H, W, K, FCE[tag]["channels"] if tag in FCE else 0)
+    m.test_feat = feat
     return m.cuda(), image, labels, (B, C_img, H, W, K)
 
 
@@ -48,9 +54,11 @@ def test_unet_variant_vs_oracle(cuda_device, tag, prec):
     m, image, labels, (B, C_img, H, W, K) = _variant(tag)
     m.unet.precision = prec
     t = torch.full((B,), 23.0)
-    ref = unet_ref.unet_forward({k: v.cpu() for k, v in m.unet.state_dict().items()}, _onehot(labels, K), image, None, t,
-                                head_channels=EXTRA.get(tag, {}).get("num_head_channels", 32))
-    got = m.unet(_onehot(labels, K).cuda(), image.cuda(), None, t.cuda())["diffusion_out"].cpu()
+    feat = m.test_feat
+    ref = unet_ref.unet_forward({k: v.cpu() for k, v in m.unet.state_dict().items()}, _onehot(labels, K), image, feat, t,
+                                head_channels=EXTRA.get(tag, {}).get("num_head_channels", 32),
+                                feature_condition_idx=FCE[tag]["target_layer"] if tag in FCE else None)
+    got = m.unet(_onehot(labels, K).cuda(), image.cuda(), feat.cuda() if feat is not None else None, t.cuda())["diffusion_out"].cpu()
     err = (got - ref).abs()
     _report(f"variant_{prec}_{tag}", max_abs_err=err.max(), mean_abs_err=err.mean())
     if prec == "bf16":
