@@ -11,9 +11,11 @@
 //     v    : "MN-major, no swizzle" (N = channels contiguous inside a 16-byte row, K = keys 16 B apart,
 //                                    LBO = 128 B between groups of 8 keys, SBO = plane stride)
 // Per key tile:  S = Q K^T (tcgen05.mma, fp32 in TMEM)  ->  every thread owns one query row: tcgen05.ld,
-// running max / sum, P = exp2((S - m) * log2(e)/sqrt(32)) as bf16 into shared memory (K-major A operand)
-// ->  O_tile = P V (tcgen05.mma)  ->  o = o * corr + O_tile in registers.  Several CTAs are resident per
-// SM (TMEM: 256 of 512 columns each at NK = 128), so one CTA's softmax overlaps another's MMAs and loads.
+// tile max / running sum, P = exp2((S - m) * log2(e)/sqrt(32)) as bf16 into shared memory (K-major A operand)
+// ->  O += P V (tcgen05.mma accumulating in TMEM over ALL tiles; m is a reference maximum that may lag the row's
+// true maximum by 2^8, a row rescales l and its TMEM lane only when a tile exceeds it by more -- see the main loop).
+// Several CTAs are resident per SM (TMEM: 256 of 512 columns each at NK = 128), so one CTA's softmax overlaps
+// another's MMAs and loads.
 //
 // Output: [B][C/8][T][8] bf16, channel(h, d) = h*32 + d (unet.py:360).
 //
