@@ -1,5 +1,5 @@
 // QKVAttentionLegacy (reference unet.py:343-360) on the 5th-generation tensor cores, for bf16 activations
-// in the plane-major layout and head_dim = 32 (every shipped configuration: num_head_channels = 32).
+// in the plane-major layout and head_dim = 32 (every shipped configuration: num_head_channels = 32) or 64.
 //
 //   softmax((q*s)(k*s)^T) v,  s = 32^-1/4, per (sample, head), never materialising the [T,T] scores.
 //
@@ -37,9 +37,8 @@
 namespace ccdm {
 namespace {
 
-constexpr int AT_D = 32;       // head_dim
+// head_dim D: 32 (every shipped UNet configuration) or 64 (ViT-S heads, the DINO condition encoder)
 constexpr int AT_QT = 128;     // queries per CTA = threads = MMA M
-constexpr int AT_PLANES = AT_D / 8;
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -88,10 +87,11 @@ struct AtP {
 // X3: fp16x2 operands (CCDM_DT_F16X2; the "exact" tensor-core mode).  Every plane of q, k, v and P exists twice (hi, lo,
 // adjacent), both products are three fp16 MMAs (hi*lo + lo*hi + hi*hi), the softmax is the same fp32 arithmetic, and P
 // is split into hi + lo before the P V product -- fp32-grade attention on the tensor cores.
-template <int NK, bool X3>
-__global__ void __launch_bounds__(AT_QT, X3 ? 2 : 3) attention_tc_kernel(const AtP p) {  // (fp16x2: 80 KB of shared memory per CTA -- two per SM anyway)
+template <int NK, bool X3, int D = 32>
+__global__ void __launch_bounds__(AT_QT, D > 32 ? (X3 ? 1 : 2) : (X3 ? 2 : 3)) attention_tc_kernel(const AtP p) {  // (fp16x2: 80 KB of shared memory per CTA -- two per SM anyway)
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int X = X3 ? 2 : 1;
+    constexpr int AT_D = D, AT_PLANES = D / 8;
     constexpr uint32_t Q_BYTES = X * AT_PLANES * AT_QT * 16;  // 8 KB
     constexpr uint32_t KV_BYTES = X * AT_PLANES * NK * 16;    // per tensor per buffer
     constexpr uint32_t P_BYTES = X * (NK / 8) * AT_QT * 16;
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(AT_QT, X3 ? 2 : 3) attention_tc_kernel(const A
     uint64_t *bars = reinterpret_cast<uint64_t *>(sP + P_BYTES);
     uint64_t *kv_full = bars, *s_done = bars + 2, *o_done = bars + 3;
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 4);
-    constexpr uint32_t TMEM_COLS = NK + 32 <= 64 ? 64 : (NK + 32 <= 128 ? 128 : 256);
+    constexpr uint32_t TMEM_COLS = NK + D <= 64 ? 64 : (NK + D <= 128 ? 128 : 256);
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int qt = blockIdx.x % p.q_tiles, bh = blockIdx.x / p.q_tiles;
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(AT_QT, X3 ? 2 : 3) attention_tc_kernel(const A
     const int nq = min(AT_QT, T - q0);
     const int n_tiles = (T + NK - 1) / NK;
     const int planes3 = p.heads * 3 * AT_PLANES;  // planes of the qkv tensor
-    // plane g of (which = 0 q | 1 k | 2 v) of this head: channel h*96 + which*32 + 8g
+    // plane g of (which = 0 q | 1 k | 2 v) of this head: channel h*3D + which*D + 8g
     // (fp16x2: tensor plane 2*that + part, part = 0 hi | 1 lo; g then counts (group, part) pairs)
     auto plane_ptr = [&](int which, int g) { return p.qkv + ((size_t(b) * planes3 * X + (h * 3 * AT_PLANES + which * AT_PLANES) * X + g) * T) * 8; };
 
@@ -133,6 +133,14 @@ __global__ void __launch_bounds__(AT_QT, X3 ? 2 : 3) attention_tc_kernel(const A
     pdl_launch_dependents();
     pdl_wait();  // qkv is written by the previous kernel of the step
     const uint32_t trow = uint32_t(warp * 32) << 16;  // this warp's TMEM lane quarter
+    auto ld_o = [&](float *dst) {
+#pragma unroll
+        for (int d0 = 0; d0 < AT_D; d0 += 32) tmem_ld32(tmem_o + trow + uint32_t(d0), dst + d0);
+    };
+    auto st_o = [&](const float *src) {
+#pragma unroll
+        for (int d0 = 0; d0 < AT_D; d0 += 32) tmem_st32(tmem_o + trow + uint32_t(d0), src + d0);
+    };
 
     auto load_kv = [&](int t, int buf, uint32_t extra_bytes) {  // thread 0
         const int k0 = t * NK, nk = min(NK, T - k0);
@@ -208,8 +216,8 @@ __global__ void __launch_bounds__(AT_QT, X3 ? 2 : 3) attention_tc_kernel(const A
         if (tid == 0 && t >= 1 && t + 1 < n_tiles) load_kv(t + 1, buf ^ 1, 0u);  // that buffer's readers (S, P V of tile t-1) have completed
         const bool flushed = X3 && t > 0 && (t % FLUSH) == 0;  // (uniform) O is quiescent here: P V(t-1) has completed, P V(t) is not issued yet
         if (flushed) {
-            float ot[32];
-            tmem_ld32(tmem_o + trow, ot);
+            float ot[AT_D];
+            ld_o(ot);
 #pragma unroll
             for (int d = 0; d < AT_D; ++d) o[d] += ot[d];
         }
@@ -237,11 +245,11 @@ __global__ void __launch_bounds__(AT_QT, X3 ? 2 : 3) attention_tc_kernel(const A
                 if (t > 0) {
                     const float corr = ex2_approx((m - m_new) * c);  // 1 on the lanes that keep their maximum
                     if (!flushed) {  // (after a flush TMEM holds nothing that counts: the next P V overwrites it)
-                        float ot[32];
-                        tmem_ld32(tmem_o + trow, ot);
+                        float ot[AT_D];
+                        ld_o(ot);
 #pragma unroll
                         for (int d = 0; d < AT_D; ++d) ot[d] *= corr;
-                        tmem_st32(tmem_o + trow, ot);
+                        st_o(ot);
                     }
                     if constexpr (X3) {
 #pragma unroll
@@ -307,8 +315,8 @@ __global__ void __launch_bounds__(AT_QT, X3 ? 2 : 3) attention_tc_kernel(const A
     mbar_wait(o_done, 0u);
     tc_fence_after();
     {
-        float ot[32];
-        tmem_ld32(tmem_o + trow, ot);
+        float ot[AT_D];
+        ld_o(ot);
 #pragma unroll
         for (int d = 0; d < AT_D; ++d) o[d] = X3 ? o[d] + ot[d] : ot[d];
     }
@@ -338,15 +346,16 @@ __global__ void __launch_bounds__(AT_QT, X3 ? 2 : 3) attention_tc_kernel(const A
     }
 }
 
-template <int NK, bool X3>
+template <int NK, bool X3, int D = 32>
 int launch_nk(const AtP &p, int grid, cudaStream_t s) {
+    constexpr int AT_PLANES = D / 8;
     constexpr size_t smem = (X3 ? 2 : 1) * (AT_PLANES * AT_QT * 16 + 4 * AT_PLANES * NK * 16 + (NK / 8) * AT_QT * 16) + 64;
     static bool attr_done = false;
     if (!attr_done) {
-        CCDM_CUDA(cudaFuncSetAttribute(attention_tc_kernel<NK, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        CCDM_CUDA(cudaFuncSetAttribute(attention_tc_kernel<NK, X3, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         attr_done = true;
     }
-    CCDM_CUDA(launch_pdl(attention_tc_kernel<NK, X3>, dim3(grid), dim3(AT_QT), smem, s, p));
+    CCDM_CUDA(launch_pdl(attention_tc_kernel<NK, X3, D>, dim3(grid), dim3(AT_QT), smem, s, p));
     CCDM_LAUNCH_CHECK("attention_tc_kernel");
     return 0;
 }
@@ -354,12 +363,13 @@ int launch_nk(const AtP &p, int grid, cudaStream_t s) {
 }  // namespace
 
 bool attention_tc_supported(const ccdm_op &op) {
-    return (op.dtype == CCDM_DT_BF16 || op.dtype == CCDM_DT_F16X2) && op.head_dim == AT_D && !op.exact && op.heads > 0;
+    return (op.dtype == CCDM_DT_BF16 || op.dtype == CCDM_DT_F16X2) && (op.head_dim == 32 || op.head_dim == 64) && !op.exact && op.heads > 0;
 }
 
 int launch_attention_tc(const ccdm_op &op, cudaStream_t s) {
     const int T = op.Hin * op.Win;
-    if (op.C0 != op.heads * AT_D * 3) CCDM_FAIL(-2, "attention_tc: qkv channels %d != 3*heads*32", op.C0);
+    const int AT_D = op.head_dim;
+    if (op.C0 != op.heads * AT_D * 3) CCDM_FAIL(-2, "attention_tc: qkv channels %d != 3*heads*%d", op.C0, AT_D);
     AtP p{};
     p.qkv = (const __nv_bfloat16 *)op.src0;
     p.out = (__nv_bfloat16 *)op.out;
@@ -377,6 +387,7 @@ int launch_attention_tc(const ccdm_op &op, cudaStream_t s) {
     p.idesc_pv = base | (uint32_t(AT_D >> 3) << 17) | (1u << 16);
     const int grid = op.B * op.heads * p.q_tiles;
     if (!p.qkv || !p.out || T <= 0 || grid <= 0) CCDM_FAIL(-2, "attention_tc: missing tensors");
+    if (AT_D == 64) return x3 ? launch_nk<64, true, 64>(p, grid, s) : launch_nk<64, false, 64>(p, grid, s);  // one CTA per SM (128 / 72 KB)
     if (x3) return launch_nk<64, true>(p, grid, s);  // 80 KB of shared memory per CTA at NK = 64: two CTAs per SM
     return NK == 64 ? launch_nk<64, false>(p, grid, s) : launch_nk<128, false>(p, grid, s);
 }

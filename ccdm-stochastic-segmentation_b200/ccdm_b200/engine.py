@@ -482,10 +482,9 @@ class Program:
                                Hin=ch, Win=cw, Hout=ch, Wout=cw, Cout=3 * C, _src=[x], _g=p + ":g", _be=p + ":be",
                                _w=p + ":wqkv", _b=p + ":bqkv")
                     hd = C // Ly.heads
-                    if hd * Ly.heads != C or hd not in ((32,) if self.exact == 0 else (32, 64)):
+                    if hd * Ly.heads != C or hd not in (32, 64):
                         # (every shipped configuration has num_head_channels = 32, params_eval.yml:56-63)
-                        raise NotImplementedError(f"{p}: attention head_dim {C}/{Ly.heads} is not implemented by the B200 sampler in "
-                                                  f"precision '{engine.precision}' (tensor-core modes: 32; 'fp32': 32 or 64)")
+                        raise NotImplementedError(f"{p}: attention head_dim {C}/{Ly.heads} is not implemented by the B200 sampler (32 or 64)")
                     a = emit(_lib.OP_ATTENTION, [qkv], new(p + ":a", C, ch, cw, stat=False), Hin=ch, Win=cw, Hout=ch, Wout=cw,
                              Cout=C, heads=Ly.heads, head_dim=C // Ly.heads, _src=[qkv])
                     fr = dict(_skip=[x], _ws=engine.weights.ident_name(C, 1)) if self.exact == 0 and (_IDENT_SKIP or self.x3) else dict(_res=x)

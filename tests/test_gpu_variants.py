@@ -21,7 +21,7 @@ VARIANTS = {
     "k19_odd_batch": (32, (1, 2, 2), [1, 4], 3, 64, 64, 19, 5),  # attention on the full-resolution map (4096 tokens), 64-channel first level
     "deep_lidc_b1": (32, (1, 1, 2, 3, 4), [32, 16, 8], 1, 128, 128, 2, 1),
     "lidc_48x80": (32, (1, 1, 2, 3, 4), [32, 16, 8], 1, 48, 80, 2, 2),   # 3x5 maps at the bottom: attention over 15 and 60 tokens
-    "head_dim_64": (64, (1, 2), [1, 2], 1, 32, 32, 3, 2),                # num_head_channels = 64 (FFMA attention only: 'fp32')
+    "head_dim_64": (64, (1, 2), [1, 2], 1, 32, 32, 3, 2),                # num_head_channels = 64
 }
 VARIANTS.update({
     "size512_mult": (64, (0.5, 1, 1, 2, 2, 4, 4), [32, 16, 8], 1, 128, 128, 2, 1),  # seven levels, 2x2 maps at the bottom
@@ -29,7 +29,7 @@ VARIANTS.update({
 })
 EXTRA = {"head_dim_64": dict(num_head_channels=64)}
 FCE = {"cs_vitb_768": dict(DINO, model="dino_vitb8", channels=768)}
-ONLY = {"head_dim_64": ("fp32",)}
+ONLY = {}
 
 
 def _variant(tag):

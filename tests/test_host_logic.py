@@ -359,19 +359,19 @@ def test_every_conv_lands_on_the_tensor_core_kernel():
 
 
 def test_unsupported_head_dim_fails_at_plan_time():
-    """head_dim other than 32 (tensor-core modes) / 32, 64 (fp32) is refused when the step program is built -- before any launch."""
+    """An attention head size other than 32 or 64 channels is refused when the step program is built -- before any launch."""
     from ccdm_b200 import models
-    for params, precs in ((dict(num_head_channels=64), ("exact", "bf16")), (dict(num_head_channels=-1, num_heads=1), ("exact", "bf16", "fp32"))):
-        p = dict(UNET_PARAMS, **params)
-        m = models.build_model(50, "cosine", {"s": 0.008}, [(1, 64, 64), (2, 64, 64)], (1, 64, 64), "unet_openai", p, "datasets.lidc",
-                               "majority", None).eval()
-        for prec in precs:
-            eng = m.unet.engine(prec, dry_run=True)
-            eng.weights.refresh()
-            with pytest.raises(NotImplementedError, match="head_dim"):
-                eng.program(2, 64, 64)
-    p = dict(UNET_PARAMS, num_head_channels=64)
+    p = dict(UNET_PARAMS, num_head_channels=-1, num_heads=1)   # one head of C = 96 / 128 channels
+    m = models.build_model(50, "cosine", {"s": 0.008}, [(1, 64, 64), (2, 64, 64)], (1, 64, 64), "unet_openai", p, "datasets.lidc",
+                           "majority", None).eval()
+    for prec in ("exact", "bf16", "fp32"):
+        eng = m.unet.engine(prec, dry_run=True)
+        eng.weights.refresh()
+        with pytest.raises(NotImplementedError, match="head_dim"):
+            eng.program(2, 64, 64)
+    p = dict(UNET_PARAMS, base_channels=64, num_head_channels=64)
     m = models.build_model(50, "cosine", {"s": 0.008}, [(1, 64, 64), (2, 64, 64)], (1, 64, 64), "unet_openai", p, "datasets.lidc", "majority", None).eval()
-    eng = m.unet.engine("fp32", dry_run=True)
-    eng.weights.refresh()
-    assert eng.program(2, 64, 64).n_ops > 0
+    for prec in ("exact", "bf16", "fp32"):
+        eng = m.unet.engine(prec, dry_run=True)
+        eng.weights.refresh()
+        assert eng.program(2, 64, 64).n_ops > 0
