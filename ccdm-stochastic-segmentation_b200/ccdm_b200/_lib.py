@@ -16,7 +16,7 @@ F16X2_SCALE_LOG2 = 4
 DRAW_SAMPLE, DRAW_MAJORITY, DRAW_CONFIDENCE, DRAW_X0, DRAW_POSTERIOR = 0, 1, 2, 3, 4
 NOISE_TENSOR, NOISE_PHILOX = 0, 1
 OP_INPUT_CONV, OP_CONV, OP_ATTENTION, OP_HEAD, OP_ENCODE_INPUT = 1, 2, 3, 4, 5
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class StepEntry(ctypes.Structure):
@@ -100,6 +100,12 @@ def lib():
     L.ccdm_conv_tc_config.argtypes = [ctypes.POINTER(Op), ctypes.POINTER(ctypes.c_int32)]
     L.ccdm_conv_part_floats.restype = ctypes.c_size_t
     L.ccdm_conv_part_floats.argtypes = [ctypes.c_int] * 4
+    VP, CI = ctypes.c_void_p, ctypes.c_int
+    L.ccdm_vit_linear.argtypes = [VP, VP, VP, VP, CI, CI, CI, CI, CI, CI, VP, VP]
+    L.ccdm_vit_layernorm.argtypes = [VP, VP, VP, CI, CI, CI, ctypes.c_float, VP, VP]
+    L.ccdm_vit_patch_embed.argtypes = [VP, VP, VP, VP, VP, CI, CI, CI, CI, CI, CI, VP, VP]
+    L.ccdm_vit_pos_embed.argtypes = [VP, CI, CI, CI, CI, ctypes.c_double, ctypes.c_double, VP, VP]
+    L.ccdm_vit_descriptor.argtypes = [VP, CI, CI, CI, CI, CI, CI, CI, CI, VP, VP]
     if L.ccdm_abi_version() != ABI_VERSION:
         raise CcdmError(f"ABI mismatch: library {L.ccdm_abi_version()} vs binding {ABI_VERSION}; rebuild")
     if L.ccdm_sizeof_op() != ctypes.sizeof(Op) or L.ccdm_sizeof_step_entry() != ctypes.sizeof(StepEntry):

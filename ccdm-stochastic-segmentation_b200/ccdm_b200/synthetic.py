@@ -19,6 +19,8 @@ def synthetic_tensor(key: str, shape, seed: int = 0) -> torch.Tensor:
     g.manual_seed((zlib.crc32(key.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF)
     shape = tuple(shape)
     r = torch.randn(shape, generator=g, dtype=torch.float32)
+    if key.endswith("pos_embed") or key.endswith("cls_token"):  # ViT position / class embeddings (DINO encoder)
+        return 0.2 * r
     if len(shape) == 1:
         if key.endswith(".weight"):  # GroupNorm gains are the only 1-D weights
             return 1.0 + 0.1 * r

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define CCDM_ABI_VERSION 3
+#define CCDM_ABI_VERSION 4
 
 /* storage types of activations / packed conv weights */
 #define CCDM_DT_F32 0
@@ -236,6 +236,36 @@ int ccdm_uniform_labels(uint64_t seed, uint32_t draw, uint32_t sample0, uint32_t
  * The reference builds [B,N,M,n_pix,K] boolean broadcasts on the host; here one CTA per (b, n, m) counts in integers and
  * does the final divisions in double, so the result equals numpy's to the last bits of the class mean. */
 int ccdm_pairwise_distance(const uint8_t *x, const uint8_t *y, int B, int N, int M, size_t n_pix, int K, double *dist, void *stream);
+
+/* ---- DINO ViT condition encoder ------------------------------- */
+/* The kernels under ccdm_b200.models.condition_encoder.DinoViT: ddpm/models/condition_encoder.py:26-46 (DinoViT.forward),
+ * ddpm/models/dino.py:211-229,279-309 (ViTExtractor._extract_features / extract_descriptors, 'key' facet of one block) and the
+ * torch.hub ViT they run (facebookresearch/dino vision_transformer.py).  Tokens are fp16x2 plane-major tensors
+ * [B][C/8][2][T][8] (CCDM_DT_F16X2; T = 1 + patches, token 0 = cls); the attention of a block is CCDM_OP_ATTENTION on the
+ * [B][3C/8][2][T][8] qkv tensor (Hin = 1, Win = T, head_dim 64) with channels ordered h*3d + {q,k,v}*d + i. */
+
+/* Output-channel tile of ccdm_vit_linear: w_packed is [Cout/NT][Cin/8][2][NT][8] fp16 = per (tile, 8-channel group) the NT hi
+ * rows, then the NT lo rows of 2^(acc_shift - 4) * W (nn.Linear weight [Cout, Cin]). */
+int ccdm_vit_linear_nt(void);
+/* out = x W^T + bias, optionally GELU (erf form) and / or + residual: Attention.qkv / .proj, Mlp.fc1 / .fc2 of a ViT block
+ * (vision_transformer.py Block.forward), and the 'key' rows of blocks[layer].attn.qkv (dino.py:172-176).  tcgen05: per K step
+ * A_hi x [W_hi; W_lo] and A_lo x W_hi, fp32 accumulation in TMEM.  Cin % 32 == 0, Cout % NT == 0; out must not alias x / residual. */
+int ccdm_vit_linear(const void *x, const void *w_packed, const float *bias, const void *residual, int B, int T, int Cin, int Cout,
+                    int gelu, int acc_shift, void *out, void *stream);
+/* nn.LayerNorm(C, eps) over the channels of every token (Block.norm1 / norm2). */
+int ccdm_vit_layernorm(const void *x, const float *gamma, const float *beta, int B, int T, int C, float eps, void *out, void *stream);
+/* PatchEmbed (Conv2d(3, D, patch, stride)) + cls token + position embedding (VisionTransformer.prepare_tokens): image fp32 NCHW
+ * [B,3,H,W]; w_t = proj.weight transposed to [3*patch*patch][D]; pos [1 + hp*wp][D] already resized (ccdm_vit_pos_embed);
+ * tokens [B][D/8][2][1 + hp*wp][8], hp = 1 + (H - patch) / stride. */
+int ccdm_vit_patch_embed(const float *image, const float *w_t, const float *bias, const float *cls, const float *pos, int B, int H,
+                         int W, int patch, int stride, int D, void *tokens, void *stream);
+/* interpolate_pos_encoding (dino.py:86-117): bicubic resize (align_corners False, A = -0.75) of the [n_side, n_side] grid of
+ * pos [1 + n_side^2][D] to [hp, wp] with the caller's scale factors ((hp + 0.1) / n_side, (wp + 0.1) / n_side); row 0 copied. */
+int ccdm_vit_pos_embed(const float *pos, int n_side, int D, int hp, int wp, double scale_h, double scale_w, float *out, void *stream);
+/* extract_descriptors (dino.py:291-301): key [B][C/8][2][T][8] (channel h*d + i) -> out fp32 NCHW [B, C, Ho, Wo], channel
+ * i*heads + h, cls dropped, bilinear (align_corners False) from the [hp, wp] patch grid (identity when Ho, Wo == hp, wp). */
+int ccdm_vit_descriptor(const void *key, int B, int T, int heads, int head_dim, int hp, int wp, int Ho, int Wo, float *out,
+                        void *stream);
 
 /* ---- programs: the whole reverse step as one launch sequence / CUDA graph --- */
 typedef struct ccdm_plan ccdm_plan;

@@ -11,6 +11,8 @@ for p in (ROOT, PKG):
         sys.path.insert(0, p)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+if GOLDEN not in sys.path:
+    sys.path.insert(0, GOLDEN)  # dino_cases.py: the case table shared with the fixture generator
 REFERENCE = "/root/reference/ddpm"
 
 UNET_PARAMS = dict(base_channels=32, channel_mult=None, attention_resolutions=[32, 16, 8], num_heads=1,
