@@ -458,6 +458,70 @@ def measure_workload(D, wl, precision, steps, warmup, batch=None, one_image=Fals
     return rec, last["labels"], m
 
 
+def measure_condition_encoder(D, wl, n_iter=5, cpu_budget=10.0):
+    """The DINO ViT-S/8 condition encoder on the workload's own images: it runs once per image, in front of
+    the chain.  Device time per batch (CUDA events), per-kernel shares, the linear layer against the tensor roofline, and the
+    oracle port on the host cores beside it (one image)."""
+    from ccdm_b200.models.condition_encoder import DinoViT
+    from ccdm_b200.synthetic import fill_synthetic_, synthetic_inputs
+    dev = D.dev
+    B, H, W = wl["B"], wl["H"], wl["W"]
+    fce = wl["fce"]
+    enc = DinoViT(fce["model"], False, fce["conditioning"], stride=fce["output_stride"])
+    fill_synthetic_(enc.extractor.model, 0)
+    enc = enc.to(dev).eval()
+    image = synthetic_inputs(B, 3, H, W, wl["K"], 0, seed=1234 + D.rank)[0]
+    image_host = image.pin_memory()
+    image_dev = image.to(dev)
+    for _ in range(3):
+        feat = enc(image_dev)
+    ms, _ = D.timed(lambda: enc(image_dev), n_iter)
+    ms /= n_iter
+    ms_e2e, _ = D.timed(lambda: enc(image_host.to(dev, non_blocking=True)).cpu(), n_iter)
+    ms_e2e /= n_iter
+    tl = []
+    enc.extractor.engine().key_descriptors(image_dev, [11], [None], timeline=tl)
+    torch.cuda.synchronize()
+    kinds = {}
+    for kind, a, b in tl:
+        k = kinds.setdefault(kind, [0.0, 0])
+        k[0] += a.elapsed_time(b)
+        k[1] += 1
+    p, Dm, depth, heads = 8, 384, 12, 6
+    T = 1 + (H // p) * (W // p)
+    flops = 11 * (24 * T * Dm * Dm + 4 * T * T * Dm) + 2 * (T - 1) * 3 * p * p * Dm + 2 * T * Dm * Dm
+    peaks = measured_peaks()
+    lin_ms = sum(v[0] for k, v in kinds.items() if k.startswith("vit_linear"))
+    lin_flops = B * (11 * 24 * T * Dm * Dm + 2 * T * Dm * Dm)
+    att_ms = sum(v[0] for k, v in kinds.items() if k.startswith("attention"))
+    rec = {"model": fce["model"], "images": B, "tokens_per_image": T, "ms_per_batch": ms, "images_per_s": D.world * B / (ms / 1e3),
+           "tflops": flops * B / (ms * 1e-3) / 1e12, "flops_per_image": flops, "launches": len(tl),
+           "e2e": {"images_per_s": D.world * B / (ms_e2e / 1e3), "ms_per_batch": ms_e2e, "h2d_bytes": image_host.numel() * 4,
+                   "d2h_bytes": feat.numel() * 4, "api": "DinoViT.forward(image) from pinned host memory; descriptors read back"},
+           "kernel_breakdown": sorted(([k, round(v[0], 4), v[1]] for k, v in kinds.items()), key=lambda r: -r[1]),
+           "roofline": {"bound": "tensor", "kernel": "vit_linear (all shapes)", "achieved": lin_flops / (lin_ms * 1e-3) / 1e12,
+                        "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": lin_flops / (lin_ms * 1e-3) / 1e12 / peaks["bf16_tflops"],
+                        "note": "algorithmic FLOPs (2 per multiply-add of the fp32 product); every product is two fp16 MMAs on split "
+                                "operands (N = 256 + N = 128), i.e. 3x the tensor work of one bf16 MMA", "traffic": None,
+                        "peak_source": peaks["source"]},
+           "attention_tflops": B * 11 * 4 * T * T * Dm / (att_ms * 1e-3) / 1e12 if att_ms > 0 else None}
+    if D.rank == 0 and cpu_budget > 0:
+        from oracle import dino_ref
+        vit = fill_synthetic_(dino_ref.build(fce["model"]), 0).eval()
+        n, t0 = 0, time.time()
+        while True:
+            dino_ref.extract_descriptors(vit, image[:1], 11, fce["output_stride"], None)
+            n += 1
+            if time.time() - t0 > cpu_budget or n >= 8:
+                break
+        dt = (time.time() - t0) / n
+        rec["cpu_baseline"] = {"value": 1.0 / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": f"{n} image(s) of the workload through oracle/dino_ref.py (torch fp32 restatement of the reference's "
+                                         f"extractor + hub ViT) on the host cores, {dt:.2f} s each"}
+    del enc
+    return rec, feat
+
+
 def agreement(a, b):
     eq = (a == b).float()
     return {"labels_equal": float(eq.mean()), "per_sample_min": float(eq.flatten(1).mean(1).min()),
@@ -479,6 +543,8 @@ def run_gpu_arm(args):
     rec, lab_main, m = measure_workload(D, head_wl, args.precision, steps, warm, batch=args.batch or None, op_table=args.op_table or None,
                                         dump_ops=args.dump_ops or None, op_profile_iters=None if args.no_op_profile else 5, lanes=args.lanes)
     modes, workloads = {}, {}
+    if head_wl["fce"] and not args.headline_only:
+        rec["condition_encoder"] = measure_condition_encoder(D, head_wl, cpu_budget=0 if args.no_cpu_baseline else 10.0)[0]
     if not args.headline_only:
         # ---- the other tensor-core mode on the same workload, same inputs, same noise: speed and T-step agreement ------
         other = "bf16" if args.precision != "bf16" else "exact"
@@ -495,6 +561,8 @@ def run_gpu_arm(args):
         r4, lab4, _ = measure_workload(D, owl, other, small, warm, e2e=False, keep_model=m3, op_profile_iters=None)
         r4[f"agreement_with_{args.precision}"] = agreement(lab3, lab4)
         r3["modes"] = {other: r4}
+        if owl["fce"]:
+            r3["condition_encoder"] = measure_condition_encoder(D, owl, cpu_budget=0 if args.no_cpu_baseline else 10.0)[0]
         workloads[oname] = r3
         del m3
         torch.cuda.empty_cache()
@@ -540,6 +608,8 @@ def run_gpu_arm(args):
                        "committed_report": "profiles/r02_parity_report.json"},
             "modes": modes, "workloads": workloads,
         }
+        if rec.get("condition_encoder"):
+            line["condition_encoder"] = rec["condition_encoder"]
     D.close()
     if line is not None:
         print(json.dumps(line), flush=True)

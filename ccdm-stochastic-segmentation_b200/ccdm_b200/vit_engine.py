@@ -131,10 +131,11 @@ class ViTEngine:
     # -- the launch sequence ------------------------------------------------------------------------
     @torch.no_grad()
     def key_descriptors(self, batch: torch.Tensor, layers: Sequence[int], out_sizes: Sequence[Optional[tuple]],
-                        tokens_out: Optional[dict] = None) -> List[torch.Tensor]:
+                        tokens_out: Optional[dict] = None, timeline: Optional[list] = None) -> List[torch.Tensor]:
         """One pass over blocks 0 .. max(layers); returns, per requested layer, its key facet as a descriptor map
         [B, D, Ho, Wo] fp32 NCHW (``out_sizes[i]`` or the patch grid).  ``tokens_out``: optional dict that receives raw copies
-        of intermediate token tensors (tests)."""
+        of intermediate token tensors (tests); ``timeline``: optional list that receives (kernel kind, start event, end event)
+        per launch (bench.py's per-kernel shares)."""
         L = _lib.lib()
         if batch.dim() != 4 or batch.shape[1] != 3:
             raise ValueError(f"the encoder takes [B, 3, H, W] images; got {tuple(batch.shape)}")
@@ -153,17 +154,27 @@ class ViTEngine:
         pos = self.pos_embed(H, W, hp, wp)
         acc_shift = self.shift + _lib.F16X2_SCALE_LOG2
 
+        def launch(kind, rc_fn):
+            """One kernel launch; with a ``timeline`` it is bracketed by two events."""
+            if timeline is not None:
+                ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ea.record()
+            _lib.check(rc_fn(), kind)
+            if timeline is not None:
+                eb.record()
+                timeline.append((kind, ea, eb))
+
         def linear(x, name, out, cin, cout, gelu=0, res=None):
-            _lib.check(L.ccdm_vit_linear(x.data_ptr(), w[name + ".w"].data_ptr(), w[name + ".b"].data_ptr(),
-                                         res.data_ptr() if res is not None else None, B, T, cin, cout, gelu, acc_shift, out.data_ptr(), sp),
-                       "vit_linear " + name)
+            launch("vit_linear %d->%d" % (cin, cout), lambda: L.ccdm_vit_linear(
+                x.data_ptr(), w[name + ".w"].data_ptr(), w[name + ".b"].data_ptr(), res.data_ptr() if res is not None else None, B, T,
+                cin, cout, gelu, acc_shift, out.data_ptr(), sp))
 
         def layernorm(x, name, out):
-            _lib.check(L.ccdm_vit_layernorm(x.data_ptr(), w[name + ".g"].data_ptr(), w[name + ".b"].data_ptr(), B, T, D, LN_EPS,
-                                            out.data_ptr(), sp), "vit_layernorm " + name)
+            launch("vit_layernorm", lambda: L.ccdm_vit_layernorm(x.data_ptr(), w[name + ".g"].data_ptr(), w[name + ".b"].data_ptr(), B, T, D,
+                                                                 LN_EPS, out.data_ptr(), sp))
 
-        _lib.check(L.ccdm_vit_patch_embed(img.data_ptr(), w["patch.wt"].data_ptr(), w["patch.b"].data_ptr(), w["cls"].data_ptr(),
-                                          pos.data_ptr(), B, H, W, p, s, D, ws["x0"].data_ptr(), sp), "vit_patch_embed")
+        launch("vit_patch_embed", lambda: L.ccdm_vit_patch_embed(img.data_ptr(), w["patch.wt"].data_ptr(), w["patch.b"].data_ptr(),
+                                                                 w["cls"].data_ptr(), pos.data_ptr(), B, H, W, p, s, D, ws["x0"].data_ptr(), sp))
         att = Op(kind=_lib.OP_ATTENTION, dtype=_lib.DT_F16X2, out_dtype=_lib.DT_F16X2, B=B, Hin=1, Win=T, Hout=1, Wout=T, C0=3 * D,
                  Cout=D, heads=self.heads, head_dim=self.hd, exact=0, src0=ws["qkv"].data_ptr(), out=ws["a"].data_ptr())
         results: Dict[int, torch.Tensor] = {}
@@ -178,13 +189,13 @@ class ViTEngine:
                 linear(ws["n"], pre + "key", ws["k"], D, D)
                 size = out_sizes[list(layers).index(i)] or (hp, wp)
                 out = torch.empty(B, D, size[0], size[1], dtype=torch.float32, device=self.device)
-                _lib.check(L.ccdm_vit_descriptor(ws["k"].data_ptr(), B, T, self.heads, self.hd, hp, wp, size[0], size[1], out.data_ptr(), sp),
-                           "vit_descriptor")
+                launch("vit_descriptor", lambda: L.ccdm_vit_descriptor(ws["k"].data_ptr(), B, T, self.heads, self.hd, hp, wp, size[0], size[1],
+                                                                       out.data_ptr(), sp))
                 results[i] = out
             if i == last:
                 break
             linear(ws["n"], pre + "qkv", ws["qkv"], D, 3 * D)
-            _lib.check(L.ccdm_launch_op(ctypes.byref(att), sp), "vit attention")
+            launch("attention T=%d heads=%d d=%d" % (T, self.heads, self.hd), lambda: L.ccdm_launch_op(ctypes.byref(att), sp))
             linear(ws["a"], pre + "proj", y, D, D, res=x)            # x + proj(attn(norm1(x)))
             layernorm(y, pre + "norm2", ws["n"])
             linear(ws["n"], pre + "fc1", ws["h"], D, 4 * D, gelu=1)
