@@ -538,6 +538,12 @@ def run_gpu_arm(args):
     small = max(1, min(steps, 2))  # timed chains of the secondary records
     head_wl = dict(WORKLOADS[args.workload], T=args.T or WORKLOADS[args.workload]["T"])
     line = None
+    if args.encoder_only:
+        rec = measure_condition_encoder(D, WORKLOADS["cityscapes"], n_iter=max(steps, 5), cpu_budget=0 if args.no_cpu_baseline else args.cpu_budget)[0]
+        D.close()
+        if rank == 0:
+            print(json.dumps({"condition_encoder": rec}), flush=True)
+        return
 
     # ---- headline: the named workload in the requested precision -----------------------------------------------------
     rec, lab_main, m = measure_workload(D, head_wl, args.precision, steps, warm, batch=args.batch or None, op_table=args.op_table or None,
@@ -628,6 +634,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--headline-only", action="store_true", help="skip the `modes` / `workloads` records (A/B and profiler runs)")
+    ap.add_argument("--encoder-only", action="store_true", help="measure only the DINO condition encoder of the Cityscapes workload")
     ap.add_argument("--lanes", type=int, default=0, help="sub-batch streams per chain (0: engine default, CCDM_LANES)")
     ap.add_argument("--dump-ops", default="", help="write the op list of one reverse step (launch order, op class, algorithmic bytes) as JSON")
     ap.add_argument("--op-table", default="", help="write the per-op-class CUDA-event table to this file")
