@@ -380,7 +380,8 @@ int launch_attention_tc(const ccdm_op &op, cudaStream_t s) {
     // unet.py:354: q and k are each scaled by 32^-1/4; fp16x2 operands are stored as 16 x value: S comes out 256 x too large
     p.scale_log2 = float(1.4426950408889634 / sqrt(double(AT_D))) * (x3 ? 1.0f / 256.0f : 1.0f);
     static const int env_nk = getenv("CCDM_ATT_NK") ? atoi(getenv("CCDM_ATT_NK")) : 0;  // tuning override
-    const int NK = x3 ? 64 : env_nk == 64 || env_nk == 128 ? env_nk : (T <= 256 ? 64 : 128);  // measured: T=256 16.8 vs 20.9 us, T=2048 76 vs 66 us
+    // (head_dim 64 and fp16x2 are instantiated with 64-key tiles only: the S descriptor must describe the tile the kernel streams)
+    const int NK = (x3 || AT_D == 64) ? 64 : env_nk == 64 || env_nk == 128 ? env_nk : (T <= 256 ? 64 : 128);  // measured: T=256 16.8 vs 20.9 us, T=2048 76 vs 66 us
     // cute::UMMA::InstrDescriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), b_major = MN (bit 16), N>>3 at 17, M>>4 at 24
     const uint32_t base = (1u << 4) | (x3 ? 0u : ((1u << 7) | (1u << 10))) | (uint32_t(128 >> 4) << 24);  // formats: 0 = f16, 1 = bf16
     p.idesc_s = base | (uint32_t(NK >> 3) << 17);
