@@ -28,7 +28,7 @@ class StepEntry(ctypes.Structure):
 _I32 = ["kind", "dtype", "B", "Hin", "Win", "Hout", "Wout", "C0", "C1", "Cout", "ksize", "stride", "upsample", "gn", "silu",
         "S0", "S1", "heads", "head_dim", "K", "C_img", "emb_off", "emb_cols", "emb_bstride", "noise_mode", "sample0",
         "out_dtype", "src_kind", "exact", "acc_shift", "img_rep", "st_slots0", "st_slots1", "st_ips0", "st_ips1", "st_items0", "st_items1",
-        "st_grid0", "st_grid1", "st_rows0", "st_rows1", "tile_batch"]
+        "st_grid0", "st_grid1", "st_rows0", "st_rows1", "tile_batch", "gn_cpg", "gn_off"]
 _U64 = ["seed", "src0", "src1", "stat0", "stat1", "gamma", "beta", "weight", "bias", "emb", "skip0", "skip1", "skip_w", "res",
         "out", "ostat", "part", "ticket", "labels_in", "labels_out", "image", "noise", "probs_out", "noise_out", "steps",
         "step_ptr"]

@@ -51,6 +51,7 @@ struct ConvP {
     int upsample, gn, silu, S0, S1, K, C_img, emb_off, emb_cols, emb_bstride, src_kind, out_f32;
     int tiles_x, tiles_y;
     int img_rep;  // samples per conditioning image (>= 1)
+    int gn_cpg, gn_off;  // GroupNorm group size / channel offset of channel 0 inside the normalised concatenation (ccdm_op::gn_cpg, gn_off)
 };
 
 // Element offset of channels c..c+3 of pixel `pix` (index inside the sample) of sample b in an activation
@@ -78,14 +79,15 @@ struct Geo {
 // GroupNorm scale/shift of the concatenated input, folded from per-channel sums.
 __device__ void build_gn_affine(const ConvP &p, int b, float *sA, float *sB) {
     const int Cin = p.Cin;
-    const int cpg = Cin / kGnGroups;
+    const int cpg = p.gn_cpg > 0 ? p.gn_cpg : Cin / kGnGroups;
     const int hw_in = p.Hin * p.Win;
     const double n = double(cpg) * double(hw_in);
     for (int c = threadIdx.x; c < Cin; c += NTHREADS) {
-        int g0 = (c / cpg) * cpg;
+        // (a group cut by this op's channel range is incomplete: its channels carry zero weights, ccdm_op::gn_off)
+        const int g0 = ((c + p.gn_off) / cpg) * cpg - p.gn_off;
+        const int j0 = g0 < 0 ? 0 : g0, j1 = g0 + cpg < Cin ? g0 + cpg : Cin;
         double s = 0.0, q = 0.0;
-        for (int j = 0; j < cpg; ++j) {
-            int cc = g0 + j;
+        for (int cc = j0; cc < j1; ++cc) {
             const double *st = cc < p.C0 ? p.stat0 + (size_t(b) * p.C0 + cc) * 2
                                          : p.stat1 + (size_t(b) * p.C1 + (cc - p.C0)) * 2;
             s += st[0];
@@ -425,7 +427,9 @@ int launch_conv(const ccdm_op &op, cudaStream_t s) {
     if (op.stride == 2 && (op.ksize != 3 || op.upsample)) CCDM_FAIL(-2, "conv: stride 2 needs ksize 3, no upsample");
     if (op.src_kind == 0 && ((op.C0 % 8) || (op.C1 % 8))) CCDM_FAIL(-2, "conv: source channels must be multiples of 8");
     if (op.src_kind == 1 && (op.gn || op.upsample || !op.labels_in || !op.image)) CCDM_FAIL(-2, "conv: bad one-hot input op");
-    if (op.gn && (p.Cin % kGnGroups)) CCDM_FAIL(-2, "conv: GroupNorm needs Cin %% 32 == 0 (got %d)", p.Cin);
+    if (op.gn && op.gn_cpg <= 0 && (p.Cin % kGnGroups)) CCDM_FAIL(-2, "conv: GroupNorm needs Cin %% 32 == 0 (got %d)", p.Cin);
+    if (op.gn_cpg < 0 || op.gn_off < 0) CCDM_FAIL(-2, "conv: gn_cpg / gn_off must not be negative");
+    p.gn_cpg = op.gn_cpg; p.gn_off = op.gn_off;
     if (op.gn && (!op.stat0 || (op.C1 && !op.stat1) || !op.gamma || !op.beta)) CCDM_FAIL(-2, "conv: gn without stats/affine");
     if ((op.S0 % 8) || (op.S1 % 8)) CCDM_FAIL(-2, "conv: skip channels must be multiples of 8");
     if (op.S0 > 0 && (op.stride != 1 || !op.skip0 || !op.skip_w)) CCDM_FAIL(-2, "conv: bad skip configuration");

@@ -59,6 +59,7 @@ struct WsP {
     uint32_t idesc2; // x3: the same with N = 2 NT
     int x3;          // fp16x2 storage (CCDM_DT_F16X2): operands are (hi, lo) plane pairs, three MMAs per product
     float descale;   // x3: 2^-acc_shift, applied to the accumulator in the epilogue
+    int gn_cpg, gn_off;  // GroupNorm group size / channel offset of channel 0 inside the normalised concatenation (ccdm_op::gn_cpg, gn_off)
     int dbg;         // CCDM_ABLATE builds only: bit 0 skip the MMAs, bit 1 skip the transform maths, bit 2 skip the epilogue's stores
 };
 
@@ -92,7 +93,7 @@ __device__ __forceinline__ Item decode_item(const WsP &p, int it) {
 // scratch), and after a barrier every thread adds up the cpg channels of its group from shared memory.  (The first
 // version walked cpg x rows elements per thread, one L2 round trip per channel of the group: 3 us at cpg = 4.)
 __device__ __forceinline__ void gn_build_affine(const WsP &p, int b, float *sAff, double2 *sSum, int t, int nthreads, int bar_id) {
-    const int cpg = p.Cin / kGnGroups;
+    const int cpg = p.gn_cpg > 0 ? p.gn_cpg : p.Cin / kGnGroups;
     const double inv_n = 1.0 / (double(cpg) * double(p.Hin) * double(p.Win));
     const float half = (p.silu == 1 || p.silu == 2) ? 0.5f : 1.0f;  // tanh forms of SiLU work on x/2
     int n_rows[2] = {0, 0};  // partial rows of sample b per source (32-bit: the host checked (B*ips+1)*grid < 2^31)
@@ -158,10 +159,13 @@ __device__ __forceinline__ void gn_build_affine(const WsP &p, int b, float *sAff
     }
     named_bar_sync(bar_id, nthreads);
     for (int c = t; c < p.Cin; c += nthreads) {
-        const int g0 = (c / cpg) * cpg;
+        // channels of c's group that this op sees (a group cut by the op's channel range is incomplete: its channels carry
+        // zero weights by construction, ccdm_op::gn_off)
+        const int g0 = ((c + p.gn_off) / cpg) * cpg - p.gn_off;
+        const int j0 = g0 < 0 ? 0 : g0, j1 = g0 + cpg < p.Cin ? g0 + cpg : p.Cin;
         double s = 0.0, q = 0.0;
-        for (int j = 0; j < cpg; ++j) {
-            const double2 e = sSum[g0 + j];
+        for (int j = j0; j < j1; ++j) {
+            const double2 e = sSum[j];
             s += e.x;
             q += e.y;
         }

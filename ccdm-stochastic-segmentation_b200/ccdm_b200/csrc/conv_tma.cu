@@ -981,7 +981,9 @@ int launch_conv_tma(const ccdm_op &op, cudaStream_t s) {
     if (x3 && (op.acc_shift < CCDM_F16X2_SCALE_LOG2 || op.acc_shift > 40)) CCDM_FAIL(-2, "conv_tma: fp16x2 op without a valid acc_shift (%d)", op.acc_shift);
 
     if (op.gn && (!op.stat0 || (op.C1 && !op.stat1) || !op.gamma || !op.beta)) CCDM_FAIL(-2, "conv_tma: gn without stats/affine");
-    if (op.gn && (p.Cin % kGnGroups)) CCDM_FAIL(-2, "conv_tma: GroupNorm needs Cin %% 32 == 0");
+    if (op.gn && op.gn_cpg <= 0 && (p.Cin % kGnGroups)) CCDM_FAIL(-2, "conv_tma: GroupNorm needs Cin %% 32 == 0");
+    if (op.gn_cpg < 0 || op.gn_off < 0) CCDM_FAIL(-2, "conv_tma: gn_cpg / gn_off must not be negative");
+    p.gn_cpg = op.gn_cpg; p.gn_off = op.gn_off;
     if (op.ostat && (!op.part || !op.ticket)) CCDM_FAIL(-2, "conv_tma: ostat without scratch");
     for (int i = 0; i < 2; ++i)
         if (op.st_slots[i] > 0 && (op.st_ips[i] <= 0 || op.st_items[i] <= 0 || op.st_grid[i] <= 0 || op.st_rows[i] <= 0 ||

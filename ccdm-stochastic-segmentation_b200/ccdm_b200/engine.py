@@ -208,6 +208,20 @@ def subpixel_weights(w: torch.Tensor) -> torch.Tensor:
     return out
 
 
+# the DINO channels of input_blocks[10] (unet.py:770-788, 545-550) are the same in every reverse step.  Their
+# GroupNorm groups, SiLU and share of the 3x3 conv -- and their share of the 1x1 skip conv -- are computed ONCE per chain into
+# two maps that the per-step convs pick up as identity-weight K chunks.  CCDM_FOLD_FEAT=0 keeps the per-step concatenation (A/B).
+_FOLD_FEAT = os.environ.get("CCDM_FOLD_FEAT", "1") != "0"
+
+
+def feat_fold_split(c_h: int, f: int):
+    """GroupNorm(32) over cat[h (c_h channels), features (f channels)]: (channels per group, number of leading feature channels
+    that share a group with h, that number rounded up to a K chunk of 16)."""
+    cpg = (c_h + f) // 32
+    n_f = (-c_h) % cpg
+    return cpg, n_f, _ceil(n_f, 16)
+
+
 def pack_bias(b: torch.Tensor) -> torch.Tensor:
     out = torch.zeros(_ceil(b.numel(), 32), dtype=torch.float32, device=b.device)
     out[:b.numel()] = b.float()
@@ -266,6 +280,20 @@ class PackedWeights:
                     self._reserve(p + ":w2", 9 * L.cout * L.cout, (9, L.cout, L.cout)); self._reserve(p + ":b2", L.cout)
                     if L.skip_conv:
                         self._reserve(p + ":ws", L.cin * L.cout, (1, L.cin, L.cout))
+                    if blk.feat_concat and L is blk.layers[0] and L.skip_conv:
+                        # folded form of the feature-concat ResBlock (feat_fold_split): per-step conv over h + the f16 leading
+                        # feature channels, per-chain convs over the feature tensor, skip conv over h + the per-chain skip map
+                        f = blk.feat_concat
+                        c_h = L.cin - f
+                        _, _, f16 = feat_fold_split(c_h, f)
+                        cs = c_h + f16
+                        self._reserve(p + ":g1s", cs); self._reserve(p + ":be1s", cs)
+                        self._reserve(p + ":w1s", 9 * cs * L.cout, (9, cs, L.cout))
+                        self._reserve(p + ":g1m", f); self._reserve(p + ":be1m", f)
+                        self._reserve(p + ":w1m", 9 * f * L.cout, (9, f, L.cout))
+                        self._reserve(p + ":wsm", f * L.cout, (1, f, L.cout))
+                        self._reserve(p + ":ws2", (c_h + L.cout) * L.cout, (1, c_h + L.cout, L.cout))
+                        self._reserve(p + ":b0", _ceil(L.cout, 32))
                 elif L.kind == "attn":
                     self._reserve(p + ":g", L.cin); self._reserve(p + ":be", L.cin)
                     self._reserve(p + ":wqkv", L.cin * 3 * L.cin, (1, L.cin, 3 * L.cin)); self._reserve(p + ":bqkv", 3 * L.cin)
@@ -369,6 +397,24 @@ class PackedWeights:
                         put(p + ":ws", ws[:, :, 0, 0].t().contiguous(), ws, nt=self._nt(L.cout, 9) if self.with_tc else None)
                         b2 = b2 + sd[p + ".skip_connection.bias"]
                     put(p + ":b2", b2)
+                    if p + ":w1s" in self.slots:
+                        f = blk.feat_concat
+                        c_h = L.cin - f
+                        _, n_f, f16 = feat_fold_split(c_h, f)
+                        cs = c_h + f16
+                        w1, g1, be1 = sd[p + ".in_layers.2.weight"], sd[p + ".in_layers.0.weight"], sd[p + ".in_layers.0.bias"]
+                        w1s = w1[:, :cs].clone()
+                        w1s[:, c_h + n_f:] = 0          # feature channels past the shared group belong to the per-chain map
+                        w1m = w1[:, c_h:].clone()
+                        w1m[:, :n_f] = 0                # ... and the shared group's feature channels to the per-step conv
+                        put(p + ":g1s", g1[:cs]); put(p + ":be1s", be1[:cs]); put(p + ":w1s", conv_w(w1s), w1s)
+                        put(p + ":g1m", g1[c_h:]); put(p + ":be1m", be1[c_h:]); put(p + ":w1m", conv_w(w1m), w1m)
+                        ws = sd[p + ".skip_connection.weight"]
+                        wsm = ws[:, c_h:].contiguous()
+                        put(p + ":wsm", wsm[:, :, 0, 0].t().contiguous(), wsm)
+                        ws2 = torch.cat([ws[:, :c_h], torch.eye(L.cout, device=ws.device).reshape(L.cout, L.cout, 1, 1)], 1).contiguous()
+                        put(p + ":ws2", ws2[:, :, 0, 0].t().contiguous(), ws2, nt=self._nt(L.cout, 9) if self.with_tc else None)
+                        put(p + ":b0", torch.zeros(1, device=self.device))
                     emb_w.append(sd[p + ".emb_layers.1.weight"]); emb_b.append(sd[p + ".emb_layers.1.bias"])
                 elif L.kind == "attn":
                     put(p + ":g", sd[p + ".norm.weight"]); put(p + ":be", sd[p + ".norm.bias"])
@@ -433,6 +479,10 @@ class Program:
         if fc:
             self.feat = Ten("feature_condition", fc, H // 8, W // 8, self.esize, True, fmt=self.dt, external=True)
 
+        # per-chain constants of the folded feature-concat ResBlock: set where that block is planned
+        self.feat16: Optional[Ten] = None   # the leading feature channels that share a GroupNorm group with h
+        self.fmaps: List[Ten] = []          # [conv map, skip map]
+        self._pre_dicts: List[dict] = []    # the ops that produce them, launched once per chain (run_pre)
         hs: List[Ten] = []
         h: Optional[Ten] = None
         ch, cw = H, W
@@ -457,6 +507,29 @@ class Program:
                 elif Ly.kind == "conv_in":
                     h = emit(_lib.OP_INPUT_CONV, [], new(p, Ly.cout, ch, cw), src_kind=1, ksize=3, stride=1, Hin=ch, Win=cw,
                              Hout=ch, Wout=cw, Cout=Ly.cout, K=self.K, C_img=self.C_img, img_rep=img_rep, _w=p + ":w", _b=p + ":b")
+                elif (Ly.kind == "res" and _FOLD_FEAT and blk.feat_concat and len(srcs) == 2 and srcs[1] is self.feat and Ly.skip_conv
+                      and (p + ":w1s") in engine.weights.slots and not self.fmaps):
+                    # input_blocks[10] with the constant feature channels folded into two per-chain maps:
+                    #   h1 = conv3x3(SiLU(GN(cat[h, f])))  =  conv over cat[h, f[:f16]] (the groups h takes part in; per step)
+                    #                                         + fmap1 = conv over f with the same 14-channel groups (per chain)
+                    #   skip(cat[h, f])                    =  skip over h (per step) + fmap2 = skip over f (per chain)
+                    hh, ft = srcs
+                    cpg, n_f, f16 = feat_fold_split(hh.C, ft.C)
+                    if f16:
+                        self.feat16 = Ten("feature_condition[:%d]" % f16, f16, ch, cw, self.esize, True, fmt=self.dt, external=True)
+                    self.fmaps = [Ten(p + ":fmap%d" % j, Ly.cout, ch, cw, self.esize, False, fmt=self.dt, external=True) for j in (1, 2)]
+                    geo = dict(stride=1, Hin=ch, Win=cw, Hout=ch, Wout=cw, Cout=Ly.cout)
+                    self._pre_dicts = [
+                        dict(kind=_lib.OP_CONV, ksize=3, gn=1, silu=1, gn_cpg=cpg, gn_off=hh.C, _src=[ft], _g=p + ":g1m", _be=p + ":be1m",
+                             _w=p + ":w1m", _b=p + ":b0", _ins=[ft], _out=self.fmaps[0], **geo),
+                        dict(kind=_lib.OP_CONV, ksize=1, gn=0, silu=0, _src=[ft], _w=p + ":wsm", _b=p + ":b0", _ins=[ft], _out=self.fmaps[1], **geo)]
+                    s1 = [hh] + ([self.feat16] if f16 else [])
+                    h1 = emit(_lib.OP_CONV, s1, new(p + ":h1", Ly.cout, ch, cw), ksize=3, gn=1, silu=1, gn_cpg=cpg, gn_off=0, _src=s1,
+                              _g=p + ":g1s", _be=p + ":be1s", _w=p + ":w1s", _b=p + ":b1", emb_off=Ly.emb_off, _emb=True,
+                              _skip=[self.fmaps[0]], _ws=engine.weights.ident_name(Ly.cout, 9), **geo)
+                    h = emit(_lib.OP_CONV, [h1, hh], new(p, Ly.cout, ch, cw), ksize=3, gn=1, silu=1, _src=[h1], _g=p + ":g2", _be=p + ":be2",
+                             _w=p + ":w2", _b=p + ":b2", _skip=[hh, self.fmaps[1]], _ws=p + ":ws2", **geo)
+                    srcs = [h]
                 elif Ly.kind == "res":
                     if len(srcs) == 2 and not Ly.skip_conv:
                         raise NotImplementedError("identity skip over a concatenated input")
@@ -534,6 +607,11 @@ class Program:
                       labels=_ceil(n_pix, ALIGN), image=_ceil(n_pix * self.C_img * 4, ALIGN), feat=feat_bytes,
                       feat_stat=_ceil(B * fc * 16, ALIGN) if fc else 0, probs=_ceil(n_pix * self.K * 4, ALIGN),
                       noise=_ceil(n_pix * self.K * 4, ALIGN), step=ALIGN)
+        if self.fmaps:
+            fh, fw = self.fmaps[0].H, self.fmaps[0].W
+            layout.update(fmap1=_ceil(B * self.fmaps[0].C * fh * fw * self.esize, ALIGN), fmap2=_ceil(B * self.fmaps[1].C * fh * fw * self.esize, ALIGN))
+            if self.feat16 is not None:
+                layout.update(feat16=_ceil(B * self.feat16.C * fh * fw * self.esize, ALIGN), feat16_stat=_ceil(B * self.feat16.C * 16, ALIGN))
         offs, total = {}, 0
         for k, v in layout.items():
             offs[k] = total
@@ -546,6 +624,10 @@ class Program:
         if self.feat is not None:
             self.feat.addr = self.addr["feat"]
             self.feat.stat_addr = self.addr["feat_stat"]
+        if self.fmaps:
+            self.fmaps[0].addr, self.fmaps[1].addr = self.addr["fmap1"], self.addr["fmap2"]
+            if self.feat16 is not None:
+                self.feat16.addr, self.feat16.stat_addr = self.addr["feat16"], self.addr["feat16_stat"]
         for t in tens:
             t.addr = self.addr["arena"] + t.off
             t.stat_addr = self.addr["stat"] + t.stat_off if t.want_stat else 0
@@ -618,12 +700,13 @@ class Program:
 
         # pass 1: which convs land on the tensor-core kernel.  Everything downstream -- weight layout, statistics layout of
         # the INPUT tensors -- follows from this, so it is decided before anything is bound.
+        all_dicts = self._op_dicts + self._pre_dicts  # the per-chain ops (run_pre) are bound like the step's, behind them
         use_tc = [bool(self.exact == 0 and o["kind"] == _lib.OP_CONV and L.ccdm_conv_uses_tc(ctypes.byref(base_op(o))))
-                  for o in self._op_dicts]
-        off_tc = [i for i, o in enumerate(self._op_dicts) if self.exact == 0 and o["kind"] == _lib.OP_CONV and not use_tc[i]]
+                  for o in all_dicts]
+        off_tc = [i for i, o in enumerate(all_dicts) if self.exact == 0 and o["kind"] == _lib.OP_CONV and not use_tc[i]]
         if off_tc:
-            what = ", ".join("op %d (%s -> %d ch @%dx%d)" % (i, "+".join(str(t.C) for t in self._op_dicts[i]["_src"]),
-                                                              self._op_dicts[i]["Cout"], self._op_dicts[i]["Hout"], self._op_dicts[i]["Wout"])
+            what = ", ".join("op %d (%s -> %d ch @%dx%d)" % (i, "+".join(str(t.C) for t in all_dicts[i]["_src"]),
+                                                              all_dicts[i]["Cout"], all_dicts[i]["Hout"], all_dicts[i]["Wout"])
                              for i in off_tc)
             if self.x3:
                 raise _lib.CcdmError("precision='exact': the tensor-core conv kernel cannot take " + what +
@@ -634,13 +717,13 @@ class Program:
         # a tensor's statistics are left as per-CTA partial rows (deferred fold) only if its producer is a tensor-core conv
         # AND every GroupNorm consumer is one too: the FFMA kernel reads folded double2 sums
         gn_readers: Dict[int, List[int]] = {}
-        for i, o in enumerate(self._op_dicts):
+        for i, o in enumerate(all_dicts):
             if o["kind"] == _lib.OP_CONV and o.get("gn"):
                 for sten in o.get("_src", [])[:2]:
                     gn_readers.setdefault(id(sten), []).append(i)
 
-        arr = (Op * self.n_ops)()
-        for i, o in enumerate(self._op_dicts):
+        arr: List[Op] = [None] * len(all_dicts)
+        for i, o in enumerate(all_dicts):
             op = base_op(o)
             src = o.get("_src", [])
             if o["kind"] in (_lib.OP_INPUT_CONV, _lib.OP_ENCODE_INPUT):
@@ -707,16 +790,23 @@ class Program:
             op.steps = self.steps_buf.data_ptr()
             op.step_ptr = self.addr["step"]
             arr[i] = op
-        shared = [i for i in range(self.n_ops) if arr[i].part == 1]  # folded-by-producer ops share one scratch
+        shared = [i for i in range(len(arr)) if arr[i].part == 1]  # folded-by-producer ops share one scratch
         part_floats = max([int(L.ccdm_op_part_floats(ctypes.byref(arr[i]))) for i in shared] + [1])
         self.part_buf = torch.zeros(part_floats, dtype=torch.float32, device=dev)
         for i in shared:
             arr[i].part = self.part_buf.data_ptr()
-        self.n_tc = sum(use_tc)
-        self._op_array = arr
-        self.plan = L.ccdm_plan_create(arr, self.n_ops)
+        self.n_tc = sum(use_tc[:self.n_ops])
+        self._op_array = (Op * self.n_ops)(*arr[:self.n_ops])
+        self._pre_array = arr[self.n_ops:]
+        self.plan = L.ccdm_plan_create(self._op_array, self.n_ops)
         if not self.plan:
             raise _lib.CcdmError("ccdm_plan_create failed: " + L.ccdm_last_error().decode())
+
+    def run_pre(self, stream_ptr):
+        """Launch the per-chain ops (the constant feature maps of the folded feature-concat ResBlock).  Call after bind() and
+        after the feature condition of the chain has been loaded."""
+        for op in self._pre_array:
+            _lib.check(_lib.lib().ccdm_launch_op(ctypes.byref(op), stream_ptr), "per-chain feature map")
 
     def set_noise(self, noise_mode: int, seed: int = 0, sample0: int = 0, use_noise_buf: bool = False,
                   export_noise: bool = False):
@@ -818,6 +908,12 @@ class UNetEngine:
             fcond = feature_condition.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
             _lib.check(L.ccdm_nchw_to_nhwc_stats(fcond.data_ptr(), B, f.C, f.H, f.W, prog.dt, f.addr, f.stat_addr, prog.img_rep,
                                                  self._sp()), "nchw_to_nhwc_stats")
+            if prog.feat16 is not None:
+                f16 = prog.feat16
+                head = fcond[:, :f16.C].contiguous()
+                _lib.check(L.ccdm_nchw_to_nhwc_stats(head.data_ptr(), B, f16.C, f16.H, f16.W, prog.dt, f16.addr, f16.stat_addr, prog.img_rep,
+                                                     self._sp()), "nchw_to_nhwc_stats (leading feature channels)")
+                head.record_stream(self.stream)
             fcond.record_stream(self.stream)
         # (unet.py:770: a feature_condition passed to a UNet without an encoder slot is ignored)
 
@@ -863,6 +959,7 @@ class UNetEngine:
             prog = self.program(B, H, W, rows_per_sample=1)
             self._load_inputs(prog, x, condition, feature_condition)
             self._write_tables(prog, [(ts[0], 0.0, 1.0, _lib.DRAW_X0, 0, 0)], ts)
+            prog.run_pre(self._sp())
             prog.set_noise(_lib.NOISE_PHILOX)
             _lib.check(L.ccdm_plan_step(prog.plan, 0, self._sp()), "plan_step")
             out = prog.probs.clone()
@@ -952,6 +1049,7 @@ class UNetEngine:
                 mode = _lib.DRAW_SAMPLE if t > 1 else last_mode  # :206-212
                 entries.append((float(t), a, c, mode, i, i))
             self._write_tables(prog, entries, [float(t) for t in t_values])
+            prog.run_pre(self._sp())
             use_tensor = noise == "torch"
             want_noise_out = record is not None and not use_tensor
             prog.set_noise(_lib.NOISE_TENSOR if use_tensor else _lib.NOISE_PHILOX, seed, sample0, use_noise_buf=use_tensor,
@@ -997,6 +1095,7 @@ class UNetEngine:
             prog = self.program(B, H, W, rows_per_sample=0)
             self._load_inputs(prog, x, condition, feature_condition)
             self._write_tables(prog, [(float(t), alpha, cumalpha, mode, 0, 0)], [float(t)])
+            prog.run_pre(self._sp())
             prog.set_noise(_lib.NOISE_PHILOX)
             for i, o in enumerate(prog._op_dicts):
                 _lib.check(L.ccdm_launch_op(ctypes.byref(prog._op_array[i]), self._sp()), f"op {i}")

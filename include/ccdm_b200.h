@@ -119,6 +119,11 @@ typedef struct ccdm_op {
                          * fp32 per-item partial sums of the GroupNorm statistics -- independent of how a batch is split over
                          * calls or GPUs (bit-identical results in the fp16x2 mode), at the price of fewer, larger items when the
                          * real batch is small */
+    int32_t gn_cpg;     /* GroupNorm: channels per group of the input (0: (C0 + C1) / 32, nn.py:93-100).  Set when the op sees only PART
+                         * of a normalised concatenation: the per-step half of input_blocks[10] after the constant DINO channels were
+                         * folded into a per-chain map (unet.py:770-788) */
+    int32_t gn_off;     /* ... and the number of channels of that concatenation in front of this op's channel 0: channel c belongs to
+                         * group (c + gn_off) / gn_cpg; groups cut by the op's channel range are only used with zero weights */
     uint64_t seed;      /* Philox key */
     /* device pointers (0 = absent) */
     uint64_t src0, src1;       /* inputs NHWC                                             */

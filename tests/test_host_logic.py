@@ -163,7 +163,7 @@ def test_program_planning_dry_run(cfg):
             assert lo <= o.out < hi
             assert o.B == B and o.Cout > 0
         if o.kind == _lib.OP_CONV and o.gn:
-            assert o.stat0 and o.gamma and o.beta and (o.C0 + o.C1) % 32 == 0
+            assert o.stat0 and o.gamma and o.beta and ((o.C0 + o.C1) % 32 == 0 or o.gn_cpg > 0)
     # concat never materialised: output blocks read two sources
     assert sum(1 for o in ops if o.kind == _lib.OP_CONV and o.C1 > 0) == sum(1 for b in m.unet.arch.blocks if b.stage == "out" or b.feat_concat)
     assert sum(1 for o in ops if o.S0 > 0) == sum(1 for b in m.unet.arch.blocks for l in b.layers if l.kind == "res" and l.skip_conv)
@@ -375,3 +375,60 @@ def test_unsupported_head_dim_fails_at_plan_time():
         eng = m.unet.engine(prec, dry_run=True)
         eng.weights.refresh()
         assert eng.program(2, 64, 64).n_ops > 0
+
+
+@pytest.mark.parametrize("c_h,f", [(64, 384), (64, 768), (128, 384)])
+def test_feature_fold_algebra(c_h, f):
+    """conv3x3(SiLU(GN32(cat[h, f]))) == per-step conv over cat[h, f[:f16]] (groups of cpg channels, the feature
+    channels past the shared group zero-weighted) + per-chain conv over f (same groups, counted from channel c_h; the shared
+    group's feature channels zero-weighted) -- the split engine.PackedWeights.refresh packs (unet.py:770-788, 545-550)."""
+    from ccdm_b200.engine import feat_fold_split
+    torch.manual_seed(0)
+    cout, H, W = 32, 6, 10
+    h, ft = torch.randn(2, c_h, H, W, dtype=torch.float64) * 1.5 + 0.2, torch.randn(2, f, H, W, dtype=torch.float64) * 0.8 - 0.1
+    g, be = 1 + 0.1 * torch.randn(c_h + f, dtype=torch.float64), 0.1 * torch.randn(c_h + f, dtype=torch.float64)
+    w = torch.randn(cout, c_h + f, 3, 3, dtype=torch.float64) / 30
+    want = torch.nn.functional.conv2d(torch.nn.functional.silu(torch.nn.functional.group_norm(torch.cat([h, ft], 1), 32, g, be, 1e-5)), w, padding=1)
+    cpg, n_f, f16 = feat_fold_split(c_h, f)
+    assert cpg == (c_h + f) // 32 and (c_h + n_f) % cpg == 0 and 0 <= n_f < cpg and f16 % 16 == 0 and f16 >= n_f
+
+    def gn_part(x, off, gam, bet):
+        """GroupNorm of channel range [off, off + C) of the concatenation with the statistics of the channels it SEES (what the
+        kernels do with ccdm_op::gn_cpg / gn_off): complete groups are exact, cut groups are garbage (zero-weighted)."""
+        C = x.shape[1]
+        out = torch.zeros_like(x)
+        for c in range(C):
+            g0 = ((c + off) // cpg) * cpg - off
+            j0, j1 = max(g0, 0), min(g0 + cpg, C)
+            n = cpg * H * W
+            mean = x[:, j0:j1].sum(dim=(1, 2, 3)) / n
+            var = (x[:, j0:j1] ** 2).sum(dim=(1, 2, 3)) / n - mean ** 2
+            out[:, c] = (x[:, c] - mean[:, None, None]) / torch.sqrt(var.clamp(min=0)[:, None, None] + 1e-5) * gam[c] + bet[c]
+        return out
+
+    cs = c_h + f16
+    xs = torch.cat([h, ft[:, :f16]], 1)
+    w1s = w[:, :cs].clone(); w1s[:, c_h + n_f:] = 0
+    w1m = w[:, c_h:].clone(); w1m[:, :n_f] = 0
+    step = torch.nn.functional.conv2d(torch.nn.functional.silu(gn_part(xs, 0, g[:cs], be[:cs])), w1s, padding=1)
+    chain = torch.nn.functional.conv2d(torch.nn.functional.silu(gn_part(ft, c_h, g[c_h:], be[c_h:])), w1m, padding=1)
+    assert float((step + chain - want).abs().max()) < 1e-10
+
+
+def test_feature_fold_is_planned_for_the_dino_block():
+    """The Cityscapes program runs input_blocks[10] in its folded form in every precision mode, on the tensor-core kernel in the
+    tensor-core modes, with two per-chain ops beside the step."""
+    from ccdm_b200 import _lib
+    m = _build(3, 256, 512, 20, True, None)
+    for prec in ("exact", "bf16", "fp32"):
+        eng = m.unet.engine(prec, dry_run=True)
+        eng.weights.refresh()
+        prog = eng.program(2, 256, 512)
+        prog.bind(8)
+        assert len(prog._pre_array) == 2 and not prog.off_tc
+        pre_conv, pre_skip = prog._pre_array
+        assert (pre_conv.C0, pre_conv.ksize, pre_conv.gn, pre_conv.gn_cpg, pre_conv.gn_off) == (384, 3, 1, 14, 64)
+        assert (pre_skip.C0, pre_skip.ksize, pre_skip.gn) == (384, 1, 0)
+        folded = [o for o in prog._op_array if o.kind == _lib.OP_CONV and o.gn_cpg > 0]
+        assert len(folded) == 1 and (folded[0].C0, folded[0].C1, folded[0].gn_cpg, folded[0].gn_off) == (64, 16, 14, 0)
+        assert not [o for o in prog._op_array if o.kind == _lib.OP_CONV and (o.C0 + o.C1 > 256 or o.S0 + o.S1 > 256)]  # no 448-channel op is left
