@@ -507,7 +507,7 @@ class Program:
                 elif Ly.kind == "conv_in":
                     h = emit(_lib.OP_INPUT_CONV, [], new(p, Ly.cout, ch, cw), src_kind=1, ksize=3, stride=1, Hin=ch, Win=cw,
                              Hout=ch, Wout=cw, Cout=Ly.cout, K=self.K, C_img=self.C_img, img_rep=img_rep, _w=p + ":w", _b=p + ":b")
-                elif (Ly.kind == "res" and _FOLD_FEAT and blk.feat_concat and len(srcs) == 2 and srcs[1] is self.feat and Ly.skip_conv
+                elif (Ly.kind == "res" and engine.fold_features and blk.feat_concat and len(srcs) == 2 and srcs[1] is self.feat and Ly.skip_conv
                       and (p + ":w1s") in engine.weights.slots and not self.fmaps):
                     # input_blocks[10] with the constant feature channels folded into two per-chain maps:
                     #   h1 = conv3x3(SiLU(GN(cat[h, f])))  =  conv over cat[h, f[:f16]] (the groups h takes part in; per step)
@@ -863,11 +863,14 @@ class UNetEngine:
         # N > 0 = as if the batch were N.  With a fixed value the `exact` mode's result for a sample is bit-identical
         # whatever batch it runs in (DenoisingModel.tile_batch; sample_sharded sets 64).
         self.tile_batch = 0
+        # run the feature-concat ResBlock in its folded form (constant DINO channels as per-chain maps); False keeps
+        # the per-step 448-channel concatenation (A/B, tests)
+        self.fold_features = _FOLD_FEAT
         self._children: List["UNetEngine"] = []
 
     # -- helpers ----------------------------------------------------------------------
     def program(self, B, H, W, rows_per_sample=0, img_rep=1) -> Program:
-        key = (B, H, W, rows_per_sample, img_rep, self.tile_batch)
+        key = (B, H, W, rows_per_sample, img_rep, self.tile_batch, self.fold_features)
         prog = self.programs.get(key)
         if prog is None:
             # bounded cache: a ragged last batch or a change of batch size must not pile up ~1 GB workspaces
@@ -974,6 +977,7 @@ class UNetEngine:
             c.dry_run, c.unet, c.precision, c.device, c.weights = False, self.unet, self.precision, self.device, self.weights
             c.programs, c.stream, c.use_graph, c.lanes, c._children = OrderedDict(), torch.cuda.Stream(device=self.device), self.use_graph, 1, []
             c.tile_batch = self.tile_batch
+            c.fold_features = self.fold_features
             self._children.append(c)
         for c in self._children:
             c.use_graph = self.use_graph

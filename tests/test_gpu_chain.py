@@ -437,3 +437,28 @@ def test_sample_many_indexes_the_image_and_votes_on_device(cuda_device):
             assert torch.equal(out["majority"].long(), out["mean_onehot"].argmax(dim=1))
     with pytest.raises(ValueError):
         m.sample_many(image.cuda(), 0)
+
+
+@pytest.mark.parametrize("prec", PARITY_MODES + ["bf16"])
+def test_feature_fold_equals_the_per_step_concatenation(cuda_device, prec):
+    """input_blocks[10] with the constant DINO channels folded into per-chain maps (the default) against the same
+    block run on the 448-channel concatenation every step (engine.fold_features = False): the UNet outputs agree to the
+    storage precision of the two maps, and both sit inside the tolerance against the reference fixture."""
+    T, B, C_img, H, W, K, fce, mult, t_probe, steps = GOLDEN_CASES["cs64x128"]
+    g = golden("cs64x128.npz")
+    m, image, feat, labels = _case("cs64x128")
+    m.unet.precision = prec
+    x = _onehot(labels, K).cuda()
+    eng = m.unet.engine(prec)
+    outs = {}
+    for fold in (True, False):
+        eng.fold_features = fold
+        prog = eng.program(B, H, W, rows_per_sample=1)
+        assert bool(prog.fmaps) == fold
+        outs[fold] = m.unet(x, image.cuda(), feat.cuda(), torch.full((B,), float(t_probe[0])).cuda())["diffusion_out"].permute(0, 2, 3, 1).cpu().numpy()
+    eng.fold_features = True
+    d = float(np.abs(outs[True] - outs[False]).max())
+    e = [float(np.abs(outs[f] - g[f"x0pred_t{t_probe[0]}"]).max()) for f in (True, False)]
+    _report(f"feature_fold_{prec}", folded_vs_unfolded=d, folded_vs_fixture=e[0], unfolded_vs_fixture=e[1])
+    tol = X0_TOL if prec != "bf16" else 6e-2
+    assert d <= tol and e[0] <= tol and e[1] <= tol, (d, e)
