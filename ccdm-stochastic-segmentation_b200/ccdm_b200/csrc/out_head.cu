@@ -28,7 +28,6 @@ constexpr int OH_TW = 32, OH_TH = 16;            // output tile
 constexpr int OH_WP = 37, OH_HP = OH_TH + 2;     // staged positions per tile row (34 used; 37: see above), staged rows
 constexpr int OH_CH = 16, OH_PITCH = OH_CH + 4;  // channels per pass, floats per staged position
 constexpr int OH_THREADS = 128;
-constexpr int OH_UNR = 5;                       // staged items in flight per thread
 constexpr int OH_MAXC = 64;
 
 struct OhP {
@@ -80,55 +79,33 @@ __global__ void __launch_bounds__(OH_THREADS) out_head_kernel(const OhP p) {
     for (int c0 = 0; c0 < C; c0 += OH_CH) {
         __syncthreads();  // the previous pass's readers are done (first pass: sAff / sW are complete)
         // ---- stage 34 x 18 positions x 16 channels, transformed ------------------------------------------------------
-        // (batches of OH_UNR items per thread: all loads of a batch are issued before the first value is used -- with one
-        // item at a time the pass was a chain of exposed HBM round trips, ncu: 3.1 long-scoreboard stalls per issue)
-        constexpr int N_ITEMS = 2 * OH_HP * (OH_TW + 2);
-        for (int base = t; base < N_ITEMS; base += OH_THREADS * OH_UNR) {
-            uint4 hi[OH_UNR], lo[OH_UNR];
-            bool in[OH_UNR];
+        for (int it = t; it < 2 * OH_HP * (OH_TW + 2); it += OH_THREADS) {
+            const int g = it / (OH_HP * (OH_TW + 2)), pos = it - g * (OH_HP * (OH_TW + 2));
+            const int r = pos / (OH_TW + 2), c = pos - r * (OH_TW + 2);
+            const int gy = y0 - 1 + r, gx = x0 - 1 + c;
+            float v[8];
+            if (unsigned(gy) < unsigned(H) && unsigned(gx) < unsigned(W)) {
+                const int gg = c0 / 8 + g;
+                const __half *ph = src + (size_t(b) * G + gg) * 2 * plane + (size_t(gy) * W + gx) * 8;
+                const uint4 hi = *reinterpret_cast<const uint4 *>(ph);
+                const uint4 lo = *reinterpret_cast<const uint4 *>(ph + plane);
+                const uint32_t h4[4] = {hi.x, hi.y, hi.z, hi.w}, l4[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
-            for (int u = 0; u < OH_UNR; ++u) {
-                const int it = base + u * OH_THREADS;
-                const int g = it / (OH_HP * (OH_TW + 2)), pos = it - g * (OH_HP * (OH_TW + 2));
-                const int r = pos / (OH_TW + 2), c = pos - r * (OH_TW + 2);
-                const int gy = y0 - 1 + r, gx = x0 - 1 + c;
-                in[u] = it < N_ITEMS && unsigned(gy) < unsigned(H) && unsigned(gx) < unsigned(W);
-                if (in[u]) {
-                    const __half *ph = src + (size_t(b) * G + (c0 / 8 + g)) * 2 * plane + (size_t(gy) * W + gx) * 8;
-                    hi[u] = ldg_nc16(ph);
-                    lo[u] = ldg_nc16(ph + plane);
+                for (int i = 0; i < 4; ++i) {
+                    const float2 xh = unpack_f16x2(h4[i]), xl = unpack_f16x2(l4[i]);
+                    const int ch = gg * 8 + 2 * i;
+                    float h0 = fmaf(xh.x, sAff[ch], fmaf(xl.x, sAff[ch], sAff[C + ch]));
+                    float h1 = fmaf(xh.y, sAff[ch + 1], fmaf(xl.y, sAff[ch + 1], sAff[C + ch + 1]));
+                    v[2 * i] = __fdividef(h0, 1.0f + __expf(-h0));       // the transform of conv_tma's fp16x2 path (xf_row_x3)
+                    v[2 * i + 1] = __fdividef(h1, 1.0f + __expf(-h1));
                 }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = 0.f;
             }
-#pragma unroll
-            for (int u = 0; u < OH_UNR; ++u) {
-                const int it = base + u * OH_THREADS;
-                if (it >= N_ITEMS) break;
-                const int g = it / (OH_HP * (OH_TW + 2)), pos = it - g * (OH_HP * (OH_TW + 2));
-                const int r = pos / (OH_TW + 2), c = pos - r * (OH_TW + 2);
-                float v[8];
-                if (in[u]) {
-                    const int gg = c0 / 8 + g;
-                    const uint32_t h4[4] = {hi[u].x, hi[u].y, hi[u].z, hi[u].w}, l4[4] = {lo[u].x, lo[u].y, lo[u].z, lo[u].w};
-                    const float4 fa0 = *reinterpret_cast<const float4 *>(sAff + gg * 8), fa1 = *reinterpret_cast<const float4 *>(sAff + gg * 8 + 4);
-                    const float4 fb0 = *reinterpret_cast<const float4 *>(sAff + C + gg * 8), fb1 = *reinterpret_cast<const float4 *>(sAff + C + gg * 8 + 4);
-                    const float fa[8] = {fa0.x, fa0.y, fa0.z, fa0.w, fa1.x, fa1.y, fa1.z, fa1.w};
-                    const float fb[8] = {fb0.x, fb0.y, fb0.z, fb0.w, fb1.x, fb1.y, fb1.z, fb1.w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float2 xh = unpack_f16x2(h4[i]), xl = unpack_f16x2(l4[i]);
-                        const float h0 = fmaf(xh.x, fa[2 * i], fmaf(xl.x, fa[2 * i], fb[2 * i]));
-                        const float h1 = fmaf(xh.y, fa[2 * i + 1], fmaf(xl.y, fa[2 * i + 1], fb[2 * i + 1]));
-                        v[2 * i] = __fdividef(h0, 1.0f + __expf(-h0));       // the transform of conv_tma's fp16x2 path (xf_row_x3)
-                        v[2 * i + 1] = __fdividef(h1, 1.0f + __expf(-h1));
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = 0.f;
-                }
-                float *dst = sAct + (size_t(r) * OH_WP + c) * OH_PITCH + g * 8;
-                *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4 *>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-            }
+            float *dst = sAct + (size_t(r) * OH_WP + c) * OH_PITCH + g * 8;
+            *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4 *>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
         }
         __syncthreads();
         // ---- accumulate --------------------------------------------------------------------------------------------------
@@ -144,17 +121,10 @@ __global__ void __launch_bounds__(OH_THREADS) out_head_kernel(const OhP p) {
                 for (int dx = 0; dx < 3; ++dx) {
                     const float *wp = sW + (size_t(dy * 3 + dx) * C + c0 + c4 * 4) * KMAX;
                     float wv[4][KMAX];
-                    if constexpr (KMAX == 2) {  // 8 weights = two broadcast LDS.128
-                        const float4 w0 = *reinterpret_cast<const float4 *>(wp), w1 = *reinterpret_cast<const float4 *>(wp + 4);
-                        wv[0][0] = w0.x; wv[0][1] = w0.y; wv[1][0] = w0.z; wv[1][1] = w0.w;
-                        wv[2][0] = w1.x; wv[2][1] = w1.y; wv[3][0] = w1.z; wv[3][1] = w1.w;
-                    } else {
 #pragma unroll
-                        for (int ch = 0; ch < 4; ++ch) {
-                            const float4 w4 = *reinterpret_cast<const float4 *>(wp + ch * KMAX);
-                            wv[ch][0] = w4.x; wv[ch][1] = w4.y; wv[ch][2] = w4.z; wv[ch][3] = w4.w;
-                        }
-                    }
+                    for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+                        for (int k = 0; k < KMAX; ++k) wv[ch][k] = wp[ch * KMAX + k];
 #pragma unroll
                     for (int px = 0; px < 4; ++px) {
                         const float4 av = a[px + dx];
