@@ -221,8 +221,6 @@ def op_bytes(o, esize):
         return B * o.Hin * o.Win * (o.C0 + o.Cout) * esize
     if o.kind == _lib.OP_HEAD:
         return B * o.Hin * o.Win * (4 * o.K + 2)
-    if o.kind == _lib.OP_OUT_HEAD:  # input once, labels in and out, the logits written for record runs
-        return B * o.Hin * o.Win * (o.C0 * esize + 4 * o.K + 2)
     return 0
 
 
@@ -234,8 +232,6 @@ def op_flops(o):
     if o.kind == _lib.OP_ATTENTION:
         T = o.Hin * o.Win
         return 4.0 * o.B * o.heads * T * T * o.head_dim
-    if o.kind == _lib.OP_OUT_HEAD:
-        return 2.0 * o.B * o.Hout * o.Wout * o.K * 9 * o.C0
     return 0.0
 
 
@@ -245,8 +241,6 @@ def op_class(o):
         return f"attention T={o.Hin * o.Win} heads={o.heads}"
     if o.kind == _lib.OP_HEAD:
         return f"head K={o.K}"
-    if o.kind == _lib.OP_OUT_HEAD:
-        return f"conv3x3 {o.C0}->{o.K} + head K={o.K} @{o.Hout}x{o.Wout} [fused, cuda cores]"
     if o.kind == _lib.OP_ENCODE_INPUT:
         return f"encode_input {o.K}+{o.C_img}->{o.Cout} planes @{o.Hout}x{o.Wout}"
     if o.kind == _lib.OP_INPUT_CONV:
@@ -423,10 +417,7 @@ def measure_workload(D, wl, precision, steps, warmup, batch=None, one_image=Fals
                              "tflops": wl["flops"] * B * T / (ms_step * 1e-3) / 1e12}
     if rank == 0 and dump_ops:
         with open(dump_ops, "w") as fh:
-            # (per-chain ops first -- they are launched right after the embedding table, before the first reverse step)
-            json.dump([dict(index=-1 - i, op_class="per-chain " + op_class(o), bytes=op_bytes(o, prog.esize), flops=op_flops(o), per_chain=True)
-                       for i, o in enumerate(prog._pre_array)] +
-                      [dict(index=i, op_class=op_class(prog._op_array[i]), bytes=op_bytes(prog._op_array[i], prog.esize),
+            json.dump([dict(index=i, op_class=op_class(prog._op_array[i]), bytes=op_bytes(prog._op_array[i], prog.esize),
                             flops=op_flops(prog._op_array[i])) for i in range(prog.n_ops)], fh, indent=0)
     if rank == 0 and op_profile_iters is not None:
         rows, step_ms_eager = per_op_profile(prof_engine, prog, n_iter=op_profile_iters)

@@ -15,7 +15,7 @@ DT_F32, DT_BF16, DT_F16X2 = 0, 1, 2
 F16X2_SCALE_LOG2 = 4
 DRAW_SAMPLE, DRAW_MAJORITY, DRAW_CONFIDENCE, DRAW_X0, DRAW_POSTERIOR = 0, 1, 2, 3, 4
 NOISE_TENSOR, NOISE_PHILOX = 0, 1
-OP_INPUT_CONV, OP_CONV, OP_ATTENTION, OP_HEAD, OP_ENCODE_INPUT, OP_OUT_HEAD = 1, 2, 3, 4, 5, 6
+OP_INPUT_CONV, OP_CONV, OP_ATTENTION, OP_HEAD, OP_ENCODE_INPUT = 1, 2, 3, 4, 5
 ABI_VERSION = 4
 
 
@@ -95,7 +95,6 @@ def lib():
     L.ccdm_op_part_floats.argtypes = [ctypes.POINTER(Op)]
     L.ccdm_conv_uses_tc.argtypes = [ctypes.POINTER(Op)]
     L.ccdm_conv_uses_tma.argtypes = [ctypes.POINTER(Op)]
-    L.ccdm_out_head_supported.argtypes = [ctypes.POINTER(Op)]
     L.ccdm_conv_stat_layout.argtypes = [ctypes.POINTER(Op), ctypes.POINTER(ctypes.c_int32)]
     L.ccdm_conv_tc_nt.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
     L.ccdm_conv_tc_config.argtypes = [ctypes.POINTER(Op), ctypes.POINTER(ctypes.c_int32)]

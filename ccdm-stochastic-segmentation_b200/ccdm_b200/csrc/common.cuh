@@ -33,8 +33,6 @@ int launch_conv(const ccdm_op &op, cudaStream_t s);
 int launch_attention(const ccdm_op &op, cudaStream_t s);
 int launch_head(const ccdm_op &op, cudaStream_t s);
 int launch_encode_input(const ccdm_op &op, cudaStream_t s);
-int launch_out_head(const ccdm_op &op, cudaStream_t s);
-bool out_head_supported(const ccdm_op &op);
 
 // ---- programmatic dependent launch (PDL) -----------------------------------------
 // Every kernel of the reverse step is launched with programmatic stream serialization: the next kernel's

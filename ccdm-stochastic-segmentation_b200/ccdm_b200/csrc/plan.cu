@@ -46,7 +46,6 @@ static int launch_any(const ccdm_op &op, cudaStream_t s) {
         case CCDM_OP_CONV: return launch_conv(op, s);
         case CCDM_OP_ATTENTION: return launch_attention(op, s);
         case CCDM_OP_HEAD: return launch_head(op, s);
-        case CCDM_OP_OUT_HEAD: return launch_out_head(op, s);
         case CCDM_OP_ENCODE_INPUT: return launch_encode_input(op, s);
         default: CCDM_FAIL(-2, "unknown op kind %d", op.kind);
     }
@@ -80,7 +79,6 @@ extern "C" int ccdm_conv_tc_config(const ccdm_op *op, int32_t *out16) {
     return ccdm::conv_tma_config(*op, out16);
 }
 extern "C" int ccdm_conv_uses_tma(const ccdm_op *op) { return op && ccdm::conv_uses_tma(*op) ? 1 : 0; }
-extern "C" int ccdm_out_head_supported(const ccdm_op *op) { return op && ccdm::out_head_supported(*op) ? 1 : 0; }
 namespace ccdm { int conv_tma_stat_layout(const ccdm_op &op, int32_t *out5); }
 extern "C" int ccdm_conv_stat_layout(const ccdm_op *op, int32_t *out5) {
     if (!op || !out5 || !ccdm::conv_uses_tc(*op)) return -1;
@@ -132,7 +130,7 @@ extern "C" int ccdm_plan_set_noise(ccdm_plan *plan, int noise_mode, uint64_t see
     if (!plan) CCDM_FAIL(-1, "null plan");
     bool changed = false;
     for (auto &op : plan->ops) {
-        if (op.kind != CCDM_OP_HEAD && op.kind != CCDM_OP_OUT_HEAD) continue;
+        if (op.kind != CCDM_OP_HEAD) continue;
         if (op.noise_mode != noise_mode || op.seed != seed || op.sample0 != sample0 || op.noise != (uint64_t)noise ||
             op.noise_out != (uint64_t)noise_out)
             changed = true;

@@ -214,12 +214,6 @@ def subpixel_weights(w: torch.Tensor) -> torch.Tensor:
 _FOLD_FEAT = os.environ.get("CCDM_FOLD_FEAT", "1") != "0"
 
 
-# Output conv + categorical head as one CUDA-core launch where the class count is small (K <= 4, `exact` mode): the tensor-core
-# conv pays for nine shifted A-operand fetches per 16 input channels whatever the number of output channels is.
-# CCDM_FUSE_HEAD=0 keeps the two launches (A/B).
-_FUSE_HEAD = os.environ.get("CCDM_FUSE_HEAD", "1") != "0"
-
-
 def feat_fold_split(c_h: int, f: int):
     """GroupNorm(32) over cat[h (c_h channels), features (f channels)]: (channels per group, number of leading feature channels
     that share a group with h, that number rounded up to a K chunk of 16)."""
@@ -585,19 +579,10 @@ class Program:
                 hs.append(h)
                 h.last = 10 ** 9  # provisional: popped later, fixed when consumed
         assert (ch, cw) == (H, W) and not hs
-        fused_head = dict(kind=_lib.OP_OUT_HEAD, dtype=self.dt, B=B, ksize=3, stride=1, gn=1, silu=1, Hin=H, Win=W, Hout=H, Wout=W,
-                          C0=h.C, Cout=self.K, K=self.K)
-        self.fused_head = bool(engine.fuse_head and self.x3 and L.ccdm_out_head_supported(ctypes.byref(Op(**fused_head))))
-        if self.fused_head:
-            # (the logits are still written -- 4 K bytes per pixel -- so that record / trace runs see them)
-            fused_head.pop("kind"); fused_head.pop("dtype"); fused_head.pop("B"); fused_head.pop("C0")
-            emit(_lib.OP_OUT_HEAD, [h], new("logits", self.K, H, W, stat=False, esize=4), _src=[h], _g="out:g", _be="out:be",
-                 _w="out:w", _b="out:b", out_dtype=_lib.DT_F32, **fused_head)
-        else:
-            logits = emit(_lib.OP_CONV, [h], new("logits", self.K, H, W, stat=False, esize=4), ksize=3, stride=1, gn=1, silu=1,
-                          Hin=H, Win=W, Hout=H, Wout=W, Cout=self.K, _src=[h], _g="out:g", _be="out:be", _w="out:w", _b="out:b",
-                          out_dtype=_lib.DT_F32)
-            emit(_lib.OP_HEAD, [logits], None, Hin=H, Win=W, K=self.K, _src=[logits])
+        logits = emit(_lib.OP_CONV, [h], new("logits", self.K, H, W, stat=False, esize=4), ksize=3, stride=1, gn=1, silu=1,
+                      Hin=H, Win=W, Hout=H, Wout=W, Cout=self.K, _src=[h], _g="out:g", _be="out:be", _w="out:w", _b="out:b",
+                      out_dtype=_lib.DT_F32)
+        emit(_lib.OP_HEAD, [logits], None, Hin=H, Win=W, K=self.K, _src=[logits])
 
         # skip tensors: recompute true last use (emit() already recorded every reader)
         for t in tens:
@@ -700,7 +685,7 @@ class Program:
             fields.update(f)
             op = Op(**fields)
             src = o.get("_src", [])
-            if o["kind"] in (_lib.OP_CONV, _lib.OP_ATTENTION, _lib.OP_OUT_HEAD):
+            if o["kind"] in (_lib.OP_CONV, _lib.OP_ATTENTION):
                 op.src0, op.C0 = src[0].addr, src[0].C
                 if len(src) > 1:
                     op.src1, op.C1 = src[1].addr, src[1].C
@@ -716,9 +701,7 @@ class Program:
         # pass 1: which convs land on the tensor-core kernel.  Everything downstream -- weight layout, statistics layout of
         # the INPUT tensors -- follows from this, so it is decided before anything is bound.
         all_dicts = self._op_dicts + self._pre_dicts  # the per-chain ops (run_pre) are bound like the step's, behind them
-        # (the fused output head folds deferred statistics rows with the same code as the tensor-core conv: it counts as one here)
-        use_tc = [bool(self.exact == 0 and ((o["kind"] == _lib.OP_CONV and L.ccdm_conv_uses_tc(ctypes.byref(base_op(o)))) or
-                                            o["kind"] == _lib.OP_OUT_HEAD))
+        use_tc = [bool(self.exact == 0 and o["kind"] == _lib.OP_CONV and L.ccdm_conv_uses_tc(ctypes.byref(base_op(o))))
                   for o in all_dicts]
         off_tc = [i for i, o in enumerate(all_dicts) if self.exact == 0 and o["kind"] == _lib.OP_CONV and not use_tc[i]]
         if off_tc:
@@ -735,7 +718,7 @@ class Program:
         # AND every GroupNorm consumer is one too: the FFMA kernel reads folded double2 sums
         gn_readers: Dict[int, List[int]] = {}
         for i, o in enumerate(all_dicts):
-            if o["kind"] in (_lib.OP_CONV, _lib.OP_OUT_HEAD) and o.get("gn"):
+            if o["kind"] == _lib.OP_CONV and o.get("gn"):
                 for sten in o.get("_src", [])[:2]:
                     gn_readers.setdefault(id(sten), []).append(i)
 
@@ -746,7 +729,7 @@ class Program:
             if o["kind"] in (_lib.OP_INPUT_CONV, _lib.OP_ENCODE_INPUT):
                 op.labels_in = self.addr["labels"]
                 op.image = self.addr["image"]
-            if o["kind"] in (_lib.OP_CONV, _lib.OP_OUT_HEAD) and o.get("gn"):
+            if o["kind"] == _lib.OP_CONV and o.get("gn"):
                 for si, sten in enumerate(src[:2]):
                     if sten.stat_layout is not None:  # the producer left per-CTA partial rows: this op folds them
                         assert use_tc[i]
@@ -760,13 +743,12 @@ class Program:
             # attention: exact=0 selects the tcgen05 kernel (head_dim 32); head: exact=0 selects fast maths for sampling steps
             if o["kind"] == _lib.OP_CONV and not use_tc[i]:
                 op.exact = 1
-            if o["kind"] in (_lib.OP_HEAD, _lib.OP_OUT_HEAD) and self.x3:
+            if o["kind"] == _lib.OP_HEAD and self.x3:
                 op.exact = 1  # the exact tensor-core mode draws with the bit-exact posterior arithmetic
             if use_tc[i] and self.x3:
                 op.acc_shift = W.shift + _lib.F16X2_SCALE_LOG2
             if "_w" in o:
-                tc_w = use_tc[i] and o["kind"] == _lib.OP_CONV  # (the fused output head reads the fp32 [tap][Cin][32] layout)
-                op.weight, op.bias = (W.addr16(o["_w"]) if tc_w else W.addr(o["_w"])), W.addr(o["_b"])
+                op.weight, op.bias = (W.addr16(o["_w"]) if use_tc[i] else W.addr(o["_w"])), W.addr(o["_b"])
             if o.get("_emb"):
                 op.emb = self.emb_buf.data_ptr()
                 op.emb_cols = emb_cols
@@ -798,7 +780,7 @@ class Program:
                     op.ostat = out.stat_addr
                     op.part = 1  # patched below once the scratch size is known
                     op.ticket = self.addr["ticket"]
-            if o["kind"] in (_lib.OP_HEAD, _lib.OP_OUT_HEAD):
+            if o["kind"] == _lib.OP_HEAD:
                 op.src0 = src[0].addr
                 op.labels_in = self.addr["labels"]
                 op.labels_out = self.addr["labels"]
@@ -813,7 +795,7 @@ class Program:
         self.part_buf = torch.zeros(part_floats, dtype=torch.float32, device=dev)
         for i in shared:
             arr[i].part = self.part_buf.data_ptr()
-        self.n_tc = sum(1 for i in range(self.n_ops) if use_tc[i] and all_dicts[i]["kind"] == _lib.OP_CONV)
+        self.n_tc = sum(use_tc[:self.n_ops])
         self._op_array = (Op * self.n_ops)(*arr[:self.n_ops])
         self._pre_array = arr[self.n_ops:]
         self.plan = L.ccdm_plan_create(self._op_array, self.n_ops)
@@ -835,7 +817,7 @@ class Program:
         _lib.check(L.ccdm_plan_set_noise(self.plan, noise_mode, int(seed), int(sample0), ctypes.c_void_p(nz or None),
                                          ctypes.c_void_p(nz_out or None)), "plan_set_noise")
         for i in range(self.n_ops):
-            if self._op_array[i].kind in (_lib.OP_HEAD, _lib.OP_OUT_HEAD):
+            if self._op_array[i].kind == _lib.OP_HEAD:
                 o = self._op_array[i]
                 o.noise_mode, o.seed, o.sample0, o.noise, o.noise_out = noise_mode, int(seed), int(sample0), nz, nz_out
 
@@ -884,12 +866,11 @@ class UNetEngine:
         # run the feature-concat ResBlock in its folded form (constant DINO channels as per-chain maps); False keeps
         # the per-step 448-channel concatenation (A/B, tests)
         self.fold_features = _FOLD_FEAT
-        self.fuse_head = _FUSE_HEAD  # output conv + categorical head as one launch where supported (K <= 4, `exact` mode)
         self._children: List["UNetEngine"] = []
 
     # -- helpers ----------------------------------------------------------------------
     def program(self, B, H, W, rows_per_sample=0, img_rep=1) -> Program:
-        key = (B, H, W, rows_per_sample, img_rep, self.tile_batch, self.fold_features, self.fuse_head)
+        key = (B, H, W, rows_per_sample, img_rep, self.tile_batch, self.fold_features)
         prog = self.programs.get(key)
         if prog is None:
             # bounded cache: a ragged last batch or a change of batch size must not pile up ~1 GB workspaces
@@ -996,7 +977,7 @@ class UNetEngine:
             c.dry_run, c.unet, c.precision, c.device, c.weights = False, self.unet, self.precision, self.device, self.weights
             c.programs, c.stream, c.use_graph, c.lanes, c._children = OrderedDict(), torch.cuda.Stream(device=self.device), self.use_graph, 1, []
             c.tile_batch = self.tile_batch
-            c.fold_features, c.fuse_head = self.fold_features, self.fuse_head
+            c.fold_features = self.fold_features
             self._children.append(c)
         for c in self._children:
             c.use_graph = self.use_graph

@@ -80,11 +80,6 @@ typedef struct ccdm_step_entry {
                                   Cout = ceil16(K + C_img) channels (zero padded), the input of input_blocks[0] run as
                                   an ordinary tensor-core conv */
 
-#define CCDM_OP_OUT_HEAD 6   /* fp16x2 mode, K <= 4: the output head (unet.py:701-707: GN + SiLU + conv3x3 C -> K, softmax) AND the
-                                categorical head (diffusion_denoising.py:197-212) in one launch on the CUDA cores; fields: src0 /
-                                stat0 / gamma / beta as a conv with gn = silu = 1, weight = fp32 [9][C][32], bias fp32 [32], out =
-                                fp32 logits [B,H,W,K] (optional), and every field of CCDM_OP_HEAD */
-
 typedef struct ccdm_op {
     int32_t kind; /* CCDM_OP_* */
     int32_t dtype; /* CCDM_DT_* of activations in/out */
@@ -181,8 +176,6 @@ int ccdm_conv_tc_config(const ccdm_op *op, int32_t *out16);
 /* Deferred-fold layout of the statistics a tensor-core conv `op` writes to `part`: out5 = {slots, items per sample,
  * items, grid, row length}; the consumer's st_* fields.  Returns -1 if `op` does not run on a tensor-core kernel. */
 int ccdm_conv_stat_layout(const ccdm_op *op, int32_t *out5);
-/* 1 if `op` (kind CCDM_OP_OUT_HEAD) is a configuration the fused output-conv + head kernel takes. */
-int ccdm_out_head_supported(const ccdm_op *op);
 /* 0 if the current device is compute capability 10.x, negative otherwise. */
 int ccdm_check_device(void);
 

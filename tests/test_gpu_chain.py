@@ -462,40 +462,3 @@ def test_feature_fold_equals_the_per_step_concatenation(cuda_device, prec):
     _report(f"feature_fold_{prec}", folded_vs_unfolded=d, folded_vs_fixture=e[0], unfolded_vs_fixture=e[1])
     tol = X0_TOL if prec != "bf16" else 6e-2
     assert d <= tol and e[0] <= tol and e[1] <= tol, (d, e)
-
-
-@pytest.mark.parametrize("tag", ["lidc64", "lidc128"])
-def test_fused_output_head_equals_conv_plus_head(cuda_device, tag):
-    """`exact` mode, K <= 4: the output conv + categorical head as ONE CUDA-core launch (CCDM_OP_OUT_HEAD, the default) against
-    the tensor-core output conv followed by head_kernel (engine.fuse_head = False): same logits to fp32 rounding, same
-    probabilities, and the labels drawn from the same Philox noise agree except on near-ties of the race."""
-    from ccdm_b200 import _lib
-    T, B, C_img, H, W, K, fce, mult, t_probe, steps = GOLDEN_CASES[tag]
-    m, image, feat, labels = _case(tag)
-    eng = m.unet.engine("exact")
-    al, ca = m._schedule_host()
-    res = {}
-    for fuse in (True, False):
-        eng.fuse_head = fuse
-        prog = eng.program(B, H, W, rows_per_sample=0)
-        assert prog.fused_head == fuse
-        kinds = [o["kind"] for o in prog._op_dicts]
-        assert (kinds[-1] == _lib.OP_OUT_HEAD) if fuse else (kinds[-2:] == [_lib.OP_CONV, _lib.OP_HEAD])
-        t = 37
-        tr = eng.trace_step(labels.cuda(), image.cuda(), None, float(t), alpha=al[t - 1], cumalpha=ca[t - 2], mode=_lib.DRAW_SAMPLE)
-        res[fuse] = (tr["logits"].cpu(), tr["labels"].cpu())
-        tr0 = eng.trace_step(labels.cuda(), image.cuda(), None, float(t), mode=_lib.DRAW_X0)
-        res[fuse] += (tr0["probs"].cpu(),)
-    eng.fuse_head = True
-    d_logit = float((res[True][0] - res[False][0]).abs().max())
-    d_prob = float((res[True][2] - res[False][2]).abs().max())
-    agree = float((res[True][1] == res[False][1]).float().mean())
-    _report(f"fused_head_{tag}", logits_max_abs_diff=d_logit, probs_max_abs_diff=d_prob, label_agreement=agree)
-    assert d_logit <= 2e-5 * max(1.0, float(res[False][0].abs().max())) and d_prob <= 1e-5 and agree >= 0.9995, (d_logit, d_prob, agree)
-    # and the fused path against the reference fixture, like test_unet_matches_reference_fixture
-    g = golden(tag + ".npz")
-    m.unet.precision = "exact"
-    x = _onehot(labels, K).cuda()
-    for t in t_probe:
-        p = m.unet(x, image.cuda(), None, torch.full((B,), float(t)).cuda())["diffusion_out"]
-        assert np.abs(p.permute(0, 2, 3, 1).cpu().numpy() - g[f"x0pred_t{t}"]).max() <= X0_TOL
