@@ -417,7 +417,10 @@ def measure_workload(D, wl, precision, steps, warmup, batch=None, one_image=Fals
                              "tflops": wl["flops"] * B * T / (ms_step * 1e-3) / 1e12}
     if rank == 0 and dump_ops:
         with open(dump_ops, "w") as fh:
-            json.dump([dict(index=i, op_class=op_class(prog._op_array[i]), bytes=op_bytes(prog._op_array[i], prog.esize),
+            # (per-chain ops first -- they are launched right after the embedding table, before the first reverse step)
+            json.dump([dict(index=-1 - i, op_class="per-chain " + op_class(o), bytes=op_bytes(o, prog.esize), flops=op_flops(o), per_chain=True)
+                       for i, o in enumerate(prog._pre_array)] +
+                      [dict(index=i, op_class=op_class(prog._op_array[i]), bytes=op_bytes(prog._op_array[i], prog.esize),
                             flops=op_flops(prog._op_array[i])) for i in range(prog.n_ops)], fh, indent=0)
     if rank == 0 and op_profile_iters is not None:
         rows, step_ms_eager = per_op_profile(prof_engine, prog, n_iter=op_profile_iters)

@@ -45,7 +45,7 @@ def step(metrics_csv, ops_json, out_json):
         out.append(rec)
         a = agg.setdefault(o["op_class"], dict(launches=0, ns=0.0, dram_bytes=0.0, algorithmic_bytes=0))
         a["launches"] += 1; a["ns"] += t; a["dram_bytes"] += dram; a["algorithmic_bytes"] += o["bytes"]
-    total_ns = sum(r["ns"] for r in out)
+    total_ns = sum(r["ns"] for r in out if r["index"] >= 0)  # one reverse step (per-chain ops, index < 0, are listed but not part of it)
     for a in agg.values():
         a["share_of_step"] = a["ns"] / total_ns
         a["dram_bytes_per_launch"] = a["dram_bytes"] / a["launches"]
