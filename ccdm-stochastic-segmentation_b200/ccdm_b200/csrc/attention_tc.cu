@@ -14,8 +14,6 @@
 // tile max / running sum, P = exp2((S - m) * log2(e)/sqrt(32)) as bf16 into shared memory (K-major A operand)
 // ->  O += P V (tcgen05.mma accumulating in TMEM over ALL tiles; m is a reference maximum that may lag the row's
 // true maximum by 2^8, a row rescales l and its TMEM lane only when a tile exceeds it by more -- see the main loop).
-// MMA issue is spread over the warps: one thread issues at most one tcgen05.mma per ~125 cycles (profiles/r02_mma_rate.txt),
-// so lane 0 of 2-4 warps each issue a share of the P V K-steps into a private accumulator while warp 0 issues S(t+1).
 // Several CTAs are resident per SM (TMEM: 256 of 512 columns each at NK = 128), so one CTA's softmax overlaps
 // another's MMAs and loads.
 //
@@ -102,15 +100,9 @@ __global__ void __launch_bounds__(AT_QT, D > 32 ? (X3 ? 1 : 2) : (X3 ? 2 : 3)) a
     uint8_t *sV = sK + 2 * KV_BYTES;   // [2][KV_BYTES]
     uint8_t *sP = sV + 2 * KV_BYTES;   // [NK/8 planes][128 rows][16 B]
     uint64_t *bars = reinterpret_cast<uint64_t *>(sP + P_BYTES);
-    uint64_t *kv_full = bars, *s_done = bars + 2, *pv_done = bars + 3;
+    uint64_t *kv_full = bars, *s_done = bars + 2, *o_done = bars + 3;
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 4);
-    // A thread can issue one tcgen05.mma per ~125 cycles whatever its shape (tools/micro/mma_rate.cu: 124.7 cycles per MMA from
-    // one thread, 62.3 from two, 31.2 from four), so the NK/16 x (1 | 3) MMAs of P V are issued by lane 0 of NP warps, each
-    // accumulating its share of the K steps into ITS OWN accumulator (a fixed summation order: results stay bit-reproducible);
-    // the row sums the NP partials when it reads O back.  Warp 0 issues S(t+1) in front of its share.
-    constexpr int NP = X3 ? (D > 32 ? 2 : 4) : (NK == 128 ? 4 : 2);  // (chosen so that no variant needs more TMEM columns per SM than before)
-    constexpr uint32_t TMEM_NEED = NK + NP * D;
-    constexpr uint32_t TMEM_COLS = TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512));
+    constexpr uint32_t TMEM_COLS = NK + D <= 64 ? 64 : (NK + D <= 128 ? 128 : 256);
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int qt = blockIdx.x % p.q_tiles, bh = blockIdx.x / p.q_tiles;
@@ -128,7 +120,7 @@ __global__ void __launch_bounds__(AT_QT, D > 32 ? (X3 ? 1 : 2) : (X3 ? 2 : 3)) a
         mbar_init(kv_full + 0, 1);
         mbar_init(kv_full + 1, 1);
         mbar_init(s_done, 1);
-        mbar_init(pv_done, NP);
+        mbar_init(o_done, 1);
         fence_barrier_init();
     }
     // rows of a partial tile that no copy overwrites must hold finite values (0 * NaN would poison P V)
@@ -141,23 +133,13 @@ __global__ void __launch_bounds__(AT_QT, D > 32 ? (X3 ? 1 : 2) : (X3 ? 2 : 3)) a
     pdl_launch_dependents();
     pdl_wait();  // qkv is written by the previous kernel of the step
     const uint32_t trow = uint32_t(warp * 32) << 16;  // this warp's TMEM lane quarter
-    auto ld_part = [&](int w, float *dst) {  // partial accumulator w of this thread's row
+    auto ld_o = [&](float *dst) {
 #pragma unroll
-        for (int d0 = 0; d0 < AT_D; d0 += 32) tmem_ld32(tmem_o + trow + uint32_t(w * AT_D + d0), dst + d0);
+        for (int d0 = 0; d0 < AT_D; d0 += 32) tmem_ld32(tmem_o + trow + uint32_t(d0), dst + d0);
     };
-    auto st_part = [&](int w, const float *src) {
+    auto st_o = [&](const float *src) {
 #pragma unroll
-        for (int d0 = 0; d0 < AT_D; d0 += 32) tmem_st32(tmem_o + trow + uint32_t(w * AT_D + d0), src + d0);
-    };
-    auto ld_o = [&](float *dst) {  // the row's O: the partials added in a fixed order
-        ld_part(0, dst);
-#pragma unroll
-        for (int w = 1; w < NP; ++w) {
-            float tmp[AT_D];
-            ld_part(w, tmp);
-#pragma unroll
-            for (int d = 0; d < AT_D; ++d) dst[d] += tmp[d];
-        }
+        for (int d0 = 0; d0 < AT_D; d0 += 32) tmem_st32(tmem_o + trow + uint32_t(d0), src + d0);
     };
 
     auto load_kv = [&](int t, int buf, uint32_t extra_bytes) {  // thread 0
@@ -229,8 +211,7 @@ __global__ void __launch_bounds__(AT_QT, D > 32 ? (X3 ? 1 : 2) : (X3 ? 2 : 3)) a
     for (int t = 0; t < n_tiles; ++t) {
         const int buf = t & 1;
         const int nk = min(NK, T - t * NK);
-        mbar_wait(s_done, uint32_t(t) & 1u);             // S(t) is complete
-        if (t > 0) mbar_wait(pv_done, uint32_t(t - 1) & 1u);  // ... and P V(t-1), whichever warp issued its parts
+        mbar_wait(s_done, uint32_t(t) & 1u);  // S(t) is complete -- and with it every MMA issued before it, P V(t-1) included
         tc_fence_after();
         if (tid == 0 && t >= 1 && t + 1 < n_tiles) load_kv(t + 1, buf ^ 1, 0u);  // that buffer's readers (S, P V of tile t-1) have completed
         const bool flushed = X3 && t > 0 && (t % FLUSH) == 0;  // (uniform) O is quiescent here: P V(t-1) has completed, P V(t) is not issued yet
@@ -264,14 +245,11 @@ __global__ void __launch_bounds__(AT_QT, D > 32 ? (X3 ? 1 : 2) : (X3 ? 2 : 3)) a
                 if (t > 0) {
                     const float corr = ex2_approx((m - m_new) * c);  // 1 on the lanes that keep their maximum
                     if (!flushed) {  // (after a flush TMEM holds nothing that counts: the next P V overwrites it)
+                        float ot[AT_D];
+                        ld_o(ot);
 #pragma unroll
-                        for (int w = 0; w < NP; ++w) {
-                            float ot[AT_D];
-                            ld_part(w, ot);
-#pragma unroll
-                            for (int d = 0; d < AT_D; ++d) ot[d] *= corr;
-                            st_part(w, ot);
-                        }
+                        for (int d = 0; d < AT_D; ++d) ot[d] *= corr;
+                        st_o(ot);
                     }
                     if constexpr (X3) {
 #pragma unroll
@@ -321,25 +299,20 @@ __global__ void __launch_bounds__(AT_QT, D > 32 ? (X3 ? 1 : 2) : (X3 ? 2 : 3)) a
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();  // P (and a rescaled O) complete and visible to the tensor core; every thread is done reading S
-        if ((tid & 31) == 0 && warp < NP) {
+        if (tid == 0) {
             tc_fence_after();
-            // S(t+1) first: it overwrites S, which every thread finished reading before the barrier above, and the next
-            // tile's softmax waits for nothing else; P is rewritten only after P V(t) has completed (pv_done)
-            if (warp == 0 && t + 1 < n_tiles) issue_s(t + 1);
             const uint32_t v_lo = (smem_u32(sV + buf * KV_BYTES) >> 4) | (8u << 16);  // LBO = 128 B between groups of 8 keys
-            const uint32_t d_part = tmem_o + uint32_t(warp * AT_D);
-            bool first = true;
 #pragma unroll
             for (int j = 0; j < NK / 16; ++j)
-                if (j % NP == warp) {
-                    mma(d_part, p_lo + uint32_t(j * 2 * X * AT_QT), desc_hi, uint32_t(AT_QT), v_lo + uint32_t(j * 16), v_hi, uint32_t(NK), p.idesc_pv,
-                        ((t > 0 && !flushed) || !first) ? 1u : 0u);
-                    first = false;
-                }
-            umma_commit(pv_done);
+                mma(tmem_o, p_lo + uint32_t(j * 2 * X * AT_QT), desc_hi, uint32_t(AT_QT), v_lo + uint32_t(j * 16), v_hi, uint32_t(NK), p.idesc_pv,
+                    ((t > 0 && !flushed) || j > 0) ? 1u : 0u);
+            // S(t+1) right behind it: it overwrites S, which every thread finished reading before the barrier above; P is
+            // rewritten only after S(t+1) -- and so P V(t) -- has completed
+            if (t + 1 < n_tiles) issue_s(t + 1);
+            else umma_commit(o_done);
         }
     }
-    mbar_wait(pv_done, uint32_t(n_tiles - 1) & 1u);
+    mbar_wait(o_done, 0u);
     tc_fence_after();
     {
         float ot[AT_D];
