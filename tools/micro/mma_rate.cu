@@ -30,10 +30,12 @@ __device__ __forceinline__ void commit(uint64_t *bar) {
 // mode 1: A, B in shared memory, K-major SWIZZLE_128B (rows of 128 B, SBO = 1024 B; the K = 16 step is 32 B inside the row)
 // mode 2: A in tensor memory (columns 256..263), B in shared memory no swizzle
 // shift: extra 16-byte rows added to the A start address per MMA (0, or 1 = the "shifted window" of a 3x3 tap)
-__global__ void __launch_bounds__(128) rate_kernel(int mode, int N, int n_mma, int shift, unsigned long long *out) {
+// n_acc: accumulators the MMAs rotate over (1 = every MMA accumulates onto the previous one's result: a dependent chain)
+// n_issue: issuing threads (lane 0 of the first n_issue warps), each with its own accumulator(s) and its own commit barrier
+__global__ void __launch_bounds__(128) rate_kernel(int mode, int N, int n_mma, int shift, int n_acc, int n_issue, unsigned long long *out) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + 8);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem);  // [4]
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + 64);
     uint8_t *sA = smem + 1024;             // 64 KB region
     uint8_t *sB = smem + 1024 + 65536;     // 64 KB region
     for (int i = threadIdx.x * 16; i < 2 * 65536; i += 128 * 16) *reinterpret_cast<uint4 *>(sA + i) = make_uint4(0, 0, 0, 0);
@@ -42,7 +44,7 @@ __global__ void __launch_bounds__(128) rate_kernel(int mode, int N, int n_mma, i
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
+        for (int w = 0; w < 4; ++w) mbar_init(bar + w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -50,7 +52,9 @@ __global__ void __launch_bounds__(128) rate_kernel(int mode, int N, int n_mma, i
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *s_tmem;
-    if (threadIdx.x == 0) {
+    const int w = threadIdx.x >> 5;
+    __shared__ long long t_begin[4], t_end[4];
+    if ((threadIdx.x & 31) == 0 && w < n_issue) {
         const uint32_t idesc = (1u << 4) | (uint32_t(N >> 3) << 17) | (uint32_t(128 >> 4) << 24);  // f16 x f16 -> f32, K-major both
         uint64_t a_desc, b_desc;
         if (mode == 1) {
@@ -64,22 +68,38 @@ __global__ void __launch_bounds__(128) rate_kernel(int mode, int N, int n_mma, i
             a_desc = hi | uint64_t((smem_u32(sA) & 0x3FFFF) >> 4);
             b_desc = hi | uint64_t((smem_u32(sB) & 0x3FFFF) >> 4);
         }
-        // warm-up
-        for (int i = 0; i < 64; ++i) {
-            if (mode == 2) mma_ts(tmem, tmem + 256, b_desc, idesc, 1u);
-            else mma_ss(tmem, a_desc, b_desc, idesc, 1u);
+        const uint32_t a_tmem = tmem + 496;  // A operand in tensor memory: 8 columns behind every accumulator
+        const uint32_t d0 = tmem + uint32_t(w * n_acc * N);
+        for (int i = 0; i < 48; ++i) {  // warm-up
+            if (mode == 2) mma_ts(d0, a_tmem, b_desc, idesc, 1u);
+            else mma_ss(d0, a_desc, b_desc, idesc, 1u);
         }
-        commit(bar);
-        mbar_wait(bar, 0);
-        const long long t0 = clock64();
-        for (int i = 0; i < n_mma; ++i) {
-            if (mode == 2) mma_ts(tmem, tmem + 256, b_desc, idesc, 1u);
-            else mma_ss(tmem, a_desc + uint64_t((i % 3) * shift), b_desc, idesc, 1u);
+        commit(bar + w);
+        mbar_wait(bar + w, 0);
+        // 12 MMAs per loop iteration, operands precomputed: the issuing thread's own instructions must not be what is measured
+        const uint64_t a3[3] = {a_desc, a_desc + uint64_t(shift), a_desc + uint64_t(2 * shift)};
+        uint32_t dj[12];
+        for (int u = 0; u < 12; ++u) dj[u] = d0 + uint32_t((u % n_acc) * N);
+        t_begin[w] = clock64();
+        for (int i = 0; i < n_mma; i += 12) {
+#pragma unroll
+            for (int u = 0; u < 12; ++u) {
+                if (mode == 2) mma_ts(dj[u], a_tmem, b_desc, idesc, 1u);
+                else mma_ss(dj[u], a3[u % 3], b_desc, idesc, 1u);
+            }
         }
-        commit(bar);
-        mbar_wait(bar, 1);
-        const long long t1 = clock64();
-        out[0] = (unsigned long long)(t1 - t0);
+        commit(bar + w);
+        mbar_wait(bar + w, 1);
+        t_end[w] = clock64();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long b0 = t_begin[0], e0 = t_end[0];
+        for (int k = 1; k < n_issue; ++k) {
+            b0 = t_begin[k] < b0 ? t_begin[k] : b0;
+            e0 = t_end[k] > e0 ? t_end[k] : e0;
+        }
+        out[0] = (unsigned long long)(e0 - b0);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -95,23 +115,37 @@ int main() {
     const size_t smem = 1024 + 2 * 65536;
     cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const char *names[3] = {"A,B smem  K-major no-swizzle", "A,B smem  K-major SWIZZLE_128B", "A tmem, B smem no-swizzle"};
-    const int n_mma = 4096;
-    printf("tcgen05.mma.cta_group::1.kind::f16, M = 128, K = 16, one issuing thread, %d back-to-back MMAs into one accumulator\n", n_mma);
+    const int n_mma = 4092;
+    printf("tcgen05.mma.cta_group::1.kind::f16, M = 128, K = 16: cycles per MMA on one SM\n");
     printf("(math floor at 8192 dense fp16 FLOP/clk/SM: N / 2 cycles)\n");
-    for (int mode = 0; mode < 3; ++mode)
-        for (int shift = 0; shift <= (mode == 0 ? 1 : 0); ++shift) {
-            printf("%-32s%s:", names[mode], shift ? " (A start +0/+1/+2 rows per MMA)" : "");
-            for (int N : {16, 32, 64, 96, 128, 192, 256}) {
-                rate_kernel<<<1, 128, smem>>>(mode, N, n_mma, shift, d);
-                cudaError_t e = cudaDeviceSynchronize();
-                if (e != cudaSuccess) {
-                    printf(" N=%d: %s\n", N, cudaGetErrorString(e));
-                    return 1;
+    for (int n_issue = 1; n_issue <= 4; n_issue *= 2) {
+        printf("-- %d issuing thread(s), %d MMAs each, one accumulator per thread (N <= 120 so that four fit)\n", n_issue, n_mma);
+        for (int mode = 0; mode < 3; ++mode)
+            for (int shift = 0; shift <= (mode == 0 ? 1 : 0); ++shift) {
+                printf("%-32s%s:", names[mode], shift ? " (A start +0/+1/+2 rows per MMA)" : "");
+                for (int N : {16, 32, 64, 96, 120}) {
+                    rate_kernel<<<1, 128, smem>>>(mode, N, n_mma, shift, 1, n_issue, d);
+                    cudaError_t e = cudaDeviceSynchronize();
+                    if (e != cudaSuccess) {
+                        printf(" N=%d: %s\n", N, cudaGetErrorString(e));
+                        return 1;
+                    }
+                    cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+                    printf("  N=%d: %.1f", N, double(h) / (double(n_mma) * n_issue));
                 }
-                cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
-                printf("  N=%d: %.1f", N, double(h) / n_mma);
+                printf("  cycles per MMA (all threads together)\n");
             }
-            printf("  cycles/MMA\n");
+    }
+    printf("-- 1 issuing thread, one accumulator, large N\n");
+    for (int mode = 0; mode < 3; mode += 2) {
+        printf("%-32s:", names[mode]);
+        for (int N : {128, 192, 256}) {
+            rate_kernel<<<1, 128, smem>>>(mode, N, n_mma, 0, 1, 1, d);
+            if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+            cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+            printf("  N=%d: %.1f", N, double(h) / n_mma);
         }
+        printf("  cycles per MMA\n");
+    }
     return 0;
 }
