@@ -432,3 +432,28 @@ def test_feature_fold_is_planned_for_the_dino_block():
         folded = [o for o in prog._op_array if o.kind == _lib.OP_CONV and o.gn_cpg > 0]
         assert len(folded) == 1 and (folded[0].C0, folded[0].C1, folded[0].gn_cpg, folded[0].gn_off) == (64, 16, 14, 0)
         assert not [o for o in prog._op_array if o.kind == _lib.OP_CONV and (o.C0 + o.C1 > 256 or o.S0 + o.S1 > 256)]  # no 448-channel op is left
+
+
+def test_docs_quote_the_current_abi_version():
+    """INTEGRATION.md's binding snippet asserts the ABI version: it must be the one the header defines and _lib.py checks."""
+    import re
+    from ccdm_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "ccdm_b200.h")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    v_hdr = int(re.search(r"#define CCDM_ABI_VERSION (\d+)", hdr).group(1))
+    v_doc = [int(v) for v in re.findall(r"ccdm_abi_version\(\) == (\d+)", doc)]
+    assert v_hdr == _lib.ABI_VERSION and v_doc and all(v == v_hdr for v in v_doc)
+
+
+def test_vit_qkv_row_permutation_matches_the_attention_kernels_order():
+    """The encoder packs a ViT block's qkv rows [which][head][d] (Attention.forward: reshape(B, N, 3, heads, d)) into the
+    attention kernel's per-head order [head][which][d] (QKVAttentionLegacy, unet.py:343-360): row r of the packed weight is
+    row perm[r] of the original."""
+    D, heads, hd = 384, 6, 64
+    perm = torch.arange(3 * D).reshape(3, heads, hd).permute(1, 0, 2).reshape(-1)
+    for h in (0, 3, 5):
+        for which in (0, 1, 2):
+            for d in (0, 17, 63):
+                assert int(perm[h * 3 * hd + which * hd + d]) == which * D + h * hd + d
+    assert sorted(perm.tolist()) == list(range(3 * D))
