@@ -409,6 +409,30 @@ def measure_workload(D, wl, precision, steps, warmup, batch=None, one_image=Fals
         h2d = x_host.numel() * 4 + image_host.numel() * 4 + (feat_host.numel() * 4 if feat_host is not None else 0)
         rec["e2e"] = {"value": world * B / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": world * B * H * W,
                       "ms_per_step": ms_e2e, "api": "DenoisingModel.forward(x one-hot fp32, image[, features]) from pinned host tensors; labels read back"}
+    if e2e and wl["fce"] and not one_image:
+        # the same call sequence a DINO-conditioned evaluator makes (eval_cdm.py:154-174): predict_feature_condition(image) on
+        # the device, then the chain -- the feature condition never crosses the host boundary
+        from ccdm_b200.models.condition_encoder import DinoViT
+        from ccdm_b200.synthetic import fill_synthetic_
+        enc = DinoViT(wl["fce"]["model"], False, wl["fce"]["conditioning"], stride=wl["fce"]["output_stride"])
+        fill_synthetic_(enc.extractor.model, 0)
+        enc = enc.to(dev).eval()
+
+        def chain_from_image():
+            img = image_host.to(dev, non_blocking=True)
+            out = m(x_host.to(dev, non_blocking=True), img, enc(img))["diffusion_out"]
+            lab = out.argmax(dim=1).to(torch.uint8)
+            if world > 1:
+                D.dist.all_gather_into_tensor(gathered, lab)
+                return gathered.cpu()
+            return lab.cpu()
+
+        chain_from_image()
+        ms_img = D.timed(chain_from_image, 1)[0]
+        rec["e2e_from_image"] = {"value": world * B / (ms_img / 1e3), "unit": "samples/s", "ms_per_step": ms_img,
+                                 "h2d_bytes_per_step": x_host.numel() * 4 + image_host.numel() * 4, "d2h_bytes_per_step": world * B * H * W,
+                                 "api": "DinoViT.forward(image) + DenoisingModel.forward(x, image, features): the condition encoder inside the timed region"}
+        del enc
     chain_bytes = (wl["elements"] * prog.esize + 3 * K * H * W * 4) * B * T
     peaks = measured_peaks()
     roof_chain = chain_bytes / (ms_step * 1e-3) / 1e9
