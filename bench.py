@@ -643,6 +643,8 @@ def run_gpu_arm(args):
         }
         if rec.get("condition_encoder"):
             line["condition_encoder"] = rec["condition_encoder"]
+        if rec.get("e2e_from_image"):
+            line["e2e_from_image"] = rec["e2e_from_image"]
     D.close()
     if line is not None:
         print(json.dumps(line), flush=True)
