@@ -88,7 +88,7 @@ struct AtP {
 // adjacent), both products are three fp16 MMAs (hi*lo + lo*hi + hi*hi), the softmax is the same fp32 arithmetic, and P
 // is split into hi + lo before the P V product -- fp32-grade attention on the tensor cores.
 template <int NK, bool X3, int D = 32>
-__global__ void __launch_bounds__(AT_QT, D > 32 ? (X3 ? 1 : 2) : (X3 ? 2 : 3)) attention_tc_kernel(const AtP p) {  // (fp16x2: 80 KB of shared memory per CTA -- two per SM anyway)
+__global__ void __launch_bounds__(AT_QT, D > 32 ? (X3 ? 1 : 2) : 3) attention_tc_kernel(const AtP p) {  // (head_dim 32: 72 KB of shared memory per CTA in fp16x2, three per SM; 168 registers, 16 bytes spilled)
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int X = X3 ? 2 : 1;
     constexpr int AT_D = D, AT_PLANES = D / 8;
@@ -97,11 +97,13 @@ __global__ void __launch_bounds__(AT_QT, D > 32 ? (X3 ? 1 : 2) : (X3 ? 2 : 3)) a
     constexpr uint32_t P_BYTES = X * (NK / 8) * AT_QT * 16;
     uint8_t *sQ = smem;
     uint8_t *sK = sQ + Q_BYTES;        // [2][KV_BYTES]
-    uint8_t *sV = sK + 2 * KV_BYTES;   // [2][KV_BYTES]
-    uint8_t *sP = sV + 2 * KV_BYTES;   // [NK/8 planes][128 rows][16 B]
+    uint8_t *sV = sK + 2 * KV_BYTES;   // [KV_BYTES]: ONE buffer -- V(t) is needed only after the softmax of tile t, so it is fetched
+                                       // at the top of iteration t (when P V(t-1) has completed) and its latency hides behind the
+                                       // softmax; the 8 KB saved make a third CTA fit an SM at head_dim 32 in fp16x2
+    uint8_t *sP = sV + KV_BYTES;       // [NK/8 planes][128 rows][16 B]
     uint64_t *bars = reinterpret_cast<uint64_t *>(sP + P_BYTES);
-    uint64_t *kv_full = bars, *s_done = bars + 2, *o_done = bars + 3;
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 4);
+    uint64_t *kv_full = bars, *s_done = bars + 2, *o_done = bars + 3, *v_full = bars + 4;  // kv_full: K tiles (and Q with the first)
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 5);
     constexpr uint32_t TMEM_COLS = NK + D <= 64 ? 64 : (NK + D <= 128 ? 128 : 256);
 
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -121,10 +123,11 @@ __global__ void __launch_bounds__(AT_QT, D > 32 ? (X3 ? 1 : 2) : (X3 ? 2 : 3)) a
         mbar_init(kv_full + 1, 1);
         mbar_init(s_done, 1);
         mbar_init(o_done, 1);
+        mbar_init(v_full, 1);
         fence_barrier_init();
     }
     // rows of a partial tile that no copy overwrites must hold finite values (0 * NaN would poison P V)
-    for (uint32_t i = tid * 16; i < Q_BYTES + 4 * KV_BYTES; i += AT_QT * 16) *reinterpret_cast<uint4 *>(smem + i) = make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t i = tid * 16; i < Q_BYTES + 3 * KV_BYTES; i += AT_QT * 16) *reinterpret_cast<uint4 *>(smem + i) = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -142,17 +145,21 @@ __global__ void __launch_bounds__(AT_QT, D > 32 ? (X3 ? 1 : 2) : (X3 ? 2 : 3)) a
         for (int d0 = 0; d0 < AT_D; d0 += 32) tmem_st32(tmem_o + trow + uint32_t(d0), src + d0);
     };
 
-    auto load_kv = [&](int t, int buf, uint32_t extra_bytes) {  // thread 0
+    auto load_k = [&](int t, int buf, uint32_t extra_bytes) {  // thread 0
         const int k0 = t * NK, nk = min(NK, T - k0);
-        mbar_expect_tx(kv_full + buf, uint32_t(2 * X * AT_PLANES * nk * 16) + extra_bytes);
+        mbar_expect_tx(kv_full + buf, uint32_t(X * AT_PLANES * nk * 16) + extra_bytes);
 #pragma unroll
-        for (int g = 0; g < X * AT_PLANES; ++g) {
-            bulk_g2s(sK + buf * KV_BYTES + g * NK * 16, plane_ptr(1, g) + size_t(k0) * 8, uint32_t(nk * 16), kv_full + buf);
-            bulk_g2s(sV + buf * KV_BYTES + g * NK * 16, plane_ptr(2, g) + size_t(k0) * 8, uint32_t(nk * 16), kv_full + buf);
-        }
+        for (int g = 0; g < X * AT_PLANES; ++g) bulk_g2s(sK + buf * KV_BYTES + g * NK * 16, plane_ptr(1, g) + size_t(k0) * 8, uint32_t(nk * 16), kv_full + buf);
+    };
+    auto load_v = [&](int t) {  // thread 0; the single V buffer must be free: P V(t-1) has completed
+        const int k0 = t * NK, nk = min(NK, T - k0);
+        mbar_expect_tx(v_full, uint32_t(X * AT_PLANES * nk * 16));
+#pragma unroll
+        for (int g = 0; g < X * AT_PLANES; ++g) bulk_g2s(sV + g * NK * 16, plane_ptr(2, g) + size_t(k0) * 8, uint32_t(nk * 16), v_full);
     };
     if (tid == 0) {
-        load_kv(0, 0, uint32_t(X * AT_PLANES * nq * 16));
+        load_k(0, 0, uint32_t(X * AT_PLANES * nq * 16));
+        load_v(0);
 #pragma unroll
         for (int g = 0; g < X * AT_PLANES; ++g) bulk_g2s(sQ + g * AT_QT * 16, plane_ptr(0, g) + size_t(q0) * 8, uint32_t(nq * 16), kv_full + 0);
     }
@@ -204,7 +211,7 @@ __global__ void __launch_bounds__(AT_QT, D > 32 ? (X3 ? 1 : 2) : (X3 ? 2 : 3)) a
         umma_commit(s_done);
     };
     if (tid == 0) {
-        if (n_tiles > 1) load_kv(1, 1, 0u);
+        if (n_tiles > 1) load_k(1, 1, 0u);
         issue_s(0);
     }
 
@@ -213,7 +220,10 @@ __global__ void __launch_bounds__(AT_QT, D > 32 ? (X3 ? 1 : 2) : (X3 ? 2 : 3)) a
         const int nk = min(NK, T - t * NK);
         mbar_wait(s_done, uint32_t(t) & 1u);  // S(t) is complete -- and with it every MMA issued before it, P V(t-1) included
         tc_fence_after();
-        if (tid == 0 && t >= 1 && t + 1 < n_tiles) load_kv(t + 1, buf ^ 1, 0u);  // that buffer's readers (S, P V of tile t-1) have completed
+        if (tid == 0 && t >= 1) {
+            load_v(t);                                      // P V(t-1), the buffer's last reader, has completed
+            if (t + 1 < n_tiles) load_k(t + 1, buf ^ 1, 0u);  // likewise S(t-1), the last reader of that K buffer
+        }
         const bool flushed = X3 && t > 0 && (t % FLUSH) == 0;  // (uniform) O is quiescent here: P V(t-1) has completed, P V(t) is not issued yet
         if (flushed) {
             float ot[AT_D];
@@ -300,8 +310,9 @@ __global__ void __launch_bounds__(AT_QT, D > 32 ? (X3 ? 1 : 2) : (X3 ? 2 : 3)) a
         tc_fence_before();
         __syncthreads();  // P (and a rescaled O) complete and visible to the tensor core; every thread is done reading S
         if (tid == 0) {
+            mbar_wait(v_full, uint32_t(t) & 1u);
             tc_fence_after();
-            const uint32_t v_lo = (smem_u32(sV + buf * KV_BYTES) >> 4) | (8u << 16);  // LBO = 128 B between groups of 8 keys
+            const uint32_t v_lo = (smem_u32(sV) >> 4) | (8u << 16);  // LBO = 128 B between groups of 8 keys
 #pragma unroll
             for (int j = 0; j < NK / 16; ++j)
                 mma(tmem_o, p_lo + uint32_t(j * 2 * X * AT_QT), desc_hi, uint32_t(AT_QT), v_lo + uint32_t(j * 16), v_hi, uint32_t(NK), p.idesc_pv,
@@ -349,7 +360,7 @@ __global__ void __launch_bounds__(AT_QT, D > 32 ? (X3 ? 1 : 2) : (X3 ? 2 : 3)) a
 template <int NK, bool X3, int D = 32>
 int launch_nk(const AtP &p, int grid, cudaStream_t s) {
     constexpr int AT_PLANES = D / 8;
-    constexpr size_t smem = (X3 ? 2 : 1) * (AT_PLANES * AT_QT * 16 + 4 * AT_PLANES * NK * 16 + (NK / 8) * AT_QT * 16) + 64;
+    constexpr size_t smem = (X3 ? 2 : 1) * (AT_PLANES * AT_QT * 16 + 3 * AT_PLANES * NK * 16 + (NK / 8) * AT_QT * 16) + 64;
     static bool attr_done = false;
     if (!attr_done) {
         CCDM_CUDA(cudaFuncSetAttribute(attention_tc_kernel<NK, X3, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -389,7 +400,7 @@ int launch_attention_tc(const ccdm_op &op, cudaStream_t s) {
     const int grid = op.B * op.heads * p.q_tiles;
     if (!p.qkv || !p.out || T <= 0 || grid <= 0) CCDM_FAIL(-2, "attention_tc: missing tensors");
     if (AT_D == 64) return x3 ? launch_nk<64, true, 64>(p, grid, s) : launch_nk<64, false, 64>(p, grid, s);  // one CTA per SM (128 / 72 KB)
-    if (x3) return launch_nk<64, true>(p, grid, s);  // 80 KB of shared memory per CTA at NK = 64: two CTAs per SM
+    if (x3) return launch_nk<64, true>(p, grid, s);  // 72 KB of shared memory per CTA at NK = 64: three CTAs per SM
     return NK == 64 ? launch_nk<64, false>(p, grid, s) : launch_nk<128, false>(p, grid, s);
 }
 
