@@ -26,9 +26,12 @@ VARIANTS = {
 VARIANTS.update({
     "size512_mult": (64, (0.5, 1, 1, 2, 2, 4, 4), [32, 16, 8], 1, 128, 128, 2, 1),  # seven levels, 2x2 maps at the bottom
     "cs_vitb_768": (32, (1, 1, 2, 2, 4, 4), [32, 16, 8], 3, 64, 128, 20, 2),         # a 768-channel feature condition (dino_vitb8)
+    # base_channels 64 with the DINO concat: 128 + 384 channels, groups of 16 -- no GroupNorm group straddles the boundary, so the
+    # per-step half of the folded block takes no feature channels at all
+    "cs_base64_dino": (64, (1, 1, 2, 2), [8], 3, 64, 128, 20, 2),
 })
 EXTRA = {"head_dim_64": dict(num_head_channels=64)}
-FCE = {"cs_vitb_768": dict(DINO, model="dino_vitb8", channels=768)}
+FCE = {"cs_vitb_768": dict(DINO, model="dino_vitb8", channels=768), "cs_base64_dino": dict(DINO)}
 ONLY = {}
 
 
